@@ -1,0 +1,245 @@
+/*
+ * kgat_b200.h  --  C ABI of libkgat_b200.so: the sm_100a CUDA kernels behind the KGAT hot path.
+ *
+ * The reference (Konippi/problem-recommender-system-using-kgat-in-codeforces) is pure Python on top
+ * of PyTorch ATen; it has no FFI of its own.  The drop-in boundary is therefore the Python class
+ * surface `src.model.KGAT.model.{KGAT, KGATArgs, KGATMode}` (reference src/model/KGAT/model.py:13-431)
+ * and this header is what that surface binds underneath: one entry point per ATen call chain it
+ * replaces.  Every entry point cites the reference lines whose arithmetic it implements.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked "host";
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - no allocation and no global state inside: the caller owns every buffer, incl. workspaces
+ *     (sizes from the matching *_workspace_bytes function);
+ *   - return 0 on success, a negative KGAT_ERR_* code otherwise (kgat_error_string explains);
+ *   - fp32 values, int32 indices inside the graph containers, int64 ids at the model boundary
+ *     (`ids64` arguments), row-major dense matrices with an explicit leading dimension where useful.
+ *   - all kernels are asynchronous on `stream` except the functions documented as synchronous.
+ */
+#ifndef KGAT_B200_H_
+#define KGAT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGAT_OK 0
+#define KGAT_ERR_INVALID_ARGUMENT (-1)
+#define KGAT_ERR_CUDA (-2)
+#define KGAT_ERR_UNSUPPORTED (-3)
+#define KGAT_ERR_WORKSPACE (-4)
+
+#define KGAT_ABI_VERSION 1
+#define KGAT_MAX_LAYERS 8   /* embedding table + up to 7 propagation layers */
+#define KGAT_MAX_TENSORS 24 /* tensors per multi-tensor Adam launch */
+
+/* ------------------------------------------------------------------------------------------- */
+/* misc                                                                                        */
+/* ------------------------------------------------------------------------------------------- */
+int kgat_abi_version(void);
+const char* kgat_error_string(int code);
+/* last CUDA error string seen by this library on the calling thread ("" if none) */
+const char* kgat_last_cuda_error(void);
+/* device properties the host side sizes grids with (synchronous, host out-pointers) */
+int kgat_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes);
+
+/* ------------------------------------------------------------------------------------------- */
+/* graph containers: replaces torch.sparse COO coalescing (reference model.py:359-364, the      */
+/* implicit coalesce inside torch.sparse.softmax) and scipy's coo->csr (preprocess.py:629)      */
+/* ------------------------------------------------------------------------------------------- */
+
+/* Group n 64-bit keys (arbitrary order, duplicates allowed).  Stable: entries with equal keys keep
+ * their input order inside the group.  Outputs:
+ *   order[n]        sorted position -> input entry index
+ *   group_of[n]     input entry index -> group id (dense rank of its key, ascending key order)
+ *   group_ptr[g+1]  group id -> first sorted position (group_ptr[n_groups] = n)
+ *   unique_keys[g]  ascending unique keys
+ *   *n_groups_host  number of groups (host pointer)
+ * SYNCHRONOUS (returns after the stream has drained; n_groups is needed on the host). */
+int64_t kgat_group_by_key_workspace_bytes(int64_t n);
+int kgat_group_by_key(const uint64_t* keys, int64_t n, int key_bits, void* workspace, int64_t workspace_bytes,
+                      int32_t* order, int32_t* group_of, int32_t* group_ptr, uint64_t* unique_keys,
+                      int64_t* n_groups_host, void* stream);
+
+/* Decode ascending unique keys  key = major * n_minor + minor  into a compressed pointer array over
+ * `n_major` majors and the minor index of every key (CSR: major=row, minor=col; CSC: swapped). */
+int kgat_decode_sorted_keys(const uint64_t* unique_keys, int64_t n_keys, int64_t n_major, int64_t n_minor,
+                            int32_t* major_ptr /* n_major+1 */, int32_t* minor_idx /* n_keys */, void* stream);
+
+/* out[g] = sum over sorted positions p in [group_ptr[g], group_ptr[g+1]) of in[order[p]], summed in
+ * that order (deterministic duplicate merge: what COO coalescing does, model.py:364). */
+int kgat_segment_sum_f32(const float* in, const int32_t* order, const int32_t* group_ptr, int64_t n_groups, float* out,
+                         void* stream);
+
+/* out[i] = in[index[i]]  (permute CSR values into CSC order after each attention refresh) */
+int kgat_gather_f32(const float* in, const int32_t* index, int64_t n, float* out, void* stream);
+/* out[i] = (int32) in[i] with range check against [0, bound): returns KGAT_ERR_INVALID_ARGUMENT
+ * through *bad_count_dev (device int32, incremented per offending element) */
+int kgat_ids64_to_i32(const int64_t* in, int64_t n, int64_t bound, int32_t* out, int32_t* bad_count_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* K1: attentive SpMM  Y = A * X (+ Z)    reference aggregator.py:54 and its autograd transpose  */
+/* ------------------------------------------------------------------------------------------- */
+/* A in CSR (row_ptr unused: the task list carries the ranges); X: n_cols x d (leading dim ldx),
+ * Y: n_rows x d (ldy); optional addend Z (ldz) or NULL.  d must be a multiple of 4, <= 256.
+ * tasks: n_tasks x {row, begin, end, partial_slot}; a row longer than the plan's chunk is split into
+ * several tasks with partial_slot >= 0 whose sums go to `partials` (n_partials x d floats) and are
+ * reduced in chunk order for heavy_rows[h] = {row, first_partial_slot, n_chunks, 0} (deterministic,
+ * no atomics).  The plan is host logic (graph.py: spmm_plan). */
+int kgat_spmm_csr(const int32_t* tasks, int64_t n_tasks, const int32_t* heavy_rows, int64_t n_heavy,
+                  const int32_t* col_idx, const float* vals, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                  const float* Z, int64_t ldz, int32_t d, float* partials, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* K2/K3: bi-interaction aggregator   reference aggregator.py:57-65                              */
+/* ------------------------------------------------------------------------------------------- */
+/* out = normalize( dropout( lrelu((E+S) W1^T + b1) + lrelu((E*S) W2^T + b2) ) ), row-wise L2, eps 1e-12.
+ * W1, W2: d_out x d_in row-major (nn.Linear.weight).  Dropout: p in [0,1); keep decisions come from
+ * keep_bits (packed, (d_out+31)/32 words per row, bit=1 keeps) when non-NULL, else from the Philox
+ * counter RNG (seed, offset) when p > 0; seed_dev (nullable device u64, e.g. the optimiser's step
+ * counter) is mixed into the seed so a replayed CUDA graph draws a fresh mask every step.  Saved for backward: inv_norm[n] (1/max(||x||,eps); negative
+ * when the eps clamp was active) and flags[n x d_out] (bit0: z1 > 0, bit1: z2 > 0, bit2: kept). */
+int kgat_biagg_forward(const float* E, const float* S, int64_t n, int32_t d_in, int32_t d_out, const float* W1,
+                       const float* b1, const float* W2, const float* b2, float dropout_p, uint64_t seed,
+                       uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits, float* out, int64_t ld_out,
+                       float* inv_norm, uint8_t* flags, void* stream);
+
+/* Backward of the above.  g_out: n x d_out (ld_gout).  Produces g_S and g_E_direct (n x d_in) and
+ * per-CTA partial parameter gradients in `partials` (n_ctas x (2*d_out*d_in + 2*d_out) floats,
+ * n_ctas from kgat_biagg_backward_ctas), which kgat_biagg_reduce_param_grads sums in a fixed order
+ * into gW1, gb1, gW2, gb2 (accumulate = 0 overwrites, 1 adds). */
+int kgat_biagg_backward_ctas(int64_t n, int32_t d_in, int32_t d_out);
+int kgat_biagg_backward(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm,
+                        const uint8_t* flags, const float* E, const float* S, int64_t n, int32_t d_in, int32_t d_out,
+                        const float* W1, const float* W2, float dropout_p, float* g_S, float* g_E, float* partials,
+                        int32_t n_ctas, void* stream);
+int kgat_biagg_reduce_param_grads(const float* partials, int32_t n_ctas, int32_t d_in, int32_t d_out, float* gW1,
+                                  float* gb1, float* gW2, float* gb2, int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* K4: BPR loss over the layer tables      reference model.py:189-202, 142-163                   */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_tables;
+    int32_t dims[KGAT_MAX_LAYERS];
+    const float* tables[KGAT_MAX_LAYERS]; /* table l: n_nodes x dims[l] */
+    int64_t lds[KGAT_MAX_LAYERS];
+} kgat_tables_t;
+
+typedef struct {
+    int32_t n_tables;
+    int32_t dims[KGAT_MAX_LAYERS];
+    float* tables[KGAT_MAX_LAYERS];
+    int64_t lds[KGAT_MAX_LAYERS];
+} kgat_grad_tables_t;
+
+/* loss[0] = -mean(logsigmoid(pos - neg)) + reg * (mean|u|^2/2 + mean|p|^2/2 + mean|n|^2/2);
+ * margin: scratch of 2*batch floats: [pos_b - neg_b (saved for the backward)][per-sample l2 term].
+ * ids are used as given (no user offset). */
+int kgat_bpr_forward(const kgat_tables_t* tables, const int64_t* users, const int64_t* pos, const int64_t* neg,
+                     int32_t batch, float reg, float* loss, float* margin, void* stream);
+/* Scatter-adds d loss / d table rows into grad tables (atomicAdd; tables[l] may be NULL to skip a
+ * layer).  g_loss: device scalar (upstream gradient). */
+int kgat_bpr_backward(const kgat_tables_t* tables, const kgat_grad_tables_t* grads, const int64_t* users,
+                      const int64_t* pos, const int64_t* neg, int32_t batch, float reg, const float* margin,
+                      const float* g_loss, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* K5: TransR loss                           reference model.py:204-261                          */
+/* ------------------------------------------------------------------------------------------- */
+/* emb: n_nodes x d; rel_emb: n_rel x k; W: n_rel x d x k (row-vector convention x = e W_r).
+ * loss[0] = -mean(logsigmoid(neg - pos)) + reg * (4 l2 means).  No W_r materialisation. */
+int kgat_transr_forward(const float* emb, const float* rel_emb, const float* W, int32_t d, int32_t k,
+                        const int64_t* heads, const int64_t* rels, const int64_t* pos_tails, const int64_t* neg_tails,
+                        int32_t batch, float reg, float* loss, float* margin, void* stream);
+/* Accumulates (atomicAdd) into g_emb (n_nodes x d), g_rel_emb (n_rel x k), g_W (n_rel x d x k);
+ * the caller zeroes them. */
+int kgat_transr_backward(const float* emb, const float* rel_emb, const float* W, int32_t d, int32_t k,
+                         const int64_t* heads, const int64_t* rels, const int64_t* pos_tails,
+                         const int64_t* neg_tails, int32_t batch, float reg, const float* margin, const float* g_loss,
+                         float* g_emb, float* g_rel_emb, float* g_W, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* K6-K8: attention refresh                  reference model.py:263-366,                         */
+/*                                           multi_head_attention.py:35-58                       */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const float* Wv; /* d x d  _value_weight.weight (out x in) */
+    const float* bv;
+    const float* Wo; /* d x d  _output.weight */
+    const float* bo;
+    const float* ln_gamma;
+    const float* ln_beta;
+    float ln_eps;
+    int32_t n_heads;
+} kgat_mha_t;
+
+/* Per unique (tail, relation) pair: x = e_t W_r, v = Wv x + bv.  If v_out != NULL stores v (n_pairs x d).
+ * If score_out != NULL also o = Wo v + bo, LayerNorm, score = sum tanh  (the eval-mode edge score
+ * before the degree weight: the reference's query/key path cancels). d = k = 64. */
+int kgat_att_pair_scores(const float* emb, const float* W, int32_t d, const int32_t* pair_tail,
+                         const int32_t* pair_rel, int64_t n_pairs, const kgat_mha_t* mha, float* v_out,
+                         float* score_out, void* stream);
+/* Train-mode (attention dropout live): per edge, per-head keep decision from head_bits
+ * (one byte per edge, bit h keeps head h) when non-NULL else from Philox(seed, offset + edge);
+ * kept heads are scaled by 1/(1-p).  score[e] = sum tanh(LN(Wo (mask * v[pair_of_edge[e]]) + bo)). */
+int kgat_att_edge_scores_dropout(const float* pair_v, const int32_t* pair_of_edge, int64_t n_edges, int32_t d,
+                                 const kgat_mha_t* mha, float dropout_p, const uint8_t* head_bits, uint64_t seed,
+                                 uint64_t offset, const uint64_t* seed_dev, float* score_out, void* stream);
+/* Row softmax over CSR slots with duplicate merge.  Edges are given in slot-sorted order: slot s owns
+ * sorted edges [slot_ptr[s], slot_ptr[s+1]).  Edge score = (pair_score ? pair_score[pair_of_edge[p]] :
+ * edge_score[p]) * edge_weight[p].  vals[s] = softmax over the row of sum of its edges' scores. */
+int kgat_att_row_softmax(const int32_t* row_ptr, int64_t n_rows, const int32_t* slot_ptr, const float* pair_score,
+                         const int32_t* pair_of_edge, const float* edge_score, const float* edge_weight, float* vals,
+                         void* stream);
+/* edge_weight[p] = mult / (log1p(deg_h) + log1p(deg_t))     reference model.py:309-314 */
+int kgat_att_edge_weights(const int32_t* deg_head, const int32_t* deg_tail, const float* mult, int64_t n_edges,
+                          float* edge_weight, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* K9/K10: predict                           reference model.py:388-391, metrics_calculator.py   */
+/* ------------------------------------------------------------------------------------------- */
+/* out[b, :] = concat_l tables[l][ids[b], :]   (b < n_ids; out: n_ids x sum(dims), ld_out) */
+int kgat_gather_concat(const kgat_tables_t* tables, const int64_t* ids64, int64_t n_ids, float* out, int64_t ld_out,
+                       void* stream);
+/* C (m x n) = A (m x k) * B^T (n x k), fp32 CUDA cores with fp32 accumulation */
+int kgat_sgemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int32_t m,
+                  int32_t n, int32_t k, void* stream);
+/* In-place mask: scores[b, items of user b] = -inf  (CSR-like mask_ptr / mask_items, int32) */
+int kgat_mask_scores(float* scores, int64_t ld, int32_t m, int32_t n, const int32_t* mask_ptr,
+                     const int32_t* mask_items, void* stream);
+/* Top-K per row, descending, exact ties broken lowest column first (CPU torch.sort order).
+ * k <= 128.  idx_out: m x k int32, val_out (optional): m x k. */
+int kgat_topk_rows(const float* scores, int64_t ld, int32_t m, int32_t n, int32_t k, int32_t* idx_out,
+                   float* val_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* K11: Adam                                 reference model.py:393-419 (torch.optim.Adam)       */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_tensors;
+    float* param[KGAT_MAX_TENSORS];
+    const float* grad[KGAT_MAX_TENSORS];
+    float* exp_avg[KGAT_MAX_TENSORS];
+    float* exp_avg_sq[KGAT_MAX_TENSORS];
+    int64_t numel[KGAT_MAX_TENSORS];
+} kgat_adam_tensors_t;
+/* One torch.optim.Adam step (no weight decay, no amsgrad) over all listed tensors in one launch,
+ * split in two so a captured CUDA graph replays correctly: kgat_adam_advance increments the device
+ * step counter and writes the step-dependent scalars {1-b1, b2, 1-b2, lr/bc1, 1/sqrt(bc2), eps} to
+ * hyper_dev (6 floats, bias corrections in double); kgat_adam_apply streams over the tensors. */
+int kgat_adam_advance(int64_t* step_dev, double lr, double beta1, double beta2, double eps, float* hyper_dev, void* stream);
+/* same scalars from a host-known 1-based step (the torch.optim.Optimizer path keeps step on the host) */
+int kgat_adam_set_hyper(int64_t step, double lr, double beta1, double beta2, double eps, float* hyper_dev, void* stream);
+int kgat_adam_apply(const kgat_adam_tensors_t* t, const float* hyper_dev, void* stream);
+
+/* utility: fill / axpy used by the host glue so no torch kernel sits on the hot path */
+int kgat_fill_f32(float* p, int64_t n, float value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGAT_B200_H_ */

@@ -1,0 +1,190 @@
+// K1: attentive SpMM  Y = A * X (+ Z) over the CSR attentive matrix.
+// Replaces torch.matmul(sparse_coo, dense) (reference aggregator.py:54) and, run on the transposed
+// container, its autograd backward A^T * g.
+//
+// HBM/L2-bound gather: one warp per task (a whole short row, or a <=chunk slice of a long row).
+// A feature row of D floats is fetched by D/4 lanes with one 128-bit read-only load each, so a warp
+// covers 32/(D/4) edges per step and keeps several steps in flight (4 independent 128-bit loads per
+// lane).  (col, val) of 32 consecutive edges are read coalesced once and broadcast by shuffle.
+// Long rows are split by the host-side plan into chunks whose partial sums are reduced in a fixed
+// order by a second tiny kernel: deterministic, no atomics.
+#include "common.cuh"
+
+namespace kgat {
+namespace {
+
+__device__ __forceinline__ int ld_stream_i32(const int32_t* p) {
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_stream_f32(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+template <int D, int U>
+__global__ void __launch_bounds__(128) spmm_task_kernel(const int4* __restrict__ tasks, int64_t n_tasks,
+                                                        const int32_t* __restrict__ col_idx, const float* __restrict__ vals,
+                                                        const float* __restrict__ X, int64_t ldx, float* __restrict__ Y,
+                                                        int64_t ldy, const float* __restrict__ Z, int64_t ldz,
+                                                        float* __restrict__ partials) {
+    constexpr int LPE = D / 4;        // lanes per edge
+    constexpr int EPW = 32 / LPE;     // edges per warp step
+    constexpr int EPI = EPW * U;      // edges per unrolled iteration (divides 32)
+    static_assert(32 % EPI == 0, "unroll must divide the 32-edge batch");
+    const int lane = threadIdx.x & 31;
+    const int64_t task_id = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (task_id >= n_tasks) return;
+    const int4 t = __ldg(tasks + task_id);  // {row, begin, end, partial_slot}
+    const int sub = lane % LPE;
+    const int slot = lane / LPE;
+    const float* xbase = X + sub * 4;
+
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = t.y; base < t.z; base += 32) {
+        const int k = base + lane;
+        int c = -1;
+        float v = 0.f;
+        if (k < t.z) {
+            c = ld_stream_i32(col_idx + k);
+            v = ld_stream_f32(vals + k);
+        }
+        const int cnt = min(32, t.z - base);
+        for (int j = 0; j < cnt; j += EPI) {
+            float4 x[U];
+            float w[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = j + u * EPW + slot;
+                const int cc = __shfl_sync(kFull, c, e);
+                w[u] = __shfl_sync(kFull, v, e);
+                x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cc >= 0) x[u] = ldg4(xbase + (int64_t)cc * ldx);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) fma4(acc, w[u], x[u]);
+        }
+    }
+#pragma unroll
+    for (int o = LPE; o < 32; o <<= 1) {
+        acc.x += __shfl_xor_sync(kFull, acc.x, o);
+        acc.y += __shfl_xor_sync(kFull, acc.y, o);
+        acc.z += __shfl_xor_sync(kFull, acc.z, o);
+        acc.w += __shfl_xor_sync(kFull, acc.w, o);
+    }
+    if (slot == 0) {
+        if (t.w < 0) {
+            if (Z != nullptr) {
+                const float4 z = ld_stream4(Z + (int64_t)t.x * ldz + sub * 4);
+                acc.x += z.x; acc.y += z.y; acc.z += z.z; acc.w += z.w;
+            }
+            *reinterpret_cast<float4*>(Y + (int64_t)t.x * ldy + sub * 4) = acc;
+        } else {
+            *reinterpret_cast<float4*>(partials + (int64_t)t.w * D + sub * 4) = acc;
+        }
+    }
+}
+
+// any d % 4 == 0, d <= 256: a whole warp per edge, up to two float4 per lane
+__global__ void __launch_bounds__(128) spmm_task_kernel_generic(const int4* __restrict__ tasks, int64_t n_tasks,
+                                                                const int32_t* __restrict__ col_idx,
+                                                                const float* __restrict__ vals, const float* __restrict__ X,
+                                                                int64_t ldx, float* __restrict__ Y, int64_t ldy,
+                                                                const float* __restrict__ Z, int64_t ldz,
+                                                                float* __restrict__ partials, int d) {
+    const int lane = threadIdx.x & 31;
+    const int64_t task_id = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (task_id >= n_tasks) return;
+    const int4 t = __ldg(tasks + task_id);
+    const bool has0 = lane * 4 < d, has1 = (lane + 32) * 4 < d;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    for (int base = t.y; base < t.z; base += 32) {
+        const int k = base + lane;
+        int c = 0;
+        float v = 0.f;
+        if (k < t.z) {
+            c = col_idx[k];
+            v = vals[k];
+        }
+        const int cnt = min(32, t.z - base);
+        for (int j = 0; j < cnt; ++j) {
+            const int cc = __shfl_sync(kFull, c, j);
+            const float w = __shfl_sync(kFull, v, j);
+            const float* xr = X + (int64_t)cc * ldx;
+            if (has0) fma4(a0, w, ldg4(xr + lane * 4));
+            if (has1) fma4(a1, w, ldg4(xr + (lane + 32) * 4));
+        }
+    }
+    float* dst;
+    int64_t zoff = -1;
+    if (t.w < 0) {
+        dst = Y + (int64_t)t.x * ldy;
+        if (Z != nullptr) zoff = (int64_t)t.x * ldz;
+    } else {
+        dst = partials + (int64_t)t.w * d;
+    }
+    if (has0) {
+        if (zoff >= 0) { const float4 z = ldg4(Z + zoff + lane * 4); a0.x += z.x; a0.y += z.y; a0.z += z.z; a0.w += z.w; }
+        *reinterpret_cast<float4*>(dst + lane * 4) = a0;
+    }
+    if (has1) {
+        if (zoff >= 0) { const float4 z = ldg4(Z + zoff + (lane + 32) * 4); a1.x += z.x; a1.y += z.y; a1.z += z.z; a1.w += z.w; }
+        *reinterpret_cast<float4*>(dst + (lane + 32) * 4) = a1;
+    }
+}
+
+// heavy rows: sum the chunk partials in chunk order (one warp per heavy row)
+__global__ void __launch_bounds__(128) spmm_heavy_reduce_kernel(const int4* __restrict__ heavy, int64_t n_heavy,
+                                                                const float* __restrict__ partials, float* __restrict__ Y,
+                                                                int64_t ldy, const float* __restrict__ Z, int64_t ldz, int d) {
+    const int lane = threadIdx.x & 31;
+    const int64_t h = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (h >= n_heavy) return;
+    const int4 r = __ldg(heavy + h);  // {row, first_slot, n_chunks, 0}
+    for (int f = lane * 4; f < d; f += 128) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < r.z; ++c) {
+            const float4 p = ld_stream4(partials + (int64_t)(r.y + c) * d + f);
+            a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+        }
+        if (Z != nullptr) {
+            const float4 z = ld_stream4(Z + (int64_t)r.x * ldz + f);
+            a.x += z.x; a.y += z.y; a.z += z.z; a.w += z.w;
+        }
+        *reinterpret_cast<float4*>(Y + (int64_t)r.x * ldy + f) = a;
+    }
+}
+
+}  // namespace
+}  // namespace kgat
+
+using namespace kgat;
+
+extern "C" int kgat_spmm_csr(const int32_t* tasks, int64_t n_tasks, const int32_t* heavy_rows, int64_t n_heavy,
+                             const int32_t* col_idx, const float* vals, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                             const float* Z, int64_t ldz, int32_t d, float* partials, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_tasks < 0 || n_heavy < 0 || d <= 0 || (d & 3) || d > 256) return KGAT_ERR_INVALID_ARGUMENT;
+    if ((ldx & 3) || (ldy & 3) || (Z && (ldz & 3))) return KGAT_ERR_INVALID_ARGUMENT;
+    if (n_heavy > 0 && partials == nullptr) return KGAT_ERR_INVALID_ARGUMENT;
+    if (n_tasks == 0) return KGAT_OK;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((n_tasks * 32 + threads - 1) / threads);
+    const int4* t4 = reinterpret_cast<const int4*>(tasks);
+    switch (d) {
+        case 16: spmm_task_kernel<16, 2><<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials); break;
+        case 32: spmm_task_kernel<32, 4><<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials); break;
+        case 64: spmm_task_kernel<64, 4><<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials); break;
+        case 128: spmm_task_kernel<128, 4><<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials); break;
+        default:
+            spmm_task_kernel_generic<<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, d);
+    }
+    if (n_heavy > 0) {
+        const unsigned hb = (unsigned)((n_heavy * 32 + threads - 1) / threads);
+        spmm_heavy_reduce_kernel<<<hb, threads, 0, stream>>>(reinterpret_cast<const int4*>(heavy_rows), n_heavy, partials, Y, ldy, Z,
+                                                             ldz, d);
+    }
+    return check_launch();
+}

@@ -1,0 +1,179 @@
+"""Autograd glue: the hand-written forward/backward kernels wrapped as ``torch.autograd.Function``s
+so that the reference's driver code (``loss.backward()``, ``main.py:312, 341``) keeps working.
+
+* ``CFLossFunction``      TRAIN_CF: 3-layer attentive propagation + BPR loss (model.py:165-202)
+* ``KGLossFunction``      TRAIN_KG: TransR loss (model.py:204-261)
+* ``PropagateFunction``   propagation alone, differentiable w.r.t. dense output gradients
+                          (used by PREDICT when autograd is enabled and by ``Aggregator.forward``)
+
+No dense N x 176 concat is materialised: layer outputs stay in their own row-major buffers and the
+BPR kernels gather from the four tables directly (K3 of SURVEY.md section 2b).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+
+from . import ops
+from .graph import AttentiveGraph
+
+f32 = torch.float32
+
+
+@dataclass
+class DropoutSpec:
+    """Message-dropout configuration of one forward pass (aggregator.py:62)."""
+
+    ps: list[float]  # per layer; 0 disables (eval mode)
+    seed: int = 0
+    keep_bits: list | None = None  # optional injected masks, one int32 [N, ceil(d_out/32)] per layer
+    seed_dev: torch.Tensor | None = None  # optional device u64/i64 mixed into the seed (graph replay)
+
+
+@dataclass
+class PropState:
+    tables: list  # [E0, E1, ..., EL]
+    side: list = field(default_factory=list)  # S_l = A @ E_{l-1}
+    inv_norm: list = field(default_factory=list)
+    flags: list = field(default_factory=list)
+    ps: list = field(default_factory=list)
+
+
+def propagate_forward(graph: AttentiveGraph, e0: torch.Tensor, layers, drop: DropoutSpec, save: bool = True) -> PropState:
+    """E_{l} = Agg_l(E_{l-1}, A) for all layers (model.py:124-140, aggregator.py:37-65)."""
+    n = e0.shape[0]
+    dev = e0.device
+    st = PropState(tables=[e0])
+    for l, (w1, b1, w2, b2) in enumerate(layers):
+        x = st.tables[-1]
+        d_out = w1.shape[0]
+        side = graph.matmul(x)
+        out = torch.empty(n, d_out, dtype=f32, device=dev)
+        inv = torch.empty(n, dtype=f32, device=dev) if save else None
+        flags = torch.empty(n, d_out, dtype=torch.uint8, device=dev) if save else None
+        p = float(drop.ps[l])
+        ops.biagg_forward(
+            x, side, w1, b1, w2, b2, out, inv, flags, dropout_p=p, seed=drop.seed, offset=(l + 1) << 40,
+            keep_bits=None if drop.keep_bits is None else drop.keep_bits[l], seed_dev=drop.seed_dev,
+        )
+        st.tables.append(out)
+        if save:
+            st.side.append(side)
+            st.inv_norm.append(inv)
+            st.flags.append(flags)
+            st.ps.append(p)
+    return st
+
+
+def propagate_backward(graph: AttentiveGraph, st: PropState, layers, g_last: torch.Tensor, inject):
+    """Backward through all layers.  ``g_last`` is the dense gradient w.r.t. the last table;
+    ``inject(l, G)`` adds the loss's direct gradient for table ``l`` into the dense buffer ``G``
+    (called for l = L-1 .. 0, after the propagated part of G has been written).
+    Returns (g_E0, [(gW1, gb1, gW2, gb2) per layer])."""
+    n = st.tables[0].shape[0]
+    dev = g_last.device
+    g = g_last
+    param_grads = [None] * len(layers)
+    for l in range(len(layers), 0, -1):
+        w1, b1, w2, b2 = layers[l - 1]
+        x = st.tables[l - 1]
+        d_in, d_out = x.shape[1], w1.shape[0]
+        n_ctas = ops.biagg_backward_ctas(n, d_in, d_out)
+        partials = torch.empty(n_ctas * (2 * d_in * d_out + 2 * d_out), dtype=f32, device=dev)
+        g_s = torch.empty(n, d_in, dtype=f32, device=dev)
+        g_e = torch.empty(n, d_in, dtype=f32, device=dev)
+        ops.biagg_backward(g, st.tables[l], st.inv_norm[l - 1], st.flags[l - 1], x, st.side[l - 1], w1, w2, st.ps[l - 1],
+                           g_s, g_e, partials, n_ctas)
+        gw1, gb1, gw2, gb2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2)
+        ops.biagg_reduce_param_grads(partials, n_ctas, d_in, d_out, gw1, gb1, gw2, gb2)
+        param_grads[l - 1] = (gw1, gb1, gw2, gb2)
+        g_prev = graph.matmul_t(g_s, addend=g_e)  # dL/dE_{l-1} = g_E(direct) + A^T g_S
+        inject(l - 1, g_prev)
+        g = g_prev
+    return g, param_grads
+
+
+def _flat_layers(flat):
+    return [tuple(flat[i : i + 4]) for i in range(0, len(flat), 4)]
+
+
+class CFLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, graph, users, pos, neg, reg, drop, e0, *flat):
+        layers = _flat_layers([t.detach() for t in flat])
+        e0d = e0.detach()
+        st = propagate_forward(graph, e0d, layers, drop, save=True)
+        b = users.numel()
+        loss = torch.empty(1, dtype=f32, device=e0.device)
+        scratch = torch.empty(2 * b, dtype=f32, device=e0.device)
+        ops.bpr_forward(st.tables, users, pos, neg, reg, loss, scratch)
+        ctx.graph, ctx.st, ctx.layers = graph, st, layers
+        ctx.ids = (users, pos, neg)
+        ctx.reg, ctx.scratch = reg, scratch
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        st, layers, graph = ctx.st, ctx.layers, ctx.graph
+        users, pos, neg = ctx.ids
+        g_loss = g_loss.reshape(1).to(f32).contiguous()
+        n_tab = len(st.tables)
+
+        def inject(l, buf):
+            grads = [None] * n_tab
+            grads[l] = buf
+            ops.bpr_backward(st.tables, grads, users, pos, neg, ctx.reg, ctx.scratch, g_loss)
+
+        g_last = torch.zeros_like(st.tables[-1])
+        inject(n_tab - 1, g_last)
+        g_e0, pgrads = propagate_backward(graph, st, layers, g_last, inject)
+        flat = [t for grp in pgrads for t in grp]
+        return (None, None, None, None, None, None, g_e0, *flat)
+
+
+class PropagateFunction(torch.autograd.Function):
+    """(E1, ..., EL) = propagate(E0); backward takes dense output gradients."""
+
+    @staticmethod
+    def forward(ctx, graph, drop, e0, *flat):
+        layers = _flat_layers([t.detach() for t in flat])
+        st = propagate_forward(graph, e0.detach(), layers, drop, save=True)
+        ctx.graph, ctx.st, ctx.layers = graph, st, layers
+        return tuple(st.tables[1:])
+
+    @staticmethod
+    def backward(ctx, *g_tables):
+        st, layers, graph = ctx.st, ctx.layers, ctx.graph
+        g_last = g_tables[-1]
+        g_last = torch.zeros_like(st.tables[-1]) if g_last is None else g_last.contiguous()
+
+        def inject(l, buf):
+            if l >= 1 and g_tables[l - 1] is not None:
+                buf.add_(g_tables[l - 1])
+
+        g_e0, pgrads = propagate_backward(graph, st, layers, g_last, inject)
+        flat = [t for grp in pgrads for t in grp]
+        return (None, None, g_e0, *flat)
+
+
+class KGLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, heads, rels, pos_t, neg_t, reg, emb, rel_emb, w):
+        embd, reld, wd = emb.detach(), rel_emb.detach(), w.detach()
+        b = heads.numel()
+        loss = torch.empty(1, dtype=f32, device=emb.device)
+        scratch = torch.empty(2 * b, dtype=f32, device=emb.device)
+        ops.transr_forward(embd, reld, wd, heads, rels, pos_t, neg_t, reg, loss, scratch)
+        ctx.saved = (embd, reld, wd, heads, rels, pos_t, neg_t, scratch)
+        ctx.reg = reg
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        embd, reld, wd, heads, rels, pos_t, neg_t, scratch = ctx.saved
+        g_loss = g_loss.reshape(1).to(f32).contiguous()
+        g_emb, g_rel, g_w = torch.zeros_like(embd), torch.zeros_like(reld), torch.zeros_like(wd)
+        ops.transr_backward(embd, reld, wd, heads, rels, pos_t, neg_t, ctx.reg, scratch, g_loss, g_emb, g_rel, g_w)
+        return (None, None, None, None, None, g_emb, g_rel, g_w)

@@ -1,0 +1,409 @@
+"""Thin tensor-level wrappers over the C ABI (one Python function per ``kgat_*`` entry point).
+
+PyTorch is used here for device memory and streams only: every wrapper validates its tensors
+(CUDA, dtype, contiguity), takes raw ``data_ptr()`` values and launches on torch's *current* CUDA
+stream so the kernels compose with torch's stream/graph machinery.  Nothing falls back to a torch
+op when the library or a GPU is missing -- the call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import AdamTensorsT, KgatLibraryError, MhaT, TablesT, check
+
+f32, i32, i64, u8 = torch.float32, torch.int32, torch.int64, torch.uint8
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: torch.Tensor | None, dtype=None, name: str = "tensor", row_strided: bool = False) -> int | None:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise KgatLibraryError(f"{name} must be a CUDA tensor (no CPU fallback in kgat_b200)")
+    if dtype is not None and t.dtype != dtype:
+        raise KgatLibraryError(f"{name} must be {dtype}, got {t.dtype}")
+    if row_strided:  # 2-D, unit inner stride, 16-byte aligned rows
+        if t.dim() != 2 or t.stride(1) != 1 or t.stride(0) % 4 or t.data_ptr() % 16:
+            raise KgatLibraryError(f"{name} must be 2-D with unit inner stride and 16-byte aligned rows")
+    elif not t.is_contiguous():
+        raise KgatLibraryError(f"{name} must be contiguous")
+    return t.data_ptr()
+
+
+def _tables(tensors, allow_none: bool = False) -> TablesT:
+    t = TablesT()
+    t.n_tables = len(tensors)
+    if len(tensors) > _lib.KGAT_MAX_LAYERS:
+        raise KgatLibraryError(f"at most {_lib.KGAT_MAX_LAYERS} layer tables are supported")
+    for i, x in enumerate(tensors):
+        if x is None:
+            if not allow_none:
+                raise KgatLibraryError("missing table")
+            t.dims[i], t.tables[i], t.lds[i] = 0, None, 0
+            continue
+        t.dims[i] = x.shape[1]
+        t.tables[i] = _ptr(x, f32, "table")
+        t.lds[i] = x.stride(0)
+    return t
+
+
+def device_info() -> dict:
+    lib = _lib.load()
+    sm, ma, mi, l2 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+    check(lib.kgat_device_info(C.byref(sm), C.byref(ma), C.byref(mi), C.byref(l2)), "device_info")
+    return {"sm_count": sm.value, "cc": (ma.value, mi.value), "l2_bytes": l2.value}
+
+
+# ----------------------------------------------------------------------------------------------
+# graph containers
+# ----------------------------------------------------------------------------------------------
+
+
+def group_by_key(keys: torch.Tensor, key_bits: int = 64):
+    """Stable grouping of int64 keys (treated as unsigned).  Returns
+    (order i32[n], group_of i32[n], group_ptr i32[g+1], unique_keys i64[g])."""
+    lib = _lib.load()
+    n = keys.numel()
+    dev = keys.device
+    ws_bytes = lib.kgat_group_by_key_workspace_bytes(n)
+    if ws_bytes < 0:
+        raise KgatLibraryError("group_by_key: too many keys")
+    ws = torch.empty(ws_bytes, dtype=u8, device=dev)
+    order = torch.empty(n, dtype=i32, device=dev)
+    group_of = torch.empty(n, dtype=i32, device=dev)
+    group_ptr = torch.empty(n + 1, dtype=i32, device=dev)
+    uniq = torch.empty(max(n, 1), dtype=i64, device=dev)
+    ng = C.c_int64(0)
+    check(
+        lib.kgat_group_by_key(
+            _ptr(keys, i64, "keys"), n, key_bits, ws.data_ptr(), ws_bytes, order.data_ptr(), group_of.data_ptr(),
+            group_ptr.data_ptr(), uniq.data_ptr(), C.byref(ng), _stream(),
+        ),
+        "group_by_key",
+    )
+    g = ng.value
+    return order, group_of, group_ptr[: g + 1].clone(), uniq[:g].clone()
+
+
+def decode_sorted_keys(unique_keys: torch.Tensor, n_major: int, n_minor: int):
+    lib = _lib.load()
+    n = unique_keys.numel()
+    dev = unique_keys.device
+    major_ptr = torch.empty(n_major + 1, dtype=i32, device=dev)
+    minor_idx = torch.empty(n, dtype=i32, device=dev)
+    check(
+        lib.kgat_decode_sorted_keys(_ptr(unique_keys, i64), n, n_major, n_minor, major_ptr.data_ptr(), minor_idx.data_ptr(), _stream()),
+        "decode_sorted_keys",
+    )
+    return major_ptr, minor_idx
+
+
+def segment_sum(values: torch.Tensor, order: torch.Tensor, group_ptr: torch.Tensor, out: torch.Tensor | None = None):
+    lib = _lib.load()
+    g = group_ptr.numel() - 1
+    if out is None:
+        out = torch.empty(g, dtype=f32, device=values.device)
+    check(lib.kgat_segment_sum_f32(_ptr(values, f32), _ptr(order, i32), _ptr(group_ptr, i32), g, _ptr(out, f32), _stream()), "segment_sum")
+    return out
+
+
+def gather_f32(src: torch.Tensor, index: torch.Tensor, out: torch.Tensor | None = None):
+    lib = _lib.load()
+    n = index.numel()
+    if out is None:
+        out = torch.empty(n, dtype=f32, device=src.device)
+    check(lib.kgat_gather_f32(_ptr(src, f32), _ptr(index, i32), n, _ptr(out, f32), _stream()), "gather_f32")
+    return out
+
+
+def fill_(t: torch.Tensor, value: float = 0.0):
+    lib = _lib.load()
+    check(lib.kgat_fill_f32(_ptr(t, f32), t.numel(), float(value), _stream()), "fill")
+    return t
+
+
+# ----------------------------------------------------------------------------------------------
+# K1 SpMM
+# ----------------------------------------------------------------------------------------------
+
+
+def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.Tensor | None = None, partials=None):
+    """out = A @ x (+ addend); ``plan`` is a graph.SpmmPlan."""
+    lib = _lib.load()
+    d = x.shape[1]
+    if plan.n_heavy > 0:
+        need = plan.n_partials * d
+        if partials is None or partials.numel() < need:
+            raise KgatLibraryError("spmm: partials scratch too small")
+    check(
+        lib.kgat_spmm_csr(
+            _ptr(plan.tasks, i32), plan.n_tasks, _ptr(plan.heavy, i32) if plan.n_heavy else None, plan.n_heavy,
+            _ptr(col_idx, i32), _ptr(vals, f32), _ptr(x, f32, "x", True), x.stride(0), _ptr(out, f32, "out", True), out.stride(0),
+            _ptr(addend, f32, "addend", True) if addend is not None else None, addend.stride(0) if addend is not None else 0, d,
+            _ptr(partials, f32) if partials is not None else None, _stream(),
+        ),
+        "spmm_csr",
+    )
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# K2/K3 bi-interaction aggregator
+# ----------------------------------------------------------------------------------------------
+
+
+def biagg_forward(E, S, W1, b1, W2, b2, out, inv_norm, flags, dropout_p=0.0, seed=0, offset=0, keep_bits=None, seed_dev=None):
+    lib = _lib.load()
+    n, d_in = E.shape
+    d_out = W1.shape[0]
+    check(
+        lib.kgat_biagg_forward(
+            _ptr(E, f32, "E"), _ptr(S, f32, "S"), n, d_in, d_out, _ptr(W1, f32), _ptr(b1, f32), _ptr(W2, f32), _ptr(b2, f32),
+            float(dropout_p), int(seed), int(offset), _ptr(seed_dev, i64) if seed_dev is not None else None,
+            _ptr(keep_bits, i32) if keep_bits is not None else None,
+            _ptr(out, f32, "out"), out.stride(0), _ptr(inv_norm, f32) if inv_norm is not None else None,
+            _ptr(flags, u8) if flags is not None else None, _stream(),
+        ),
+        f"biagg_forward({d_in}->{d_out})",
+    )
+    return out
+
+
+def biagg_backward_ctas(n: int, d_in: int, d_out: int) -> int:
+    return _lib.load().kgat_biagg_backward_ctas(n, d_in, d_out)
+
+
+def biagg_backward(g_out, out, inv_norm, flags, E, S, W1, W2, dropout_p, g_S, g_E, partials, n_ctas):
+    lib = _lib.load()
+    n, d_in = E.shape
+    d_out = W1.shape[0]
+    if partials.numel() < n_ctas * (2 * d_in * d_out + 2 * d_out):
+        raise KgatLibraryError("biagg_backward: partials scratch too small")
+    check(
+        lib.kgat_biagg_backward(
+            _ptr(g_out, f32, "g_out"), g_out.stride(0), _ptr(out, f32), out.stride(0), _ptr(inv_norm, f32), _ptr(flags, u8),
+            _ptr(E, f32), _ptr(S, f32), n, d_in, d_out, _ptr(W1, f32), _ptr(W2, f32), float(dropout_p), _ptr(g_S, f32),
+            _ptr(g_E, f32), _ptr(partials, f32), n_ctas, _stream(),
+        ),
+        f"biagg_backward({d_in}->{d_out})",
+    )
+
+
+def biagg_reduce_param_grads(partials, n_ctas, d_in, d_out, gW1, gb1, gW2, gb2, accumulate=False):
+    lib = _lib.load()
+    check(
+        lib.kgat_biagg_reduce_param_grads(
+            _ptr(partials, f32), n_ctas, d_in, d_out, _ptr(gW1, f32), _ptr(gb1, f32), _ptr(gW2, f32), _ptr(gb2, f32),
+            1 if accumulate else 0, _stream(),
+        ),
+        "biagg_reduce_param_grads",
+    )
+
+
+# ----------------------------------------------------------------------------------------------
+# K4 BPR, K5 TransR
+# ----------------------------------------------------------------------------------------------
+
+
+def bpr_forward(tables, users, pos, neg, reg, loss, scratch):
+    lib = _lib.load()
+    b = users.numel()
+    if scratch.numel() < 2 * b:
+        raise KgatLibraryError("bpr_forward: scratch needs 2*batch floats")
+    t = _tables(tables)
+    check(
+        lib.kgat_bpr_forward(C.byref(t), _ptr(users, i64, "users"), _ptr(pos, i64, "pos"), _ptr(neg, i64, "neg"), b, float(reg),
+                             _ptr(loss, f32), _ptr(scratch, f32), _stream()),
+        "bpr_forward",
+    )
+
+
+def bpr_backward(tables, grad_tables, users, pos, neg, reg, scratch, g_loss):
+    lib = _lib.load()
+    t = _tables(tables)
+    g = _tables(grad_tables, allow_none=True)
+    for i, x in enumerate(grad_tables):
+        if x is not None:
+            g.dims[i] = tables[i].shape[1]
+    check(
+        lib.kgat_bpr_backward(C.byref(t), C.byref(g), _ptr(users, i64), _ptr(pos, i64), _ptr(neg, i64), users.numel(), float(reg),
+                              _ptr(scratch, f32), _ptr(g_loss, f32), _stream()),
+        "bpr_backward",
+    )
+
+
+def transr_forward(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, loss, scratch):
+    lib = _lib.load()
+    b = heads.numel()
+    if scratch.numel() < 2 * b:
+        raise KgatLibraryError("transr_forward: scratch needs 2*batch floats")
+    check(
+        lib.kgat_transr_forward(_ptr(emb, f32), _ptr(rel_emb, f32), _ptr(W, f32), emb.shape[1], rel_emb.shape[1], _ptr(heads, i64),
+                                _ptr(rels, i64), _ptr(pos_t, i64), _ptr(neg_t, i64), b, float(reg), _ptr(loss, f32),
+                                _ptr(scratch, f32), _stream()),
+        f"transr_forward(d={emb.shape[1]}, k={rel_emb.shape[1]})",
+    )
+
+
+def transr_backward(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, scratch, g_loss, g_emb, g_rel, g_W):
+    lib = _lib.load()
+    check(
+        lib.kgat_transr_backward(_ptr(emb, f32), _ptr(rel_emb, f32), _ptr(W, f32), emb.shape[1], rel_emb.shape[1], _ptr(heads, i64),
+                                 _ptr(rels, i64), _ptr(pos_t, i64), _ptr(neg_t, i64), heads.numel(), float(reg), _ptr(scratch, f32),
+                                 _ptr(g_loss, f32), _ptr(g_emb, f32), _ptr(g_rel, f32), _ptr(g_W, f32), _stream()),
+        "transr_backward",
+    )
+
+
+# ----------------------------------------------------------------------------------------------
+# K6-K8 attention refresh
+# ----------------------------------------------------------------------------------------------
+
+
+def _mha(mha_params: dict, n_heads: int, eps: float):
+    m = MhaT()
+    keep = []
+    for field, key in (("Wv", "Wv"), ("bv", "bv"), ("Wo", "Wo"), ("bo", "bo"), ("ln_gamma", "gamma"), ("ln_beta", "beta")):
+        t = mha_params[key]
+        keep.append(t)
+        setattr(m, field, _ptr(t, f32, key))
+    m.ln_eps = eps
+    m.n_heads = n_heads
+    return m, keep
+
+
+def att_pair_scores(emb, W, pair_tail, pair_rel, mha_params, n_heads=8, eps=1e-5, want_v=False, want_score=True):
+    lib = _lib.load()
+    n_pairs = pair_tail.numel()
+    d = emb.shape[1]
+    m, _keep = _mha(mha_params, n_heads, eps)
+    v_out = torch.empty(n_pairs, d, dtype=f32, device=emb.device) if want_v else None
+    s_out = torch.empty(n_pairs, dtype=f32, device=emb.device) if want_score else None
+    check(
+        lib.kgat_att_pair_scores(_ptr(emb, f32), _ptr(W, f32), d, _ptr(pair_tail, i32), _ptr(pair_rel, i32), n_pairs, C.byref(m),
+                                 _ptr(v_out, f32) if want_v else None, _ptr(s_out, f32) if want_score else None, _stream()),
+        f"att_pair_scores(d={d})",
+    )
+    return v_out, s_out
+
+
+def att_edge_scores_dropout(pair_v, pair_of_edge, mha_params, dropout_p, head_bits=None, seed=0, offset=0, n_heads=8, eps=1e-5, seed_dev=None):
+    lib = _lib.load()
+    n_edges = pair_of_edge.numel()
+    d = pair_v.shape[1]
+    m, _keep = _mha(mha_params, n_heads, eps)
+    out = torch.empty(n_edges, dtype=f32, device=pair_v.device)
+    check(
+        lib.kgat_att_edge_scores_dropout(_ptr(pair_v, f32), _ptr(pair_of_edge, i32), n_edges, d, C.byref(m), float(dropout_p),
+                                         _ptr(head_bits, u8) if head_bits is not None else None, int(seed), int(offset),
+                                         _ptr(seed_dev, i64) if seed_dev is not None else None, _ptr(out, f32), _stream()),
+        "att_edge_scores_dropout",
+    )
+    return out
+
+
+def att_row_softmax(row_ptr, slot_ptr, edge_weight, vals_out, pair_score=None, pair_of_edge=None, edge_score=None):
+    lib = _lib.load()
+    check(
+        lib.kgat_att_row_softmax(_ptr(row_ptr, i32), row_ptr.numel() - 1, _ptr(slot_ptr, i32),
+                                 _ptr(pair_score, f32) if pair_score is not None else None,
+                                 _ptr(pair_of_edge, i32) if pair_of_edge is not None else None,
+                                 _ptr(edge_score, f32) if edge_score is not None else None, _ptr(edge_weight, f32),
+                                 _ptr(vals_out, f32), _stream()),
+        "att_row_softmax",
+    )
+    return vals_out
+
+
+def att_edge_weights(deg_head, deg_tail, mult=None):
+    lib = _lib.load()
+    n = deg_head.numel()
+    out = torch.empty(n, dtype=f32, device=deg_head.device)
+    check(lib.kgat_att_edge_weights(_ptr(deg_head, i32), _ptr(deg_tail, i32), _ptr(mult, f32) if mult is not None else None, n,
+                                    _ptr(out, f32), _stream()), "att_edge_weights")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# K9/K10 predict
+# ----------------------------------------------------------------------------------------------
+
+
+def gather_concat(tables, ids, out=None):
+    lib = _lib.load()
+    t = _tables(tables)
+    n = ids.numel()
+    width = sum(x.shape[1] for x in tables)
+    if out is None:
+        out = torch.empty(n, width, dtype=f32, device=tables[0].device)
+    check(lib.kgat_gather_concat(C.byref(t), _ptr(ids, i64, "ids"), n, _ptr(out, f32), out.stride(0), _stream()), "gather_concat")
+    return out
+
+
+def sgemm_nt(A, B, out=None):
+    lib = _lib.load()
+    m, k = A.shape
+    n = B.shape[0]
+    if out is None:
+        out = torch.empty(m, n, dtype=f32, device=A.device)
+    if A.stride(1) != 1 or B.stride(1) != 1 or out.stride(1) != 1:
+        raise KgatLibraryError("sgemm_nt: inner strides must be 1")
+    for t_ in (A, B, out):
+        if not t_.is_cuda or t_.dtype != f32:
+            raise KgatLibraryError("sgemm_nt: CUDA fp32 tensors required")
+    check(lib.kgat_sgemm_nt(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), out.data_ptr(), out.stride(0), m, n, k, _stream()), "sgemm_nt")
+    return out
+
+
+def mask_scores_(scores, mask_ptr, mask_items):
+    lib = _lib.load()
+    m, n = scores.shape
+    check(lib.kgat_mask_scores(_ptr(scores, f32), scores.stride(0), m, n, _ptr(mask_ptr, i32), _ptr(mask_items, i32), _stream()), "mask_scores")
+    return scores
+
+
+def topk_rows(scores, k: int, want_values: bool = False):
+    lib = _lib.load()
+    m, n = scores.shape
+    idx = torch.empty(m, k, dtype=i32, device=scores.device)
+    val = torch.empty(m, k, dtype=f32, device=scores.device) if want_values else None
+    check(lib.kgat_topk_rows(_ptr(scores, f32), scores.stride(0), m, n, k, idx.data_ptr(), val.data_ptr() if want_values else None, _stream()), "topk_rows")
+    return (idx, val) if want_values else idx
+
+
+# ----------------------------------------------------------------------------------------------
+# K11 Adam
+# ----------------------------------------------------------------------------------------------
+
+
+def adam_set_hyper(step: int, lr, beta1, beta2, eps, hyper: torch.Tensor):
+    lib = _lib.load()
+    check(lib.kgat_adam_set_hyper(int(step), float(lr), float(beta1), float(beta2), float(eps), _ptr(hyper, f32), _stream()), "adam_set_hyper")
+
+
+def adam_advance(step_dev: torch.Tensor, lr, beta1, beta2, eps, hyper: torch.Tensor):
+    lib = _lib.load()
+    check(lib.kgat_adam_advance(_ptr(step_dev, i64), float(lr), float(beta1), float(beta2), float(eps), _ptr(hyper, f32), _stream()), "adam_advance")
+
+
+def adam_apply(params, grads, exp_avgs, exp_avg_sqs, hyper: torch.Tensor):
+    lib = _lib.load()
+    n = len(params)
+    for start in range(0, n, _lib.KGAT_MAX_TENSORS):
+        t = AdamTensorsT()
+        chunk = range(start, min(n, start + _lib.KGAT_MAX_TENSORS))
+        t.n_tensors = len(chunk)
+        for j, i in enumerate(chunk):
+            t.param[j] = _ptr(params[i], f32, "param")
+            t.grad[j] = _ptr(grads[i], f32, "grad")
+            t.exp_avg[j] = _ptr(exp_avgs[i], f32, "exp_avg")
+            t.exp_avg_sq[j] = _ptr(exp_avg_sqs[i], f32, "exp_avg_sq")
+            t.numel[j] = params[i].numel()
+        check(lib.kgat_adam_apply(C.byref(t), _ptr(hyper, f32), _stream()), "adam_apply")
