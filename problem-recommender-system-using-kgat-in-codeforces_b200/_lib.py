@@ -100,6 +100,35 @@ SIGNATURES: dict[str, tuple] = {
 
 _lib = None
 
+# kernels launched per entry-point call (our own kernels only; feeds bench.py's "gpu_launches")
+KERNELS_PER_CALL = {
+    "kgat_group_by_key": 6, "kgat_decode_sorted_keys": 1, "kgat_segment_sum_f32": 1, "kgat_gather_f32": 1,
+    "kgat_ids64_to_i32": 1, "kgat_spmm_csr": 1, "kgat_biagg_forward": 1, "kgat_biagg_backward": 1,
+    "kgat_biagg_reduce_param_grads": 1, "kgat_bpr_forward": 2, "kgat_bpr_backward": 1, "kgat_transr_forward": 2,
+    "kgat_transr_backward": 1, "kgat_att_pair_scores": 1, "kgat_att_edge_scores_dropout": 1, "kgat_att_row_softmax": 1,
+    "kgat_att_edge_weights": 1, "kgat_gather_concat": 1, "kgat_sgemm_nt": 1, "kgat_mask_scores": 1, "kgat_topk_rows": 1,
+    "kgat_adam_advance": 1, "kgat_adam_set_hyper": 1, "kgat_adam_apply": 1, "kgat_fill_f32": 1,
+}
+
+
+class LaunchCounter:
+    """Counts kernel launches issued through the C ABI (reset / read by bench.py)."""
+
+    count = 0
+
+
+def _counted(fn, name: str):
+    k = KERNELS_PER_CALL.get(name, 0)
+    if k == 0:
+        return fn
+    spmm = name == "kgat_spmm_csr"
+
+    def call(*args):
+        LaunchCounter.count += k + (1 if spmm and args[3] > 0 else 0)  # + heavy-row reduce kernel
+        return fn(*args)
+
+    return call
+
 
 def load() -> C.CDLL:
     """Load the shared library once and attach the signatures.  Raises if it is not built."""
@@ -119,6 +148,7 @@ def load() -> C.CDLL:
             raise KgatLibraryError(f"{LIB_PATH} does not export {name}") from e
         fn.restype = res
         fn.argtypes = args
+        setattr(lib, name, _counted(fn, name))
     if lib.kgat_abi_version() != ABI_VERSION:
         raise KgatLibraryError(f"ABI mismatch: library {lib.kgat_abi_version()} != binding {ABI_VERSION}")
     _lib = lib

@@ -22,6 +22,47 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class KernelTimer:
+    """Optional per-kernel CUDA-event timing on the launching stream (bench.py roofline leg).
+    ``with ops.KernelTimer() as t: ...`` then ``t.summary()`` -> {name: (launches, total_ms)}."""
+
+    active: "KernelTimer | None" = None
+
+    def __init__(self):
+        self.events: dict[str, list] = {}
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        KernelTimer.active = None
+
+    def summary(self) -> dict:
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.events.items()}
+
+
+def _timed(name_fn):
+    def deco(fn):
+        def wrapper(*args, **kwargs):
+            t = KernelTimer.active
+            if t is None:
+                return fn(*args, **kwargs)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = fn(*args, **kwargs)
+            b.record()
+            t.events.setdefault(name_fn(*args, **kwargs) if callable(name_fn) else name_fn, []).append((a, b))
+            return out
+
+        wrapper.__name__ = fn.__name__
+        wrapper.__doc__ = fn.__doc__
+        return wrapper
+
+    return deco
+
+
 def _ptr(t: torch.Tensor | None, dtype=None, name: str = "tensor", row_strided: bool = False) -> int | None:
     if t is None:
         return None
@@ -134,6 +175,7 @@ def fill_(t: torch.Tensor, value: float = 0.0):
 # ----------------------------------------------------------------------------------------------
 
 
+@_timed(lambda plan, col_idx, vals, x, out, addend=None, *a, **k: f"spmm{'T' if addend is not None else ''}_d{x.shape[1]}")
 def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.Tensor | None = None, partials=None):
     """out = A @ x (+ addend); ``plan`` is a graph.SpmmPlan."""
     lib = _lib.load()
@@ -159,6 +201,7 @@ def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.
 # ----------------------------------------------------------------------------------------------
 
 
+@_timed(lambda E, S, W1, *a, **k: f"biagg_fwd_{E.shape[1]}x{W1.shape[0]}")
 def biagg_forward(E, S, W1, b1, W2, b2, out, inv_norm, flags, dropout_p=0.0, seed=0, offset=0, keep_bits=None, seed_dev=None):
     lib = _lib.load()
     n, d_in = E.shape
@@ -180,6 +223,7 @@ def biagg_backward_ctas(n: int, d_in: int, d_out: int) -> int:
     return _lib.load().kgat_biagg_backward_ctas(n, d_in, d_out)
 
 
+@_timed(lambda g_out, out, inv_norm, flags, E, S, W1, *a, **k: f"biagg_bwd_{E.shape[1]}x{W1.shape[0]}")
 def biagg_backward(g_out, out, inv_norm, flags, E, S, W1, W2, dropout_p, g_S, g_E, partials, n_ctas):
     lib = _lib.load()
     n, d_in = E.shape
@@ -196,6 +240,7 @@ def biagg_backward(g_out, out, inv_norm, flags, E, S, W1, W2, dropout_p, g_S, g_
     )
 
 
+@_timed("biagg_reduce")
 def biagg_reduce_param_grads(partials, n_ctas, d_in, d_out, gW1, gb1, gW2, gb2, accumulate=False):
     lib = _lib.load()
     check(
@@ -212,6 +257,7 @@ def biagg_reduce_param_grads(partials, n_ctas, d_in, d_out, gW1, gb1, gW2, gb2, 
 # ----------------------------------------------------------------------------------------------
 
 
+@_timed("bpr_fwd")
 def bpr_forward(tables, users, pos, neg, reg, loss, scratch):
     lib = _lib.load()
     b = users.numel()
@@ -225,6 +271,7 @@ def bpr_forward(tables, users, pos, neg, reg, loss, scratch):
     )
 
 
+@_timed("bpr_bwd")
 def bpr_backward(tables, grad_tables, users, pos, neg, reg, scratch, g_loss):
     lib = _lib.load()
     t = _tables(tables)
@@ -239,6 +286,7 @@ def bpr_backward(tables, grad_tables, users, pos, neg, reg, scratch, g_loss):
     )
 
 
+@_timed("transr_fwd")
 def transr_forward(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, loss, scratch):
     lib = _lib.load()
     b = heads.numel()
@@ -252,6 +300,7 @@ def transr_forward(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, loss, scratc
     )
 
 
+@_timed("transr_bwd")
 def transr_backward(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, scratch, g_loss, g_emb, g_rel, g_W):
     lib = _lib.load()
     check(
@@ -393,6 +442,7 @@ def adam_advance(step_dev: torch.Tensor, lr, beta1, beta2, eps, hyper: torch.Ten
     check(lib.kgat_adam_advance(_ptr(step_dev, i64), float(lr), float(beta1), float(beta2), float(eps), _ptr(hyper, f32), _stream()), "adam_advance")
 
 
+@_timed("adam_apply")
 def adam_apply(params, grads, exp_avgs, exp_avg_sqs, hyper: torch.Tensor):
     lib = _lib.load()
     n = len(params)
