@@ -236,7 +236,13 @@ int kgat_adam_advance(int64_t* step_dev, double lr, double beta1, double beta2, 
 int kgat_adam_set_hyper(int64_t step, double lr, double beta1, double beta2, double eps, float* hyper_dev, void* stream);
 int kgat_adam_apply(const kgat_adam_tensors_t* t, const float* hyper_dev, void* stream);
 
-/* utility: fill / axpy used by the host glue so no torch kernel sits on the hot path */
+/* dst[0..elems) = src[(counter_dev[0] % n_batches) * elems + ...]: selects the current step's pre-sampled
+ * id batch from a device-resident epoch array (counter = an optimiser step counter) so that a captured
+ * CUDA graph of a training step replays through the whole epoch without host work. */
+int kgat_select_batch_i64(const int64_t* src, int64_t n_batches, int64_t elems, const int64_t* counter_dev, int64_t* dst,
+                          void* stream);
+
+/* utility: fill used by the host glue so no torch kernel sits on the hot path */
 int kgat_fill_f32(float* p, int64_t n, float value, void* stream);
 
 #ifdef __cplusplus

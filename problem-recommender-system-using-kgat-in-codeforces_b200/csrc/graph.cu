@@ -88,6 +88,16 @@ __global__ void fill_kernel(float* p, int64_t n, float v) {
     for (; i < n; i += stride) p[i] = v;
 }
 
+// dst[0 .. elems) = src[(counter % n_batches) * elems ...]: picks the current step's pre-sampled batch
+// from a device-resident epoch array inside a captured CUDA graph (the counter is the optimiser's
+// device step counter, so a replayed graph walks through the epoch with no host work).
+__global__ void select_batch_kernel(const int64_t* __restrict__ src, int64_t n_batches, int64_t elems,
+                                    const int64_t* __restrict__ counter, int64_t* __restrict__ dst) {
+    const int64_t b = counter[0] % n_batches;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < elems; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[b * elems + i];
+}
+
 inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 inline unsigned blocks_for(int64_t n, int threads = 256) { return (unsigned)((n + threads - 1) / threads); }
 
@@ -203,6 +213,14 @@ int kgat_ids64_to_i32(const int64_t* in, int64_t n, int64_t bound, int32_t* out,
     if (n < 0 || bound <= 0 || bound > 0x7fffffff) return KGAT_ERR_INVALID_ARGUMENT;
     if (n == 0) return KGAT_OK;
     ids_to_i32_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(in, n, bound, out, bad_count_dev);
+    return check_launch();
+}
+
+int kgat_select_batch_i64(const int64_t* src, int64_t n_batches, int64_t elems, const int64_t* counter_dev, int64_t* dst,
+                          void* stream) {
+    if (n_batches <= 0 || elems <= 0 || !counter_dev) return KGAT_ERR_INVALID_ARGUMENT;
+    select_batch_kernel<<<(unsigned)((elems + 255) / 256 < 64 ? (elems + 255) / 256 : 64), 256, 0, (cudaStream_t)stream>>>(
+        src, n_batches, elems, counter_dev, dst);
     return check_launch();
 }
 

@@ -1,0 +1,235 @@
+"""CUDA-graph training engine: the same kernels as the autograd path, issued as one captured graph
+per training step (CF: 3-layer propagation fwd + BPR + hand-written backward + Adam; KG: TransR fwd +
+backward + Adam), so an epoch of ~15 k short steps is replayed without per-kernel launch overhead.
+
+The engine works on the *same* parameters and the *same* Adam state as ``model._cf_optimizer`` /
+``model._kg_optimizer`` (FusedAdam), so API steps and engine steps can be mixed.  Step-dependent
+scalars (Adam bias corrections, dropout stream, which pre-sampled batch to use) live in device
+memory and are advanced by tiny kernels inside the graph; nothing is baked in at capture time.
+
+Semantics are those of the reference epoch body (main.py:290-361); see ``trainer.run_epoch`` for the
+un-captured equivalent through the public model API (the two are tested to agree).
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .functions import DropoutSpec, propagate_backward, propagate_forward
+from .model import KGAT, KGATMode
+from .optim import FusedAdam
+from .trainer import CF_BATCH, KG_BATCH, EpochData
+
+f32 = torch.float32
+
+
+class _AdamSlot:
+    """Device-side view of one FusedAdam optimiser for a fixed parameter list."""
+
+    def __init__(self, opt: FusedAdam, params):
+        self.opt, self.params = opt, list(params)
+        dev = self.params[0].device
+        group = opt.param_groups[0]
+        self.lr, (self.b1, self.b2), self.eps = group["lr"], group["betas"], group["eps"]
+        steps = set()
+        for p in self.params:
+            st = opt.state[p]
+            if not st:
+                st["step"] = 0
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            steps.add(int(st["step"]))
+        if len(steps) != 1:
+            raise RuntimeError("TrainEngine needs all parameters of a phase to share one Adam step count")
+        self.step_dev = torch.full((1,), steps.pop(), dtype=torch.int64, device=dev)
+        self.hyper = torch.empty(8, dtype=f32, device=dev)
+        self.exp_avg = [opt.state[p]["exp_avg"] for p in self.params]
+        self.exp_avg_sq = [opt.state[p]["exp_avg_sq"] for p in self.params]
+
+    def apply(self, grads):
+        ops.adam_advance(self.step_dev, self.lr, self.b1, self.b2, self.eps, self.hyper)
+        ops.adam_apply([p.data for p in self.params], grads, self.exp_avg, self.exp_avg_sq, self.hyper)
+
+    def sync_host(self, n_steps: int):
+        for p in self.params:
+            self.opt.state[p]["step"] += n_steps
+            torch.autograd.graph.increment_version(p)
+
+    def snapshot(self):
+        return ([p.detach().clone() for p in self.params], [t.clone() for t in self.exp_avg], [t.clone() for t in self.exp_avg_sq], self.step_dev.clone())
+
+    def restore(self, snap):
+        ps, ms, vs, step = snap
+        for dst, src in zip([p.data for p in self.params] + self.exp_avg + self.exp_avg_sq, ps + ms + vs):
+            dst.copy_(src)
+        self.step_dev.copy_(step)
+
+
+class TrainEngine:
+    def __init__(self, model: KGAT, cf_batch: int = CF_BATCH, kg_batch: int = KG_BATCH, use_graphs: bool = True):
+        if not hasattr(model, "_cf_optimizer"):
+            raise RuntimeError("call model.build_optimizer(...) before creating a TrainEngine")
+        self.model = model
+        self.dev = model._device()
+        self.use_graphs = use_graphs
+        self.cf_batch, self.kg_batch = cf_batch, kg_batch
+        emb = model._user_entity_embedding.weight
+        self.cf_params = [emb] + [t for grp in model._layers() for t in grp]
+        self.kg_params = [emb, model._relation_embedding.weight, model._trans_matrix]
+        self.cf_adam = _AdamSlot(model._cf_optimizer, self.cf_params)
+        self.kg_adam = _AdamSlot(model._kg_optimizer, self.kg_params)
+        dev = self.dev
+        self.cf_ids = torch.zeros(3, cf_batch, dtype=torch.int64, device=dev)
+        self.kg_ids = torch.zeros(4, kg_batch, dtype=torch.int64, device=dev)
+        self.cf_loss = torch.zeros(1, dtype=f32, device=dev)
+        self.kg_loss = torch.zeros(1, dtype=f32, device=dev)
+        self.cf_loss_sum = torch.zeros(1, dtype=f32, device=dev)
+        self.kg_loss_sum = torch.zeros(1, dtype=f32, device=dev)
+        self.one = torch.ones(1, dtype=f32, device=dev)
+        self.cf_scratch = torch.empty(2 * cf_batch, dtype=f32, device=dev)
+        self.kg_scratch = torch.empty(2 * kg_batch, dtype=f32, device=dev)
+        self.kg_grads = [torch.zeros_like(p) for p in self.kg_params]
+        self._resident: EpochData | None = None
+        self._graphs: dict = {}
+        self._graph_token = None
+
+    # ------------------------------------------------------------------------------------------
+    # the two training steps, written out without autograd
+    # ------------------------------------------------------------------------------------------
+    def _cf_body(self, select: bool):
+        m = self.model
+        if select:
+            ops.select_batch(self._resident.cf, self.cf_adam.step_dev, self.cf_ids.view(-1))
+        u, p, n = self.cf_ids[0], self.cf_ids[1], self.cf_ids[2]
+        graph = m._graph()
+        layers = [tuple(t.detach() for t in grp) for grp in m._layers()]
+        drop = m._drop_spec()
+        if m.training and drop.keep_bits is None and any(q > 0 for q in drop.ps):
+            drop = DropoutSpec(ps=drop.ps, seed=drop.seed, seed_dev=self.cf_adam.step_dev)
+        st = propagate_forward(graph, m._user_entity_embedding.weight.detach(), layers, drop, save=True)
+        reg = float(m._regularization_params[0])
+        ops.bpr_forward(st.tables, u, p, n, reg, self.cf_loss, self.cf_scratch)
+        n_tab = len(st.tables)
+
+        def inject(l, buf):
+            grads = [None] * n_tab
+            grads[l] = buf
+            ops.bpr_backward(st.tables, grads, u, p, n, reg, self.cf_scratch, self.one)
+
+        g_last = torch.zeros_like(st.tables[-1])
+        inject(n_tab - 1, g_last)
+        g_e0, pgrads = propagate_backward(graph, st, layers, g_last, inject)
+        self.cf_adam.apply([g_e0] + [t for grp in pgrads for t in grp])
+        self.cf_loss_sum.add_(self.cf_loss)
+
+    def _kg_body(self, select: bool):
+        m = self.model
+        if select:
+            ops.select_batch(self._resident.kg, self.kg_adam.step_dev, self.kg_ids.view(-1))
+        h, r, pt, nt = self.kg_ids[0], self.kg_ids[1], self.kg_ids[2], self.kg_ids[3]
+        emb, rel, w = (p.detach() for p in self.kg_params)
+        reg = float(m._regularization_params[1])
+        ops.transr_forward(emb, rel, w, h, r, pt, nt, reg, self.kg_loss, self.kg_scratch)
+        for g in self.kg_grads:
+            ops.fill_(g, 0.0)
+        ops.transr_backward(emb, rel, w, h, r, pt, nt, reg, self.kg_scratch, self.one, *self.kg_grads)
+        self.kg_adam.apply(self.kg_grads)
+        self.kg_loss_sum.add_(self.kg_loss)
+
+    # ------------------------------------------------------------------------------------------
+    # capture / replay
+    # ------------------------------------------------------------------------------------------
+    def _token(self):
+        g = self.model._graph()
+        return (id(g), g.vals.data_ptr(), g.t_vals.data_ptr(), self.model.training, id(self._resident))
+
+    def _get(self, kind: str, select: bool):
+        """Returns a callable running one step (a captured graph replay when graphs are enabled)."""
+        body = self._cf_body if kind == "cf" else self._kg_body
+        if not self.use_graphs:
+            return lambda: body(select)
+        token = self._token()
+        if token != self._graph_token:
+            self._graphs.clear()
+            self._graph_token = token
+        key = (kind, select)
+        if key not in self._graphs:
+            adam = self.cf_adam if kind == "cf" else self.kg_adam
+            snap = adam.snapshot()
+            sums = (self.cf_loss_sum.clone(), self.kg_loss_sum.clone())
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body(select)  # eager warm-up (lazy kernel attributes, allocator pools); undone below
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            adam.restore(snap)
+            self.cf_loss_sum.copy_(sums[0])
+            self.kg_loss_sum.copy_(sums[1])
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body(select)
+            self._graphs[key] = g
+        return self._graphs[key].replay
+
+    # ------------------------------------------------------------------------------------------
+    # public
+    # ------------------------------------------------------------------------------------------
+    def bind_resident(self, data: EpochData):
+        """Keep an epoch of pre-sampled batches in HBM: cf [n_cf, 3, B], kg [n_kg, 4, B] int64."""
+        cf = torch.stack([t.to(self.dev) for t in data.cf], dim=1).contiguous()
+        kg = torch.stack([t.to(self.dev) for t in data.kg], dim=1).contiguous()
+        holder = EpochData(cf=cf, kg=kg, edges=tuple(t.to(self.dev) for t in data.edges))
+        self._resident = holder
+        return holder
+
+    def run_epoch(self, data: EpochData | None = None, read_loss_every_step: bool = False, n_cf: int | None = None, n_kg: int | None = None,
+                  refresh: bool = True):
+        """One reference epoch body.  ``data=None`` uses the batches bound with ``bind_resident``
+        (selected on the device by the optimiser step counter: step s uses batch s mod n); a host
+        ``EpochData`` (pinned tensors) is copied host->device step by step instead.
+        Returns (mean CF loss, mean KG loss, bytes host->device, bytes device->host)."""
+        m = self.model
+        m.train()
+        resident = data is None
+        src = self._resident if resident else data
+        if src is None:
+            raise RuntimeError("no resident epoch bound and no data given")
+        n_cf = int(src.cf.shape[0] if resident else src.n_cf) if n_cf is None else n_cf
+        n_kg = int(src.kg.shape[0] if resident else src.n_kg) if n_kg is None else n_kg
+        h2d = d2h = 0
+        self.cf_loss_sum.zero_()
+        self.kg_loss_sum.zero_()
+        cf_host = kg_host = 0.0
+        step = self._get("cf", resident) if n_cf else None
+        for i in range(n_cf):
+            if not resident:
+                for j in range(3):
+                    self.cf_ids[j].copy_(data.cf[j][i], non_blocking=True)
+                h2d += 3 * self.cf_batch * 8
+            step()
+            if read_loss_every_step:
+                cf_host += float(self.cf_loss.item())
+                d2h += 4
+        self.cf_adam.sync_host(n_cf)
+        step = self._get("kg", resident) if n_kg else None
+        for i in range(n_kg):
+            if not resident:
+                for j in range(4):
+                    self.kg_ids[j].copy_(data.kg[j][i], non_blocking=True)
+                h2d += 4 * self.kg_batch * 8
+            step()
+            if read_loss_every_step:
+                kg_host += float(self.kg_loss.item())
+                d2h += 4
+        self.kg_adam.sync_host(n_kg)
+        if refresh:
+            eh, er, et, ri = src.edges
+            if not eh.is_cuda:
+                h2d += eh.numel() * eh.element_size() + er.numel() * 8 + et.numel() * et.element_size() + ri.numel() * 8
+            m(eh, er, et, ri, mode=KGATMode.UPDATE_ATTENTION)
+        if not read_loss_every_step:
+            cf_host, kg_host = float(self.cf_loss_sum.item()), float(self.kg_loss_sum.item())
+            d2h += 8
+        return cf_host / max(n_cf, 1), kg_host / max(n_kg, 1), h2d, d2h

@@ -248,7 +248,7 @@ class KGAT(nn.Module):
         emb = self._user_entity_embedding.weight.detach()
         w = self._trans_matrix.detach()
         graph = idx.graph
-        vals = torch.empty(graph.nnz, dtype=torch.float32, device=emb.device)
+        vals = graph.vals  # refreshed in place: pointers captured by CUDA graphs / the COO view stay valid
         p = mha.dropout_p if self.training else 0.0
         if p == 0.0:
             _, score = ops.att_pair_scores(emb, w, idx.pair_tail, idx.pair_rel, params, mha.head_num, mha.ln_eps)
@@ -263,7 +263,7 @@ class KGAT(nn.Module):
                 seed = int(torch.randint(0, 2**62, (1,)).item())
             edge_score = ops.att_edge_scores_dropout(pair_v, idx.pair_of_edge, params, p, head_bits, seed, 0, mha.head_num, mha.ln_eps)
             ops.att_row_softmax(graph.row_ptr, idx.slot_ptr, idx.edge_weight, vals, edge_score=edge_score)
-        graph.set_values(vals)
+        graph.refresh_transposed_values()
         coo = graph.coo_tensor()
         self.attentive_matrix.data = coo
         self._graph_cache = graph

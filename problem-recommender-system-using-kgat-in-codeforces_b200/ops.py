@@ -164,6 +164,17 @@ def gather_f32(src: torch.Tensor, index: torch.Tensor, out: torch.Tensor | None 
     return out
 
 
+def select_batch(src: torch.Tensor, counter_dev: torch.Tensor, dst: torch.Tensor):
+    """dst (flat int64) = src[counter % n_batches] where src is [n_batches, ...] int64 on the device."""
+    lib = _lib.load()
+    n_batches = src.shape[0]
+    elems = src[0].numel()
+    if dst.numel() != elems:
+        raise KgatLibraryError("select_batch: dst size mismatch")
+    check(lib.kgat_select_batch_i64(_ptr(src, i64), n_batches, elems, _ptr(counter_dev, i64), _ptr(dst, i64), _stream()), "select_batch")
+    return dst
+
+
 def fill_(t: torch.Tensor, value: float = 0.0):
     lib = _lib.load()
     check(lib.kgat_fill_f32(_ptr(t, f32), t.numel(), float(value), _stream()), "fill")
