@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from .functions import DropoutSpec, propagate_backward, propagate_forward
 from .model import KGAT, KGATMode
 from .optim import FusedAdam
@@ -168,10 +168,18 @@ class TrainEngine:
             self.cf_loss_sum.copy_(sums[0])
             self.kg_loss_sum.copy_(sums[1])
             g = torch.cuda.CUDAGraph()
+            before = _lib.LaunchCounter.count
             with torch.cuda.graph(g):
                 body(select)
-            self._graphs[key] = g
-        return self._graphs[key].replay
+            kernels = _lib.LaunchCounter.count - before  # our kernels recorded in this graph
+            _lib.LaunchCounter.count = before
+
+            def replay(g=g, kernels=kernels):
+                _lib.LaunchCounter.count += kernels
+                g.replay()
+
+            self._graphs[key] = replay
+        return self._graphs[key]
 
     # ------------------------------------------------------------------------------------------
     # public
