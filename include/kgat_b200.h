@@ -83,15 +83,16 @@ int kgat_ids64_to_i32(const int64_t* in, int64_t n, int64_t bound, int32_t* out,
 /* ------------------------------------------------------------------------------------------- */
 /* K1: attentive SpMM  Y = A * X (+ Z)    reference aggregator.py:54 and its autograd transpose  */
 /* ------------------------------------------------------------------------------------------- */
-/* A in CSR (row_ptr unused: the task list carries the ranges); X: n_cols x d (leading dim ldx),
+/* A in CSR (row_ptr unused: the task list carries the ranges); X: n_cols x d (leading dim ldx; tables
+ * under 4 GiB are addressed with 32-bit byte offsets),
  * Y: n_rows x d (ldy); optional addend Z (ldz) or NULL.  d must be a multiple of 4, <= 256.
  * tasks: n_tasks x {row, begin, end, partial_slot}; a row longer than the plan's chunk is split into
  * several tasks with partial_slot >= 0 whose sums go to `partials` (n_partials x d floats) and are
  * reduced in chunk order for heavy_rows[h] = {row, first_partial_slot, n_chunks, 0} (deterministic,
  * no atomics).  The plan is host logic (graph.py: spmm_plan). */
 int kgat_spmm_csr(const int32_t* tasks, int64_t n_tasks, const int32_t* heavy_rows, int64_t n_heavy,
-                  const int32_t* col_idx, const float* vals, const float* X, int64_t ldx, float* Y, int64_t ldy,
-                  const float* Z, int64_t ldz, int32_t d, float* partials, void* stream);
+                  const int32_t* col_idx, const float* vals, const float* X, int64_t n_cols, int64_t ldx, float* Y,
+                  int64_t ldy, const float* Z, int64_t ldz, int32_t d, float* partials, void* stream);
 
 /* ------------------------------------------------------------------------------------------- */
 /* K2/K3: bi-interaction aggregator   reference aggregator.py:57-65                              */

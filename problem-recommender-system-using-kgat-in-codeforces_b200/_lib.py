@@ -75,7 +75,7 @@ SIGNATURES: dict[str, tuple] = {
     "kgat_segment_sum_f32": (_I32, [_P, _P, _P, _I64, _P, _P]),
     "kgat_gather_f32": (_I32, [_P, _P, _I64, _P, _P]),
     "kgat_ids64_to_i32": (_I32, [_P, _I64, _I64, _P, _P, _P]),
-    "kgat_spmm_csr": (_I32, [_P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P, _I64, _I32, _P, _P]),
+    "kgat_spmm_csr": (_I32, [_P, _I64, _P, _I64, _P, _P, _P, _I64, _I64, _P, _I64, _P, _I64, _I32, _P, _P]),
     "kgat_biagg_forward": (_I32, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _F, _U64, _U64, _P, _P, _P, _I64, _P, _P, _P]),
     "kgat_biagg_backward_ctas": (_I32, [_I64, _I32, _I32]),
     "kgat_biagg_backward": (_I32, [_P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _F, _P, _P, _P, _I32, _P]),

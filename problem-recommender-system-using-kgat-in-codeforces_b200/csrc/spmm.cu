@@ -24,7 +24,12 @@ __device__ __forceinline__ float ld_stream_f32(const float* p) {
     return r;
 }
 
-template <int D, int U>
+// One warp per task.  The (byte offset, weight) pairs of 32 consecutive edges are staged in a
+// per-warp slab of shared memory (one coalesced global read + one STS.64 per lane), so the hot loop
+// per edge group is: LDS.64 (broadcast), LDG.128 (gather of the neighbour row), 4 FFMA -- no
+// shuffles, no predicates (tail lanes carry weight 0 and a valid, already-cached address).
+// WIDE = false: the table is < 4 GiB so a 32-bit byte offset addresses it.
+template <int D, int U, bool WIDE>
 __global__ void __launch_bounds__(128) spmm_task_kernel(const int4* __restrict__ tasks, int64_t n_tasks,
                                                         const int32_t* __restrict__ col_idx, const float* __restrict__ vals,
                                                         const float* __restrict__ X, int64_t ldx, float* __restrict__ Y,
@@ -34,38 +39,52 @@ __global__ void __launch_bounds__(128) spmm_task_kernel(const int4* __restrict__
     constexpr int EPW = 32 / LPE;     // edges per warp step
     constexpr int EPI = EPW * U;      // edges per unrolled iteration (divides 32)
     static_assert(32 % EPI == 0, "unroll must divide the 32-edge batch");
+    __shared__ int2 ebuf[4][32];
     const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
     const int64_t task_id = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (task_id >= n_tasks) return;
     const int4 t = __ldg(tasks + task_id);  // {row, begin, end, partial_slot}
     const int sub = lane % LPE;
     const int slot = lane / LPE;
-    const float* xbase = X + sub * 4;
+    const char* xb = reinterpret_cast<const char*>(X) + sub * 16;
+    const uint32_t row_bytes32 = (uint32_t)(ldx * 4);
+    const int64_t row_bytes64 = ldx * 4;
+    int2* eb = ebuf[wib];
 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int base = t.y; base < t.z; base += 32) {
+    int base = t.y;
+    int c = 0;
+    float v = 0.f;
+    if (base < t.z) {
         const int k = base + lane;
-        int c = -1;
-        float v = 0.f;
-        if (k < t.z) {
-            c = ld_stream_i32(col_idx + k);
-            v = ld_stream_f32(vals + k);
-        }
+        c = ld_stream_i32(col_idx + min(k, t.z - 1));
+        v = k < t.z ? ld_stream_f32(vals + k) : 0.f;
+    }
+    while (base < t.z) {
+        eb[lane] = make_int2(WIDE ? c : (int)((uint32_t)c * row_bytes32), __float_as_int(v));
+        __syncwarp();
         const int cnt = min(32, t.z - base);
+        base += 32;
+        if (base < t.z) {  // prefetch the next 32 (col, val) pairs while this batch is gathered
+            const int k = base + lane;
+            c = ld_stream_i32(col_idx + min(k, t.z - 1));
+            v = k < t.z ? ld_stream_f32(vals + k) : 0.f;
+        }
         for (int j = 0; j < cnt; j += EPI) {
             float4 x[U];
             float w[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int e = j + u * EPW + slot;
-                const int cc = __shfl_sync(kFull, c, e);
-                w[u] = __shfl_sync(kFull, v, e);
-                x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (cc >= 0) x[u] = ldg4(xbase + (int64_t)cc * ldx);
+                const int2 ev = eb[j + u * EPW + slot];
+                w[u] = __int_as_float(ev.y);
+                const char* src = WIDE ? xb + (int64_t)ev.x * row_bytes64 : xb + (uint32_t)ev.x;
+                x[u] = __ldg(reinterpret_cast<const float4*>(src));
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) fma4(acc, w[u], x[u]);
         }
+        __syncwarp();
     }
 #pragma unroll
     for (int o = LPE; o < 32; o <<= 1) {
@@ -163,24 +182,32 @@ __global__ void __launch_bounds__(128) spmm_heavy_reduce_kernel(const int4* __re
 using namespace kgat;
 
 extern "C" int kgat_spmm_csr(const int32_t* tasks, int64_t n_tasks, const int32_t* heavy_rows, int64_t n_heavy,
-                             const int32_t* col_idx, const float* vals, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                             const int32_t* col_idx, const float* vals, const float* X, int64_t n_cols, int64_t ldx, float* Y, int64_t ldy,
                              const float* Z, int64_t ldz, int32_t d, float* partials, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_tasks < 0 || n_heavy < 0 || d <= 0 || (d & 3) || d > 256) return KGAT_ERR_INVALID_ARGUMENT;
     if ((ldx & 3) || (ldy & 3) || (Z && (ldz & 3))) return KGAT_ERR_INVALID_ARGUMENT;
     if (n_heavy > 0 && partials == nullptr) return KGAT_ERR_INVALID_ARGUMENT;
     if (n_tasks == 0) return KGAT_OK;
+    if (n_cols <= 0) return KGAT_ERR_INVALID_ARGUMENT;
+    const bool use_wide = n_cols * ldx * 4 >= ((int64_t)1 << 32);  // 32-bit byte offsets cover tables < 4 GiB
     const int threads = 128;
     const unsigned blocks = (unsigned)((n_tasks * 32 + threads - 1) / threads);
     const int4* t4 = reinterpret_cast<const int4*>(tasks);
+#define KGAT_SPMM_LAUNCH(DD, UU)                                                                                              \
+    do {                                                                                                                      \
+        if (use_wide) spmm_task_kernel<DD, UU, true><<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials); \
+        else spmm_task_kernel<DD, UU, false><<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials);        \
+    } while (0)
     switch (d) {
-        case 16: spmm_task_kernel<16, 2><<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials); break;
-        case 32: spmm_task_kernel<32, 4><<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials); break;
-        case 64: spmm_task_kernel<64, 4><<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials); break;
-        case 128: spmm_task_kernel<128, 4><<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials); break;
+        case 16: KGAT_SPMM_LAUNCH(16, 2); break;
+        case 32: KGAT_SPMM_LAUNCH(32, 4); break;
+        case 64: KGAT_SPMM_LAUNCH(64, 4); break;
+        case 128: KGAT_SPMM_LAUNCH(128, 4); break;
         default:
             spmm_task_kernel_generic<<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, d);
     }
+#undef KGAT_SPMM_LAUNCH
     if (n_heavy > 0) {
         const unsigned hb = (unsigned)((n_heavy * 32 + threads - 1) / threads);
         spmm_heavy_reduce_kernel<<<hb, threads, 0, stream>>>(reinterpret_cast<const int4*>(heavy_rows), n_heavy, partials, Y, ldy, Z,

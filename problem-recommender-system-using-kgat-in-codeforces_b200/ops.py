@@ -198,7 +198,7 @@ def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.
     check(
         lib.kgat_spmm_csr(
             _ptr(plan.tasks, i32), plan.n_tasks, _ptr(plan.heavy, i32) if plan.n_heavy else None, plan.n_heavy,
-            _ptr(col_idx, i32), _ptr(vals, f32), _ptr(x, f32, "x", True), x.stride(0), _ptr(out, f32, "out", True), out.stride(0),
+            _ptr(col_idx, i32), _ptr(vals, f32), _ptr(x, f32, "x", True), x.shape[0], x.stride(0), _ptr(out, f32, "out", True), out.stride(0),
             _ptr(addend, f32, "addend", True) if addend is not None else None, addend.stride(0) if addend is not None else 0, d,
             _ptr(partials, f32) if partials is not None else None, _stream(),
         ),
