@@ -1,0 +1,394 @@
+"""Row-sharded multi-GPU propagation: one process per GPU, the CKG rows are
+partitioned across the ranks and every propagation layer exchanges the freshly computed rows with an
+NCCL all-gather over NVLink; the backward pass all-gathers the side-gradient and gathers over the
+local rows of A^T (no atomics, no reduce-scatter); dense-parameter gradients are all-reduced.
+
+Partition: *cyclic* -- rank r owns the rows {i : i mod P == r}.  The survey suggested contiguous
+nnz-balanced ranges; on a CKG the node types sit in contiguous id blocks (users, items, entities)
+with a 10-15x spread in row length, so contiguous ranges are either nnz- or row-balanced, never
+both, and the bi-interaction GEMMs cost per *row*.  The cyclic split balances both statistically,
+gives equal shard sizes (all-gather without padding waste) and needs only ``i % P, i // P``.
+
+Tables live in the *padded cyclic layout*: global row i sits at ``(i % P) * max_rows + i // P`` so a
+rank's rows are one contiguous slice, which is exactly what ``all_gather_into_tensor`` wants.
+
+The orchestration is written against a small ``LocalOps`` interface so the same code runs with the
+CUDA kernels (``KernelOps``) on GPUs and -- in the CPU tests, world_size 2 over gloo -- with plain
+torch ops injected by the test.
+
+Phases of the reference epoch (main.py:290-361):
+  CF steps   row-sharded as above (this is where the propagation cost is),
+  KG steps   replicated (a TransR batch touches <= 1536 rows; sharding it would add a 40 MB
+             all-gather per step for a 50 us kernel),
+  refresh    replicated and deterministic (10 ms once per epoch).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+# ----------------------------------------------------------------------------------------------
+# partition (pure index math, CPU-tested)
+# ----------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class CyclicPartition:
+    n: int
+    world: int
+    rank: int
+
+    @property
+    def max_rows(self) -> int:
+        return (self.n + self.world - 1) // self.world
+
+    @property
+    def padded(self) -> int:
+        return self.max_rows * self.world
+
+    def count(self, rank: int | None = None) -> int:
+        r = self.rank if rank is None else rank
+        return len(range(r, self.n, self.world))
+
+    def local_rows(self, rank: int | None = None) -> np.ndarray:
+        r = self.rank if rank is None else rank
+        return np.arange(r, self.n, self.world, dtype=np.int64)
+
+    def to_padded(self, ids):
+        """global row id -> row in the padded cyclic layout (numpy array or torch tensor)."""
+        return (ids % self.world) * self.max_rows + ids // self.world
+
+    def slice(self, rank: int | None = None) -> slice:
+        r = self.rank if rank is None else rank
+        return slice(r * self.max_rows, r * self.max_rows + self.count(r))
+
+    def full_slice(self, rank: int | None = None) -> slice:
+        r = self.rank if rank is None else rank
+        return slice(r * self.max_rows, (r + 1) * self.max_rows)
+
+    def scatter_rows(self, table: torch.Tensor) -> torch.Tensor:
+        """[n, d] in global order -> [padded, d] in the padded cyclic layout (pad rows zero)."""
+        out = table.new_zeros((self.padded, table.shape[1]))
+        idx = torch.arange(self.n, device=table.device)
+        out[self.to_padded(idx)] = table
+        return out
+
+    def gather_rows(self, padded_table: torch.Tensor) -> torch.Tensor:
+        idx = torch.arange(self.n, device=padded_table.device)
+        return padded_table[self.to_padded(idx)]
+
+
+def shard_csr(row_ptr: np.ndarray, col_idx: np.ndarray, part: CyclicPartition):
+    """Local CSR of the rows owned by ``part.rank``: (row_ptr_local, col_idx in padded layout,
+    slot_ids = positions of the local non-zeros in the global value array)."""
+    rows = part.local_rows()
+    lens = (row_ptr[rows + 1] - row_ptr[rows]).astype(np.int64)
+    lp = np.concatenate([[0], np.cumsum(lens)])
+    starts = np.repeat(row_ptr[rows].astype(np.int64), lens)
+    within = np.arange(int(lp[-1]), dtype=np.int64) - np.repeat(lp[:-1], lens)
+    slot_ids = starts + within
+    cols = part.to_padded(col_idx[slot_ids].astype(np.int64))
+    return lp.astype(np.int32), cols.astype(np.int32), slot_ids.astype(np.int32)
+
+
+# ----------------------------------------------------------------------------------------------
+# local compute interface
+# ----------------------------------------------------------------------------------------------
+class KernelOps:
+    """LocalOps backed by the sm_100a kernels."""
+
+    def __init__(self):
+        from . import ops
+        from .graph import make_plan
+
+        self.ops, self.make_plan = ops, make_plan
+        self._partials = None
+
+    def make_local_graph(self, row_ptr, col_idx, slot_ids, device, chunk=256):
+        rp = torch.from_numpy(row_ptr).to(device)
+        return {"row_ptr": rp, "col_idx": torch.from_numpy(col_idx).to(device), "slot_ids": torch.from_numpy(slot_ids).to(device),
+                "plan": self.make_plan(rp, chunk), "vals": torch.empty(col_idx.shape[0], dtype=torch.float32, device=device)}
+
+    def refresh_values(self, lg, global_vals):
+        self.ops.gather_f32(global_vals, lg["slot_ids"], out=lg["vals"])
+
+    def spmm(self, lg, x_full, out, addend=None):
+        plan = lg["plan"]
+        need = plan.n_partials * x_full.shape[1]
+        if need and (self._partials is None or self._partials.numel() < need):
+            self._partials = torch.empty(need, dtype=torch.float32, device=x_full.device)
+        return self.ops.spmm(plan, lg["col_idx"], lg["vals"], x_full, out, addend, self._partials)
+
+    def biagg_forward(self, e, s, layer, out, p, seed, offset, seed_dev=None):
+        n, d_out = e.shape[0], layer[0].shape[0]
+        inv = torch.empty(n, dtype=torch.float32, device=e.device)
+        flags = torch.empty(n, d_out, dtype=torch.uint8, device=e.device)
+        self.ops.biagg_forward(e, s, *layer, out, inv, flags, dropout_p=p, seed=seed, offset=offset, seed_dev=seed_dev)
+        return inv, flags
+
+    def biagg_backward(self, g_out, out, inv, flags, e, s, layer, p, g_s, g_e):
+        w1, b1, w2, b2 = layer
+        n, d_in, d_out = e.shape[0], e.shape[1], w1.shape[0]
+        n_ctas = self.ops.biagg_backward_ctas(n, d_in, d_out)
+        partials = torch.empty(n_ctas * (2 * d_in * d_out + 2 * d_out), dtype=torch.float32, device=e.device)
+        self.ops.biagg_backward(g_out, out, inv, flags, e, s, w1, w2, p, g_s, g_e, partials, n_ctas)
+        grads = [torch.empty_like(t) for t in (w1, b1, w2, b2)]
+        self.ops.biagg_reduce_param_grads(partials, n_ctas, d_in, d_out, *grads)
+        return grads
+
+    def bpr_forward(self, tables, u, p, n, reg, loss, scratch):
+        self.ops.bpr_forward(tables, u, p, n, reg, loss, scratch)
+
+    def bpr_backward(self, tables, grads, u, p, n, reg, scratch, g_loss):
+        self.ops.bpr_backward(tables, grads, u, p, n, reg, scratch, g_loss)
+
+
+def all_gather_rows(full: torch.Tensor, part: CyclicPartition):
+    """In-place all-gather of a [padded, d] table whose own slice has just been written."""
+    if part.world == 1:
+        return
+    mine = full[part.full_slice()]
+    dist.all_gather_into_tensor(full, mine)
+
+
+# ----------------------------------------------------------------------------------------------
+# sharded CF step
+# ----------------------------------------------------------------------------------------------
+class ShardedPropagation:
+    """Forward / backward of the 3-layer propagation + BPR loss on row shards.
+
+    ``layers``: list of (W1, b1, W2, b2) replicated on every rank.  ``e0_full``: [padded, d0] table
+    in padded layout whose own slice holds the current local embedding rows."""
+
+    def __init__(self, part: CyclicPartition, local_a, local_at, ops: "KernelOps", dims, device):
+        self.part, self.a, self.at, self.ops = part, local_a, local_at, ops
+        self.dims = list(dims)  # [d0, d1, ..., dL]
+        pad = part.padded
+        self.tables = [torch.zeros(pad, d, dtype=torch.float32, device=device) for d in self.dims]
+        self.g_tables = [torch.zeros(pad, d, dtype=torch.float32, device=device) for d in self.dims]
+        self.gs_full = [torch.zeros(pad, d, dtype=torch.float32, device=device) for d in self.dims[:-1]]
+        self.device = device
+        self.saved = None
+
+    def forward(self, layers, ps, seed, u, p, n, reg, loss, scratch, seed_dev=None):
+        part = self.part
+        sl = part.slice()
+        all_gather_rows(self.tables[0], part)
+        saved = []
+        for l, layer in enumerate(layers):
+            x_full = self.tables[l]
+            x_loc = x_full[sl]
+            s_loc = torch.empty(part.count(), self.dims[l], dtype=torch.float32, device=self.device)
+            self.ops.spmm(self.a, x_full, s_loc)
+            out_loc = self.tables[l + 1][sl]
+            # each rank draws its rows' dropout decisions from its own Philox stream (seed + rank)
+            inv, flags = self.ops.biagg_forward(x_loc, s_loc, layer, out_loc, ps[l], seed + 7919 * part.rank, (l + 1) << 40, seed_dev)
+            all_gather_rows(self.tables[l + 1], part)
+            saved.append((s_loc, inv, flags))
+        self.ops.bpr_forward(self.tables, u, p, n, reg, loss, scratch)
+        self.saved = (saved, (u, p, n), reg, scratch, ps)
+        return loss
+
+    def backward(self, layers, g_loss):
+        """Returns (g_e0_local [count, d0], [param grads per layer] summed over ranks)."""
+        part = self.part
+        sl = part.slice()
+        saved, (u, p, n), reg, scratch, ps = self.saved
+        L = len(layers)
+        n_tab = L + 1
+
+        def inject(l):
+            grads = [None] * n_tab
+            grads[l] = self.g_tables[l]
+            self.ops.bpr_backward(self.tables, grads, u, p, n, reg, scratch, g_loss)
+
+        self.g_tables[L].zero_()
+        inject(L)
+        pgrads = [None] * L
+        for l in range(L, 0, -1):
+            s_loc, inv, flags = saved[l - 1]
+            x_loc = self.tables[l - 1][sl]
+            g_s_loc = self.gs_full[l - 1][sl]
+            g_e_loc = torch.empty(part.count(), self.dims[l - 1], dtype=torch.float32, device=self.device)
+            pgrads[l - 1] = self.ops.biagg_backward(self.g_tables[l][sl], self.tables[l][sl], inv, flags, x_loc, s_loc, layers[l - 1], ps[l - 1],
+                                                    g_s_loc, g_e_loc)
+            all_gather_rows(self.gs_full[l - 1], part)
+            self.ops.spmm(self.at, self.gs_full[l - 1], self.g_tables[l - 1][sl], addend=g_e_loc)
+            inject(l - 1)
+        if part.world > 1:
+            flat = torch.cat([t.reshape(-1) for grp in pgrads for t in grp])
+            dist.all_reduce(flat)
+            off = 0
+            for grp in pgrads:
+                for t in grp:
+                    t.copy_(flat[off : off + t.numel()].view_as(t))
+                    off += t.numel()
+        return self.g_tables[0][sl], pgrads
+
+
+# ----------------------------------------------------------------------------------------------
+# engine + bench entry for N > 1
+# ----------------------------------------------------------------------------------------------
+class ShardedEngine:
+    """Epoch driver for P ranks: sharded CF phase, replicated KG phase and refresh."""
+
+    def __init__(self, model, part: CyclicPartition):
+        from . import ops
+        from .engine import TrainEngine
+
+        self.model, self.part, self.kops, self.ops = model, part, KernelOps(), ops
+        self.dev = model._device()
+        self.single = TrainEngine(model, use_graphs=True)  # KG phase (replicated) reuses the 1-GPU engine
+        self.layers = [tuple(t.detach() for t in grp) for grp in model._layers()]
+        dims = [model._cf_embedding_dim, *model._layer_dims]
+        self._build_graph(dims)
+        n_loc = part.count()
+        d0 = dims[0]
+        self.e0_m = torch.zeros(n_loc, d0, device=self.dev)
+        self.e0_v = torch.zeros(n_loc, d0, device=self.dev)
+        self.layer_m = [[torch.zeros_like(t) for t in grp] for grp in self.layers]
+        self.layer_v = [[torch.zeros_like(t) for t in grp] for grp in self.layers]
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.hyper = torch.empty(8, device=self.dev)
+        self.loss = torch.zeros(1, device=self.dev)
+        self.loss_sum = torch.zeros(1, device=self.dev)
+        self.scratch = torch.empty(2 * 256, device=self.dev)
+        self.one = torch.ones(1, device=self.dev)
+        self.scatter_from_model()
+
+    def _build_graph(self, dims):
+        g = self.model._graph()
+        self._graph_id = (id(g), g.vals.data_ptr())
+        rp, ci = g.row_ptr.cpu().numpy(), g.col_idx.cpu().numpy()
+        tp, ti = g.t_ptr.cpu().numpy(), g.t_idx.cpu().numpy()
+        self.a = self.kops.make_local_graph(*shard_csr(rp, ci, self.part), self.dev)
+        self.at = self.kops.make_local_graph(*shard_csr(tp, ti, self.part), self.dev)
+        self.prop = ShardedPropagation(self.part, self.a, self.at, self.kops, dims, self.dev)
+        self.refresh_values()
+
+    def refresh_values(self):
+        g = self.model._graph()
+        self.kops.refresh_values(self.a, g.vals)
+        self.kops.refresh_values(self.at, g.t_vals)
+
+    def scatter_from_model(self):
+        w = self.model._user_entity_embedding.weight.detach()
+        self.prop.tables[0].copy_(self.part.scatter_rows(w))
+
+    def gather_to_model(self):
+        all_gather_rows(self.prop.tables[0], self.part)
+        self.model._user_entity_embedding.weight.data.copy_(self.part.gather_rows(self.prop.tables[0]))
+        torch.autograd.graph.increment_version(self.model._user_entity_embedding.weight)
+
+    def cf_step(self, u, p, n):
+        """One sharded CF step; ``u, p, n`` are already rows of the padded cyclic layout."""
+        m, part = self.model, self.part
+        ps = [float(a.message_dropout.p) if m.training else 0.0 for a in m._aggregator_layers]
+        reg = float(m._regularization_params[0])
+        self.prop.forward(self.layers, ps, 12345, u, p, n, reg, self.loss, self.scratch, seed_dev=self.step_dev)
+        g_e0, pgrads = self.prop.backward(self.layers, self.one)
+        opt = m._cf_optimizer.param_groups[0]
+        self.ops.adam_advance(self.step_dev, opt["lr"], opt["betas"][0], opt["betas"][1], opt["eps"], self.hyper)
+        e0_loc = self.prop.tables[0][part.slice()]
+        params = [e0_loc] + [t for grp in self.layers for t in grp]
+        grads = [g_e0.contiguous()] + [t for grp in pgrads for t in grp]
+        ms = [self.e0_m] + [t for grp in self.layer_m for t in grp]
+        vs = [self.e0_v] + [t for grp in self.layer_v for t in grp]
+        self.ops.adam_apply(params, grads, ms, vs, self.hyper)
+        self.loss_sum.add_(self.loss)
+
+    def run_epoch(self, data, n_cf=None, n_kg=None, refresh=True):
+        """``data``: EpochData on the device (cf [n,3,B], kg [n,4,B] stacked, as TrainEngine.bind_resident)."""
+        m = self.model
+        m.train()
+        g = m._graph()
+        if (id(g), g.vals.data_ptr()) != self._graph_id:
+            self._build_graph([m._cf_embedding_dim, *m._layer_dims])
+            self.scatter_from_model()
+        n_cf = data.cf.shape[0] if n_cf is None else n_cf
+        n_kg = data.kg.shape[0] if n_kg is None else n_kg
+        self.loss_sum.zero_()
+        cf_padded = self.part.to_padded(data.cf[:n_cf])  # batch ids -> rows of the padded cyclic layout, once per epoch
+        for i in range(n_cf):
+            b = cf_padded[i]
+            self.cf_step(b[0], b[1], b[2])
+        cf_loss = float(self.loss_sum.item()) / max(n_cf, 1)
+        self.gather_to_model()
+        for grp in m._layers():  # aggregator weights were updated in place (they are the model's tensors)
+            for t in grp:
+                torch.autograd.graph.increment_version(t)
+        kg_loss = 0.0
+        if n_kg:
+            self.single._resident = data
+            kg_loss = self.single.run_epoch(None, n_cf=0, n_kg=n_kg, refresh=False)[1]
+        if refresh:
+            eh, er, et, ri = data.edges
+            from .model import KGATMode
+
+            m(eh, er, et, ri, mode=KGATMode.UPDATE_ATTENTION)
+            g = m._graph()
+            if (id(g), g.vals.data_ptr()) != self._graph_id:
+                self._build_graph([m._cf_embedding_dim, *m._layer_dims])
+            else:
+                self.refresh_values()
+        if self.part.world > 1:  # replicas of the replicated parameters: rank 0 wins (ulp-level atomics drift)
+            for t in (m._relation_embedding.weight, m._trans_matrix, m._user_entity_embedding.weight):
+                dist.broadcast(t.data, src=0)
+        self.scatter_from_model()
+        return cf_loss, kg_loss
+
+
+def bench_main(args, metric, unit, workload, make_workload, config_dict, ClockSampler):
+    """``bench.py --gpus N`` under torchrun: strong scaling of the epoch on the fixed C3-shaped CKG."""
+    import json
+    import os
+
+    from . import _lib
+    from .engine import TrainEngine
+    from .trainer import build_model
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    g, data = make_workload(workload)
+    model = build_model(g, dev)
+    part = CyclicPartition(g.node_num, world, rank)
+    holder = TrainEngine(model, use_graphs=False).bind_resident(data.tensors())
+    # the first refresh swaps the attentive structure: do it before building the sharded graph
+    from .model import KGATMode
+
+    model(*holder.edges, mode=KGATMode.UPDATE_ATTENTION)
+    eng = ShardedEngine(model, part)
+    for _ in range(max(args.warmup, 0)):
+        eng.run_epoch(holder)
+    torch.cuda.synchronize()
+    dist.barrier()
+    _lib.LaunchCounter.count = 0
+    with ClockSampler(dev.index or 0) as clocks:
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        losses = None
+        for _ in range(args.steps):
+            losses = eng.run_epoch(holder)
+        t1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+    ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    epoch_s = float(ms.item()) / 1e3 / max(args.steps, 1)
+    if rank == 0:
+        graph = model._graph()
+        line = {
+            "metric": metric, "value": epoch_s, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": epoch_s * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(g, data, world),
+            "propagation_edges_per_s": graph.nnz * 3 * 2 * data.n_cf / epoch_s,
+            "cf_loss": losses[0], "kg_loss": losses[1], "gpu_launches": _lib.LaunchCounter.count, "clocks": clocks.summary(),
+            "e2e": None, "roofline": None, "cpu_baseline": None,
+            "note": "CF phase row-sharded (cyclic) with 7 all-gathers + 1 all-reduce per step over NCCL; KG phase and the refresh are replicated; "
+                    "timed on the device, max over ranks",
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()

@@ -1,0 +1,151 @@
+"""Multi-GPU host logic on the CPU: the cyclic partition index math and -- with world_size 2 over
+gloo and plain-torch local ops injected in place of the CUDA kernels -- the exchange pattern of the
+row-sharded CF step (per-layer all-gather forward, all-gather of the side gradient backward,
+all-reduce of the dense-parameter gradients) against the unsharded oracle."""
+
+from __future__ import annotations
+
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn.functional as F
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def test_cyclic_partition_index_math():
+    from kgat_b200.sharding import CyclicPartition, shard_csr
+
+    n, world = 23, 4
+    parts = [CyclicPartition(n, world, r) for r in range(world)]
+    assert parts[0].max_rows == 6 and parts[0].padded == 24
+    assert sum(p.count() for p in parts) == n
+    ids = np.arange(n)
+    pad = parts[0].to_padded(ids)
+    assert len(set(pad.tolist())) == n and pad.max() < 24
+    for p in parts:
+        rows = p.local_rows()
+        assert (rows % world == p.rank).all()
+        sl = p.slice()
+        np.testing.assert_array_equal(p.to_padded(rows), np.arange(sl.start, sl.stop))
+    t = torch.arange(n * 3, dtype=torch.float32).view(n, 3)
+    assert torch.equal(parts[2].gather_rows(parts[2].scatter_rows(t)), t)
+    # local CSR: every non-zero lands on exactly one rank, columns remapped to the padded layout
+    rng = np.random.default_rng(0)
+    lens = rng.integers(0, 6, n)
+    rp = np.concatenate([[0], np.cumsum(lens)])
+    ci = rng.integers(0, n, rp[-1])
+    seen = np.zeros(rp[-1], int)
+    for p in parts:
+        lp, lc, slots = shard_csr(rp, ci, p)
+        seen[slots] += 1
+        np.testing.assert_array_equal(lc, p.to_padded(ci[slots]))
+        np.testing.assert_array_equal(np.diff(lp), lens[p.local_rows()])
+    assert (seen == 1).all()
+
+
+class TorchOps:
+    """LocalOps with plain torch CPU ops (test double for sharding.KernelOps)."""
+
+    def spmm(self, lg, x_full, out, addend=None):
+        y = torch.sparse.mm(lg["csr"], x_full)
+        out.copy_(y if addend is None else y + addend)
+
+    def biagg_forward(self, e, s, layer, out, p, seed, offset, seed_dev=None):
+        assert p == 0.0
+        w1, b1, w2, b2 = layer
+        x = F.leaky_relu(F.linear(e + s, w1, b1), 0.01) + F.leaky_relu(F.linear(e * s, w2, b2), 0.01)
+        out.copy_(F.normalize(x, dim=1, eps=1e-12))
+        return None, None
+
+    def biagg_backward(self, g_out, out, inv, flags, e, s, layer, p, g_s, g_e):
+        leaves = [t.detach().clone().requires_grad_(True) for t in (e, s, *layer)]
+        ee, ss, w1, b1, w2, b2 = leaves
+        x = F.leaky_relu(F.linear(ee + ss, w1, b1), 0.01) + F.leaky_relu(F.linear(ee * ss, w2, b2), 0.01)
+        F.normalize(x, dim=1, eps=1e-12).backward(g_out)
+        g_e.copy_(ee.grad)
+        g_s.copy_(ss.grad)
+        return [w1.grad, b1.grad, w2.grad, b2.grad]
+
+    def bpr_forward(self, tables, u, p, n, reg, loss, scratch):
+        from oracle import kgat_oracle as O
+
+        loss.copy_(O.bpr_loss_from_table(torch.cat(tables, dim=1), u, p, n, reg).reshape(1))
+
+    def bpr_backward(self, tables, grads, u, p, n, reg, scratch, g_loss):
+        from oracle import kgat_oracle as O
+
+        leaves = [t.detach().clone().requires_grad_(True) for t in tables]
+        (O.bpr_loss_from_table(torch.cat(leaves, dim=1), u, p, n, reg) * g_loss[0]).backward()
+        for g, leaf in zip(grads, leaves):
+            if g is not None:
+                g.add_(leaf.grad)
+
+
+def _worker(rank, world, port, ok):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from conftest import Golden
+        from kgat_b200.sharding import CyclicPartition, ShardedPropagation, shard_csr
+        from oracle import kgat_oracle as O
+
+        g = Golden("model_tiny.npz")
+        n = g.node_num
+        params = g.params()
+        att = g.att_coo().coalesce()
+        part = CyclicPartition(n, world, rank)
+        crow = torch._convert_indices_from_coo_to_csr(att.indices()[0], n).numpy()
+        col, val = att.indices()[1].numpy(), att.values()
+        att_t = att.t().coalesce()
+        trow = torch._convert_indices_from_coo_to_csr(att_t.indices()[0], n).numpy()
+        tcol, tval = att_t.indices()[1].numpy(), att_t.values()
+
+        def local(rp, ci, vals):
+            lp, lc, slots = shard_csr(rp, ci, part)
+            csr = torch.sparse_csr_tensor(torch.from_numpy(lp).long(), torch.from_numpy(lc).long(), vals[torch.from_numpy(slots).long()],
+                                          size=(part.count(), part.padded))
+            return {"csr": csr}
+
+        dims = [64, 64, 32, 16]
+        prop = ShardedPropagation(part, local(crow, col, val), local(trow, tcol, tval), TorchOps(), dims, "cpu")
+        layers = [tuple(params[f"_aggregator_layers.{l}.linear{k}.{w}"] for k in (1, 2) for w in ("weight", "bias")) for l in range(3)]
+        e0 = params["_user_entity_embedding.weight"]
+        # only the own slice is filled: the forward all-gathers the rest
+        prop.tables[0][part.slice()] = e0[torch.from_numpy(part.local_rows())]
+        u, p, q = (torch.from_numpy(g[k]) for k in ("cf_users", "cf_pos", "cf_neg"))
+        loss = torch.zeros(1)
+        prop.forward(layers, [0.0] * 3, 0, part.to_padded(u), part.to_padded(p), part.to_padded(q), 1e-5, loss, None)
+        g_e0_loc, pgrads = prop.backward(layers, torch.ones(1))
+
+        leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        ref = O.cf_loss(leaves, att, u, p, q)
+        ref.backward()
+        assert abs(float(loss) - float(ref)) < 1e-6, (float(loss), float(ref))
+        assert abs(float(loss) - float(g["cf_loss_eval"])) < 1e-6  # and against the reference golden
+        ref_g = leaves["_user_entity_embedding.weight"].grad[torch.from_numpy(part.local_rows())]
+        assert float((g_e0_loc - ref_g).abs().max()) < 1e-7 * max(1.0, float(ref_g.abs().max()) * 1e3)
+        for l in range(3):
+            for j, (k, w) in enumerate(((1, "weight"), (1, "bias"), (2, "weight"), (2, "bias"))):
+                rg = leaves[f"_aggregator_layers.{l}.linear{k}.{w}"].grad
+                assert float((pgrads[l][j] - rg).abs().max()) <= 2e-5 * float(rg.abs().max()) + 1e-9, (l, k, w)
+        ok[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_cf_step_world2_gloo_matches_oracle():
+    world = 2
+    ok = mp.get_context("spawn").Array("i", [0] * world)
+    port = 29000 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, ok), nprocs=world, join=True)
+    assert list(ok) == [1] * world
