@@ -10,6 +10,8 @@
 // shuffle reduction over the DOUT/4 threads that share a row.  The CTAs are persistent (grid =
 // k x #SM) so weights are staged once and weight-gradient accumulators stay in registers across
 // row tiles.  fp32 FMA throughout: results stay inside the 1e-5 parity budget.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace kgat {
@@ -414,6 +416,27 @@ int bwd_ctas(int64_t n) {
 }  // namespace
 }  // namespace kgat
 
+namespace kgat {
+// tensor-core (3xTF32 mma.sync) implementation, biagg_mma.cu
+int biagg_mma_forward(const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* b1, const float* W2,
+                      const float* b2, float p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits,
+                      float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, cudaStream_t stream);
+int biagg_mma_backward_ctas(int64_t n, int d_in, int d_out);
+int biagg_mma_backward(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm, const uint8_t* flags,
+                       const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* W2, float p, float* g_S,
+                       float* g_E, float* partials, int n_ctas, cudaStream_t stream);
+
+// KGAT_BIAGG_IMPL=ffma selects the CUDA-core kernels of this file (A/B comparison); default: tensor cores
+static bool use_mma() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("KGAT_BIAGG_IMPL");
+        v = (e != nullptr && e[0] == 'f') ? 0 : 1;
+    }
+    return v == 1;
+}
+}  // namespace kgat
+
 using namespace kgat;
 
 #define KGAT_DISPATCH_DIMS(DIN_, DOUT_, CALL)                          \
@@ -439,12 +462,16 @@ int kgat_biagg_forward(const float* E, const float* S, int64_t n, int32_t d_in, 
                        const uint32_t* keep_bits, float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, void* stream) {
     if (n < 0 || dropout_p < 0.f || dropout_p >= 1.f || (ld_out & 3)) return KGAT_ERR_INVALID_ARGUMENT;
     if (n == 0) return KGAT_OK;
+    if (use_mma())
+        return biagg_mma_forward(E, S, n, d_in, d_out, W1, b1, W2, b2, dropout_p, seed, offset, seed_dev, keep_bits, out, ld_out, inv_norm,
+                                 flags, (cudaStream_t)stream);
     KGAT_DISPATCH_DIMS(d_in, d_out, return (launch_fwd<DI, DO>(E, S, n, W1, b1, W2, b2, dropout_p, seed, offset, seed_dev, keep_bits, out, ld_out,
                                                                inv_norm, flags, (cudaStream_t)stream)));
 }
 
 int kgat_biagg_backward_ctas(int64_t n, int32_t d_in, int32_t d_out) {
     if (n <= 0) return 1;
+    if (use_mma()) return biagg_mma_backward_ctas(n, d_in, d_out);
     KGAT_DISPATCH_DIMS(d_in, d_out, return (bwd_ctas<DI, DO>(n)));
 }
 
@@ -452,6 +479,9 @@ int kgat_biagg_backward(const float* g_out, int64_t ld_gout, const float* out, i
                         const uint8_t* flags, const float* E, const float* S, int64_t n, int32_t d_in, int32_t d_out, const float* W1,
                         const float* W2, float dropout_p, float* g_S, float* g_E, float* partials, int32_t n_ctas, void* stream) {
     if (n <= 0 || n_ctas <= 0 || (ld_gout & 3) || (ld_out & 3)) return KGAT_ERR_INVALID_ARGUMENT;
+    if (use_mma())
+        return biagg_mma_backward(g_out, ld_gout, out, ld_out, inv_norm, flags, E, S, n, d_in, d_out, W1, W2, dropout_p, g_S, g_E, partials,
+                                  n_ctas, (cudaStream_t)stream);
     KGAT_DISPATCH_DIMS(d_in, d_out, return (launch_bwd<DI, DO>(g_out, ld_gout, out, ld_out, inv_norm, flags, E, S, n, W1, W2, dropout_p,
                                                                g_S, g_E, partials, n_ctas, (cudaStream_t)stream)));
 }

@@ -1,0 +1,493 @@
+// K2/K3 on the tensor cores: the bi-interaction aggregator's GEMMs as warp-level TF32 MMAs with
+// 3xTF32 error compensation (a = hi + lo, a*b ~= lo*hi + hi*lo + hi*hi, fp32 accumulate), which keeps
+// the result at fp32-level accuracy (~1e-6 normwise) -- inside the 1e-5 parity budget that plain TF32
+// (1e-3) would break.  Same interface, same saved tensors and the same staging / fusion as the FFMA
+// kernels in biagg.cu (which remain as the reference implementation, KGAT_BIAGG_IMPL=ffma).
+//
+// Why mma.sync and not tcgen05 here: after the switch the kernels are bound by staging and HBM, not
+// by the tensor pipe (2.6 GFLOP x 3 per layer-forward against 120 MB of traffic), so the simpler
+// register-fragment path already reaches the memory-side limit; see DESIGN.md section 4.
+#include "common.cuh"
+
+namespace kgat {
+namespace mma {
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(x);
+    lo = to_tf32(x - __uint_as_float(hi));
+}
+// D += A (16x8, row) * B (8x8, col), TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 3xTF32: small cross terms first, then the leading term
+__device__ __forceinline__ void mma_3x(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1,
+                                       uint32_t bl0, uint32_t bl1) {
+    mma_tf32(d, al, bh0, bh1);
+    mma_tf32(d, ah, bl0, bl1);
+    mma_tf32(d, ah, bh0, bh1);
+}
+
+template <int DIN, int DOUT>
+struct FwdCfg {
+    static constexpr bool kBig = (DIN > 64) || (DOUT > 64);
+    static constexpr int NT = 256;                 // 8 warps
+    static constexpr int TM = kBig ? 64 : 128;     // rows per CTA tile
+    static constexpr int WARPS = NT / 32;
+    static constexpr int MT = TM / 16;             // m-tiles per CTA tile
+    static constexpr int NTL = DOUT / 8;           // n-tiles
+    static constexpr int WPM = WARPS / MT;         // warps sharing one m-tile (1, or 2 for the big shapes)
+    static constexpr int NTW = NTL / WPM;          // n-tiles per warp
+    static constexpr int SE = DIN + 4;             // smem strides == 4 mod 32: conflict-free fragment reads
+    static constexpr int SW = DIN + 4;
+    static_assert(WARPS % MT == 0 && NTL % WPM == 0, "bad warp mapping");
+    static constexpr size_t smem = sizeof(float) * (2 * DOUT * SW + 2 * TM * SE + (WPM > 1 ? TM * WPM : 0));
+};
+
+template <int DIN, int DOUT>
+__global__ void __launch_bounds__(256) biagg_fwd_mma_kernel(
+    const float* __restrict__ E, const float* __restrict__ S, int64_t n, const float* __restrict__ W1,
+    const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2, float dropout_p,
+    uint64_t seed, uint64_t offset, const uint64_t* __restrict__ seed_dev, const uint32_t* __restrict__ keep_bits,
+    float* __restrict__ out, int64_t ld_out, float* __restrict__ inv_norm, uint8_t* __restrict__ flags) {
+    using C = FwdCfg<DIN, DOUT>;
+    extern __shared__ __align__(16) float smem[];
+    if (seed_dev != nullptr) seed += seed_dev[0] * 0x9E3779B97F4A7C15ull;
+    float* W1s = smem;                      // [DOUT][SW]
+    float* W2s = W1s + DOUT * C::SW;
+    float* Us = W2s + DOUT * C::SW;         // [TM][SE]  E + S
+    float* Vs = Us + C::TM * C::SE;         // [TM][SE]  E * S
+    float* Red = Vs + C::TM * C::SE;        // [TM][WPM] partial row sums (only when WPM > 1)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    for (int i = tid; i < DOUT * (DIN / 4); i += C::NT) {
+        const int c = i / (DIN / 4), q = i % (DIN / 4);
+        *reinterpret_cast<float4*>(W1s + c * C::SW + q * 4) = __ldg(reinterpret_cast<const float4*>(W1 + c * DIN) + q);
+        *reinterpret_cast<float4*>(W2s + c * C::SW + q * 4) = __ldg(reinterpret_cast<const float4*>(W2 + c * DIN) + q);
+    }
+    const int mt = warp % C::MT;            // m-tile of this warp
+    const int nw = warp / C::MT;            // which slice of the n-tiles
+    const int nt0 = nw * C::NTW;
+    const float keep_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+    const uint32_t keep_thr = (uint32_t)((1.f - dropout_p) * 65536.f);
+    constexpr int words_per_row = (DOUT + 31) / 32;
+    const int64_t n_tiles = (n + C::TM - 1) / C::TM;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * C::TM;
+        __syncthreads();
+        for (int i = tid; i < C::TM * (DIN / 4); i += C::NT) {
+            const int r = i / (DIN / 4), q = i % (DIN / 4);
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f), s = e;
+            if (row0 + r < n) {
+                e = ld_stream4(E + (row0 + r) * DIN + q * 4);
+                s = ld_stream4(S + (row0 + r) * DIN + q * 4);
+            }
+            *reinterpret_cast<float4*>(Us + r * C::SE + q * 4) = make_float4(e.x + s.x, e.y + s.y, e.z + s.z, e.w + s.w);
+            *reinterpret_cast<float4*>(Vs + r * C::SE + q * 4) = make_float4(e.x * s.x, e.y * s.y, e.z * s.z, e.w * s.w);
+        }
+        __syncthreads();
+
+        float z1[C::NTW][4], z2[C::NTW][4];
+#pragma unroll
+        for (int j = 0; j < C::NTW; ++j) {
+            const int c = (nt0 + j) * 8 + 2 * t;
+            z1[j][0] = z1[j][2] = b1[c];
+            z1[j][1] = z1[j][3] = b1[c + 1];
+            z2[j][0] = z2[j][2] = b2[c];
+            z2[j][1] = z2[j][3] = b2[c + 1];
+        }
+        const float* ua = Us + (mt * 16 + g) * C::SE + t;
+        const float* va = Vs + (mt * 16 + g) * C::SE + t;
+#pragma unroll 2
+        for (int ks = 0; ks < DIN / 8; ++ks) {
+            uint32_t uh[4], ul[4], vh[4], vl[4];
+            split_tf32(ua[ks * 8], uh[0], ul[0]);
+            split_tf32(ua[ks * 8 + 8 * C::SE], uh[1], ul[1]);
+            split_tf32(ua[ks * 8 + 4], uh[2], ul[2]);
+            split_tf32(ua[ks * 8 + 8 * C::SE + 4], uh[3], ul[3]);
+            split_tf32(va[ks * 8], vh[0], vl[0]);
+            split_tf32(va[ks * 8 + 8 * C::SE], vh[1], vl[1]);
+            split_tf32(va[ks * 8 + 4], vh[2], vl[2]);
+            split_tf32(va[ks * 8 + 8 * C::SE + 4], vh[3], vl[3]);
+#pragma unroll
+            for (int j = 0; j < C::NTW; ++j) {
+                const int wrow = ((nt0 + j) * 8 + g) * C::SW + ks * 8 + t;
+                uint32_t bh0, bl0, bh1, bl1;
+                split_tf32(W1s[wrow], bh0, bl0);
+                split_tf32(W1s[wrow + 4], bh1, bl1);
+                mma_3x(z1[j], uh, ul, bh0, bh1, bl0, bl1);
+                split_tf32(W2s[wrow], bh0, bl0);
+                split_tf32(W2s[wrow + 4], bh1, bl1);
+                mma_3x(z2[j], vh, vl, bh0, bh1, bl0, bl1);
+            }
+        }
+
+        // epilogue: thread owns rows (mt*16 + g) and (+8), columns (nt0+j)*8 + 2t, +1
+        float x[2][C::NTW][2];
+        uint8_t f[2][C::NTW][2];
+        float ss[2] = {0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t row = row0 + mt * 16 + g + 8 * h;
+            const bool valid = row < n;
+            uint32_t rnd[(C::NTW * 2 + 7) / 8 * 4];
+            if (dropout_p > 0.f && keep_bits == nullptr && valid) {
+#pragma unroll
+                for (int q = 0; q < (C::NTW * 2 + 7) / 8; ++q) {
+                    const uint4 r4 = philox4x32(seed, offset + ((uint64_t)row * 4 + t) * 8 + nw * 2 + q);
+                    rnd[q * 4 + 0] = r4.x; rnd[q * 4 + 1] = r4.y; rnd[q * 4 + 2] = r4.z; rnd[q * 4 + 3] = r4.w;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < C::NTW; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = (nt0 + j) * 8 + 2 * t + e;
+                    bool kp = true;
+                    if (dropout_p > 0.f && valid) {
+                        if (keep_bits != nullptr) {
+                            kp = (keep_bits[row * words_per_row + (c >> 5)] >> (c & 31)) & 1u;
+                        } else {
+                            const int idx = j * 2 + e;  // 16-bit lane of the random words
+                            kp = ((rnd[idx >> 1] >> ((idx & 1) * 16)) & 0xffffu) < keep_thr;
+                        }
+                    }
+                    const float a1 = z1[j][2 * h + e], a2 = z2[j][2 * h + e];
+                    f[h][j][e] = (a1 > 0.f ? 1 : 0) | (a2 > 0.f ? 2 : 0) | (kp ? 4 : 0);
+                    const float v = lrelu(a1) + lrelu(a2);
+                    x[h][j][e] = kp ? v * keep_scale : 0.f;
+                    ss[h] = fmaf(x[h][j][e], x[h][j][e], ss[h]);
+                }
+            }
+            ss[h] += __shfl_xor_sync(kFull, ss[h], 1);
+            ss[h] += __shfl_xor_sync(kFull, ss[h], 2);
+        }
+        if (C::WPM > 1) {  // rows are split over WPM warps: combine the partial sums through smem
+            if (t == 0) {
+                Red[(mt * 16 + g) * C::WPM + nw] = ss[0];
+                Red[(mt * 16 + g + 8) * C::WPM + nw] = ss[1];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float tot = 0.f;
+#pragma unroll
+                for (int q = 0; q < C::WPM; ++q) tot += Red[(mt * 16 + g + 8 * h) * C::WPM + q];
+                ss[h] = tot;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t row = row0 + mt * 16 + g + 8 * h;
+            if (row >= n) continue;
+            const float nrm = sqrtf(ss[h]);
+            const float denom = fmaxf(nrm, KGAT_NORM_EPS);
+#pragma unroll
+            for (int j = 0; j < C::NTW; ++j) {
+                const int c = (nt0 + j) * 8 + 2 * t;
+                *reinterpret_cast<float2*>(out + row * ld_out + c) = make_float2(x[h][j][0] / denom, x[h][j][1] / denom);
+                if (flags != nullptr) *reinterpret_cast<uchar2*>(flags + row * DOUT + c) = make_uchar2(f[h][j][0], f[h][j][1]);
+            }
+            if (inv_norm != nullptr && t == 0 && nw == 0) inv_norm[row] = nrm < KGAT_NORM_EPS ? -1.f / denom : 1.f / denom;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+template <int DIN, int DOUT>
+struct BwdCfg {
+    static constexpr bool kBig = (DIN > 64) || (DOUT > 64);
+    static constexpr int NT = kBig ? 512 : 256;
+    static constexpr int WARPS = NT / 32;
+    static constexpr int TM = kBig ? 32 : 64;
+    static constexpr int SE = DIN + 4;    // E/S tiles: == 4 mod 32 (B operand of the weight-gradient MMA, permuted rows)
+    static constexpr int SG = DOUT + 4;   // dL/dz tiles: == 4 mod 32
+    static constexpr int SW = DIN + 8;    // weights: == 8 mod 32 (B operand of the input-gradient MMA)
+    // phase 1 (elementwise) mapping: CG threads per row
+    static constexpr int CG = DOUT / 4;
+    static constexpr int RGROUPS = NT / CG;
+    static constexpr int RM = (TM + RGROUPS - 1) / RGROUPS;
+    // phase 2 (input gradients): output TM x DIN = MT2 x NT2 tiles of 16x8, both products
+    static constexpr int MT2 = TM / 16;
+    static constexpr int NT2 = DIN / 8;
+    static constexpr int TILES2 = MT2 * NT2;
+    static constexpr int TPW2 = (TILES2 + WARPS - 1) / WARPS;
+    // phase 3 (weight gradients): output DOUT x DIN = MT3 x NT3 tiles, two matrices
+    static constexpr int MT3 = DOUT / 16;
+    static constexpr int NT3 = DIN / 8;
+    static constexpr int TILES3 = 2 * MT3 * NT3;
+    static constexpr int TPW3 = (TILES3 + WARPS - 1) / WARPS;
+    static constexpr size_t smem = sizeof(float) * (2 * DOUT * SW + 2 * TM * SE + 2 * TM * SG);
+};
+
+template <int DIN, int DOUT>
+__global__ void __launch_bounds__(BwdCfg<DIN, DOUT>::NT) biagg_bwd_mma_kernel(
+    const float* __restrict__ g_out, int64_t ld_gout, const float* __restrict__ out, int64_t ld_out,
+    const float* __restrict__ inv_norm, const uint8_t* __restrict__ flags, const float* __restrict__ E,
+    const float* __restrict__ S, int64_t n, const float* __restrict__ W1, const float* __restrict__ W2, float dropout_p,
+    float* __restrict__ g_S, float* __restrict__ g_E, float* __restrict__ partials) {
+    using C = BwdCfg<DIN, DOUT>;
+    extern __shared__ __align__(16) float smem[];
+    float* W1s = smem;                    // [DOUT][SW]
+    float* W2s = W1s + DOUT * C::SW;
+    float* Es = W2s + DOUT * C::SW;       // [TM][SE]
+    float* Ss = Es + C::TM * C::SE;
+    float* G1 = Ss + C::TM * C::SE;       // [TM][SG]
+    float* G2 = G1 + C::TM * C::SG;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    for (int i = tid; i < DOUT * (DIN / 4); i += C::NT) {
+        const int c = i / (DIN / 4), q = i % (DIN / 4);
+        *reinterpret_cast<float4*>(W1s + c * C::SW + q * 4) = __ldg(reinterpret_cast<const float4*>(W1 + c * DIN) + q);
+        *reinterpret_cast<float4*>(W2s + c * C::SW + q * 4) = __ldg(reinterpret_cast<const float4*>(W2 + c * DIN) + q);
+    }
+    const float keep_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+    const int cg = tid % C::CG, rg = tid / C::CG;
+
+    // persistent accumulators: weight-gradient tiles of this warp, bias-gradient column of this thread
+    float aw[C::TPW3][4];
+#pragma unroll
+    for (int q = 0; q < C::TPW3; ++q) aw[q][0] = aw[q][1] = aw[q][2] = aw[q][3] = 0.f;
+    float ab = 0.f;  // threads [0, DOUT): db1[tid]; [DOUT, 2 DOUT): db2[tid - DOUT]
+
+    const int64_t n_tiles = (n + C::TM - 1) / C::TM;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * C::TM;
+        __syncthreads();
+        for (int i = tid; i < C::TM * (DIN / 4); i += C::NT) {
+            const int r = i / (DIN / 4), q = i % (DIN / 4);
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f), s = e;
+            if (row0 + r < n) {
+                e = ld_stream4(E + (row0 + r) * DIN + q * 4);
+                s = ld_stream4(S + (row0 + r) * DIN + q * 4);
+            }
+            *reinterpret_cast<float4*>(Es + r * C::SE + q * 4) = e;
+            *reinterpret_cast<float4*>(Ss + r * C::SE + q * 4) = s;
+        }
+        // ---- phase 1: normalise / dropout / LeakyReLU backward -> dL/dz1, dL/dz2 (all threads run it:
+        //      the row reduction is a shuffle over the CG threads of a row) ----
+#pragma unroll
+        for (int i = 0; i < C::RM; ++i) {
+            const int r = rg * C::RM + i;
+            const int64_t row = row0 + r;
+            const bool in_tile = r < C::TM;
+            float4 gg = make_float4(0.f, 0.f, 0.f, 0.f), y = gg;
+            uchar4 f = make_uchar4(0, 0, 0, 0);
+            float inv = 0.f;
+            if (in_tile && row < n) {
+                gg = ld_stream4(g_out + row * ld_gout + cg * 4);
+                y = ld_stream4(out + row * ld_out + cg * 4);
+                f = *reinterpret_cast<const uchar4*>(flags + row * DOUT + cg * 4);
+                inv = inv_norm[row];
+            }
+            float tt = gg.x * y.x + gg.y * y.y + gg.z * y.z + gg.w * y.w;
+#pragma unroll
+            for (int o = 1; o < C::CG; o <<= 1) tt += __shfl_xor_sync(kFull, tt, o);
+            if (inv < 0.f) {
+                tt = 0.f;
+                inv = -inv;
+            }
+            const float gx[4] = {inv * (gg.x - y.x * tt), inv * (gg.y - y.y * tt), inv * (gg.z - y.z * tt), inv * (gg.w - y.w * tt)};
+            const uint8_t fl[4] = {f.x, f.y, f.z, f.w};
+            float a1[4], a2[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float gd = (fl[j] & 4) ? gx[j] * keep_scale : 0.f;
+                a1[j] = (fl[j] & 1) ? gd : gd * KGAT_LEAKY_SLOPE;
+                a2[j] = (fl[j] & 2) ? gd : gd * KGAT_LEAKY_SLOPE;
+            }
+            if (in_tile) {
+                *reinterpret_cast<float4*>(G1 + r * C::SG + cg * 4) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+                *reinterpret_cast<float4*>(G2 + r * C::SG + cg * 4) = make_float4(a2[0], a2[1], a2[2], a2[3]);
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: input gradients  gu = G1 W1, gv = G2 W2  (M = rows, N = DIN, K = DOUT) ----
+#pragma unroll
+        for (int q = 0; q < C::TPW2; ++q) {
+            const int tl = warp + q * C::WARPS;
+            if (tl >= C::TILES2) break;
+            const int mt = tl % C::MT2, nt = tl / C::MT2;
+            float gu[4] = {0.f, 0.f, 0.f, 0.f}, gv[4] = {0.f, 0.f, 0.f, 0.f};
+            const float* a1p = G1 + (mt * 16 + g) * C::SG + t;
+            const float* a2p = G2 + (mt * 16 + g) * C::SG + t;
+#pragma unroll 2
+            for (int cs = 0; cs < DOUT / 8; ++cs) {
+                uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
+                const int wrow = (cs * 8 + t) * C::SW + nt * 8 + g;  // B[k = c][n = k_in] = W[c][k_in]
+                split_tf32(a1p[cs * 8], ah[0], al[0]);
+                split_tf32(a1p[cs * 8 + 8 * C::SG], ah[1], al[1]);
+                split_tf32(a1p[cs * 8 + 4], ah[2], al[2]);
+                split_tf32(a1p[cs * 8 + 8 * C::SG + 4], ah[3], al[3]);
+                split_tf32(W1s[wrow], bh0, bl0);
+                split_tf32(W1s[wrow + 4 * C::SW], bh1, bl1);
+                mma_3x(gu, ah, al, bh0, bh1, bl0, bl1);
+                split_tf32(a2p[cs * 8], ah[0], al[0]);
+                split_tf32(a2p[cs * 8 + 8 * C::SG], ah[1], al[1]);
+                split_tf32(a2p[cs * 8 + 4], ah[2], al[2]);
+                split_tf32(a2p[cs * 8 + 8 * C::SG + 4], ah[3], al[3]);
+                split_tf32(W2s[wrow], bh0, bl0);
+                split_tf32(W2s[wrow + 4 * C::SW], bh1, bl1);
+                mma_3x(gv, ah, al, bh0, bh1, bl0, bl1);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = mt * 16 + g + 8 * h;
+                const int64_t row = row0 + r;
+                if (row < n) {
+                    const int k = nt * 8 + 2 * t;
+                    const float2 e = *reinterpret_cast<const float2*>(Es + r * C::SE + k);
+                    const float2 s = *reinterpret_cast<const float2*>(Ss + r * C::SE + k);
+                    // u = E + S, v = E * S:  dS = gu + gv * E,  dE = gu + gv * S
+                    *reinterpret_cast<float2*>(g_S + row * DIN + k) =
+                        make_float2(fmaf(gv[2 * h], e.x, gu[2 * h]), fmaf(gv[2 * h + 1], e.y, gu[2 * h + 1]));
+                    *reinterpret_cast<float2*>(g_E + row * DIN + k) =
+                        make_float2(fmaf(gv[2 * h], s.x, gu[2 * h]), fmaf(gv[2 * h + 1], s.y, gu[2 * h + 1]));
+                }
+            }
+        }
+
+        // ---- phase 3: weight gradients  dW1 += G1^T (E+S),  dW2 += G2^T (E*S)  (M = c, N = k_in, K = rows).
+        //      The k index j of an 8-row step maps to row 2j (j<4) / 2(j-4)+1 (j>=4): with strides == 4 mod 32
+        //      this permutation makes both fragment reads bank-conflict free; A and B use the same map. ----
+#pragma unroll
+        for (int q = 0; q < C::TPW3; ++q) {
+            const int tl = warp + q * C::WARPS;
+            if (tl >= C::TILES3) break;
+            const int mat = tl / (C::MT3 * C::NT3);
+            const int rem = tl % (C::MT3 * C::NT3);
+            const int mt = rem % C::MT3, nt = rem / C::MT3;
+            const float* Gm = mat == 0 ? G1 : G2;
+#pragma unroll 2
+            for (int rs = 0; rs < C::TM / 8; ++rs) {
+                const int ra = rs * 8 + 2 * t;      // k = t      -> row 2t
+                const int rb = rs * 8 + 2 * t + 1;  // k = t + 4  -> row 2t + 1
+                uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
+                split_tf32(Gm[ra * C::SG + mt * 16 + g], ah[0], al[0]);
+                split_tf32(Gm[ra * C::SG + mt * 16 + g + 8], ah[1], al[1]);
+                split_tf32(Gm[rb * C::SG + mt * 16 + g], ah[2], al[2]);
+                split_tf32(Gm[rb * C::SG + mt * 16 + g + 8], ah[3], al[3]);
+                const float e0 = Es[ra * C::SE + nt * 8 + g], s0 = Ss[ra * C::SE + nt * 8 + g];
+                const float e1 = Es[rb * C::SE + nt * 8 + g], s1 = Ss[rb * C::SE + nt * 8 + g];
+                split_tf32(mat == 0 ? e0 + s0 : e0 * s0, bh0, bl0);
+                split_tf32(mat == 0 ? e1 + s1 : e1 * s1, bh1, bl1);
+                mma_3x(aw[q], ah, al, bh0, bh1, bl0, bl1);
+            }
+        }
+        if (tid < 2 * DOUT) {
+            const float* Gm = tid < DOUT ? G1 : G2;
+            const int c = tid < DOUT ? tid : tid - DOUT;
+            float sacc = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < C::TM; ++r) sacc += Gm[r * C::SG + c];
+            ab += sacc;
+        }
+    }
+
+    // per-CTA partials: [dW1 (DOUT x DIN)][dW2][db1 (DOUT)][db2]
+    float* p = partials + (int64_t)blockIdx.x * (2 * DIN * DOUT + 2 * DOUT);
+#pragma unroll
+    for (int q = 0; q < C::TPW3; ++q) {
+        const int tl = warp + q * C::WARPS;
+        if (tl >= C::TILES3) break;
+        const int mat = tl / (C::MT3 * C::NT3);
+        const int rem = tl % (C::MT3 * C::NT3);
+        const int mt = rem % C::MT3, nt = rem / C::MT3;
+        float* dst = p + mat * DIN * DOUT;
+        const int c = mt * 16 + g, k = nt * 8 + 2 * t;
+        *reinterpret_cast<float2*>(dst + c * DIN + k) = make_float2(aw[q][0], aw[q][1]);
+        *reinterpret_cast<float2*>(dst + (c + 8) * DIN + k) = make_float2(aw[q][2], aw[q][3]);
+    }
+    if (tid < 2 * DOUT) p[2 * DIN * DOUT + tid] = ab;
+}
+
+inline int grid_for(int64_t n, int tm, size_t smem_bytes) {
+    const int64_t tiles = (n + tm - 1) / tm;
+    int per_sm = (int)(220 * 1024 / (smem_bytes + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 3) per_sm = 3;
+    const int64_t cap = (int64_t)sm_count() * per_sm;
+    return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+}
+
+template <int DIN, int DOUT>
+int launch_fwd(const float* E, const float* S, int64_t n, const float* W1, const float* b1, const float* W2, const float* b2,
+               float p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits, float* out, int64_t ld_out,
+               float* inv_norm, uint8_t* flags, cudaStream_t stream) {
+    using C = FwdCfg<DIN, DOUT>;
+    static bool configured = false;
+    if (!configured) {
+        KGAT_CUDA_TRY(cudaFuncSetAttribute(biagg_fwd_mma_kernel<DIN, DOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
+        configured = true;
+    }
+    biagg_fwd_mma_kernel<DIN, DOUT><<<grid_for(n, C::TM, C::smem), C::NT, C::smem, stream>>>(E, S, n, W1, b1, W2, b2, p, seed, offset, seed_dev,
+                                                                                         keep_bits, out, ld_out, inv_norm, flags);
+    return check_launch();
+}
+
+template <int DIN, int DOUT>
+int launch_bwd(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm, const uint8_t* flags,
+               const float* E, const float* S, int64_t n, const float* W1, const float* W2, float p, float* g_S, float* g_E,
+               float* partials, int n_ctas, cudaStream_t stream) {
+    using C = BwdCfg<DIN, DOUT>;
+    static bool configured = false;
+    if (!configured) {
+        KGAT_CUDA_TRY(cudaFuncSetAttribute(biagg_bwd_mma_kernel<DIN, DOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
+        configured = true;
+    }
+    biagg_bwd_mma_kernel<DIN, DOUT><<<n_ctas, C::NT, C::smem, stream>>>(g_out, ld_gout, out, ld_out, inv_norm, flags, E, S, n, W1, W2, p, g_S,
+                                                                    g_E, partials);
+    return check_launch();
+}
+
+}  // namespace mma
+
+#define KGAT_MMA_DISPATCH(DIN_, DOUT_, CALL)                           \
+    do {                                                               \
+        const int key__ = (DIN_) * 1000 + (DOUT_);                     \
+        switch (key__) {                                               \
+            case 16016: { constexpr int DI = 16, DO = 16; CALL; }      \
+            case 32016: { constexpr int DI = 32, DO = 16; CALL; }      \
+            case 32032: { constexpr int DI = 32, DO = 32; CALL; }      \
+            case 64016: { constexpr int DI = 64, DO = 16; CALL; }      \
+            case 64032: { constexpr int DI = 64, DO = 32; CALL; }      \
+            case 64064: { constexpr int DI = 64, DO = 64; CALL; }      \
+            case 128064: { constexpr int DI = 128, DO = 64; CALL; }    \
+            case 128128: { constexpr int DI = 128, DO = 128; CALL; }   \
+            default: return KGAT_ERR_UNSUPPORTED;                      \
+        }                                                              \
+    } while (0)
+
+int biagg_mma_forward(const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* b1, const float* W2,
+                      const float* b2, float p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits,
+                      float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, cudaStream_t stream) {
+    KGAT_MMA_DISPATCH(d_in, d_out, return (mma::launch_fwd<DI, DO>(E, S, n, W1, b1, W2, b2, p, seed, offset, seed_dev, keep_bits, out, ld_out,
+                                                                   inv_norm, flags, stream)));
+}
+
+int biagg_mma_backward_ctas(int64_t n, int d_in, int d_out) {
+    KGAT_MMA_DISPATCH(d_in, d_out, return (mma::grid_for(n, mma::BwdCfg<DI, DO>::TM, mma::BwdCfg<DI, DO>::smem)));
+}
+
+int biagg_mma_backward(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm, const uint8_t* flags,
+                       const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* W2, float p, float* g_S,
+                       float* g_E, float* partials, int n_ctas, cudaStream_t stream) {
+    KGAT_MMA_DISPATCH(d_in, d_out, return (mma::launch_bwd<DI, DO>(g_out, ld_gout, out, ld_out, inv_norm, flags, E, S, n, W1, W2, p, g_S, g_E,
+                                                                   partials, n_ctas, stream)));
+}
+
+}  // namespace kgat
