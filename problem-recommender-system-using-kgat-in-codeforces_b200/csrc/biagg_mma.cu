@@ -23,7 +23,7 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 }
 // D += A (16x8, row) * B (8x8, col), TF32 inputs, fp32 accumulate
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -108,27 +108,39 @@ __global__ void __launch_bounds__(256) biagg_fwd_mma_kernel(
         }
         const float* ua = Us + (mt * 16 + g) * C::SE + t;
         const float* va = Vs + (mt * 16 + g) * C::SE + t;
-#pragma unroll 2
+        // The three TF32 terms of one accumulator are dependent MMAs: issue each term for ALL n-tiles of the
+        // warp before the next term so dependent instructions are NTW MMAs apart (hides the HMMA latency).
         for (int ks = 0; ks < DIN / 8; ++ks) {
-            uint32_t uh[4], ul[4], vh[4], vl[4];
-            split_tf32(ua[ks * 8], uh[0], ul[0]);
-            split_tf32(ua[ks * 8 + 8 * C::SE], uh[1], ul[1]);
-            split_tf32(ua[ks * 8 + 4], uh[2], ul[2]);
-            split_tf32(ua[ks * 8 + 8 * C::SE + 4], uh[3], ul[3]);
-            split_tf32(va[ks * 8], vh[0], vl[0]);
-            split_tf32(va[ks * 8 + 8 * C::SE], vh[1], vl[1]);
-            split_tf32(va[ks * 8 + 4], vh[2], vl[2]);
-            split_tf32(va[ks * 8 + 8 * C::SE + 4], vh[3], vl[3]);
 #pragma unroll
-            for (int j = 0; j < C::NTW; ++j) {
-                const int wrow = ((nt0 + j) * 8 + g) * C::SW + ks * 8 + t;
-                uint32_t bh0, bl0, bh1, bl1;
-                split_tf32(W1s[wrow], bh0, bl0);
-                split_tf32(W1s[wrow + 4], bh1, bl1);
-                mma_3x(z1[j], uh, ul, bh0, bh1, bl0, bl1);
-                split_tf32(W2s[wrow], bh0, bl0);
-                split_tf32(W2s[wrow + 4], bh1, bl1);
-                mma_3x(z2[j], vh, vl, bh0, bh1, bl0, bl1);
+            for (int mat = 0; mat < 2; ++mat) {
+                const float* ap = mat == 0 ? ua : va;
+                const float* Wm = mat == 0 ? W1s : W2s;
+                uint32_t ah[4], al[4], bh0[C::NTW], bh1[C::NTW], bl0[C::NTW], bl1[C::NTW];
+                split_tf32(ap[ks * 8], ah[0], al[0]);
+                split_tf32(ap[ks * 8 + 8 * C::SE], ah[1], al[1]);
+                split_tf32(ap[ks * 8 + 4], ah[2], al[2]);
+                split_tf32(ap[ks * 8 + 8 * C::SE + 4], ah[3], al[3]);
+#pragma unroll
+                for (int j = 0; j < C::NTW; ++j) {
+                    const int wrow = ((nt0 + j) * 8 + g) * C::SW + ks * 8 + t;
+                    split_tf32(Wm[wrow], bh0[j], bl0[j]);
+                    split_tf32(Wm[wrow + 4], bh1[j], bl1[j]);
+                }
+                if (mat == 0) {
+#pragma unroll
+                    for (int j = 0; j < C::NTW; ++j) mma_tf32(z1[j], al, bh0[j], bh1[j]);
+#pragma unroll
+                    for (int j = 0; j < C::NTW; ++j) mma_tf32(z1[j], ah, bl0[j], bl1[j]);
+#pragma unroll
+                    for (int j = 0; j < C::NTW; ++j) mma_tf32(z1[j], ah, bh0[j], bh1[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < C::NTW; ++j) mma_tf32(z2[j], al, bh0[j], bh1[j]);
+#pragma unroll
+                    for (int j = 0; j < C::NTW; ++j) mma_tf32(z2[j], ah, bl0[j], bl1[j]);
+#pragma unroll
+                    for (int j = 0; j < C::NTW; ++j) mma_tf32(z2[j], ah, bh0[j], bh1[j]);
+                }
             }
         }
 
@@ -316,77 +328,109 @@ __global__ void __launch_bounds__(BwdCfg<DIN, DOUT>::NT) biagg_bwd_mma_kernel(
         }
         __syncthreads();
 
-        // ---- phase 2: input gradients  gu = G1 W1, gv = G2 W2  (M = rows, N = DIN, K = DOUT) ----
+        // ---- phase 2: input gradients  gu = G1 W1, gv = G2 W2  (M = rows, N = DIN, K = DOUT).
+        //      A warp's TPW2 output tiles share the m-tile (WARPS % MT2 == 0), so the G fragments are split once
+        //      per c-step and each TF32 term is issued for all 2*TPW2 accumulators before the next term. ----
+        {
+            static_assert(C::WARPS % C::MT2 == 0 && C::TILES2 % C::WARPS == 0, "phase-2 mapping");
+            const int mt = warp % C::MT2;
+            const int ntb = warp / C::MT2;                 // first n-tile of this warp
+            constexpr int NSTEP = C::WARPS / C::MT2;       // n-tile stride between the warp's tiles
+            float gu[C::TPW2][4], gv[C::TPW2][4];
 #pragma unroll
-        for (int q = 0; q < C::TPW2; ++q) {
-            const int tl = warp + q * C::WARPS;
-            if (tl >= C::TILES2) break;
-            const int mt = tl % C::MT2, nt = tl / C::MT2;
-            float gu[4] = {0.f, 0.f, 0.f, 0.f}, gv[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int q = 0; q < C::TPW2; ++q) gu[q][0] = gu[q][1] = gu[q][2] = gu[q][3] = gv[q][0] = gv[q][1] = gv[q][2] = gv[q][3] = 0.f;
             const float* a1p = G1 + (mt * 16 + g) * C::SG + t;
             const float* a2p = G2 + (mt * 16 + g) * C::SG + t;
-#pragma unroll 2
             for (int cs = 0; cs < DOUT / 8; ++cs) {
-                uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
-                const int wrow = (cs * 8 + t) * C::SW + nt * 8 + g;  // B[k = c][n = k_in] = W[c][k_in]
-                split_tf32(a1p[cs * 8], ah[0], al[0]);
-                split_tf32(a1p[cs * 8 + 8 * C::SG], ah[1], al[1]);
-                split_tf32(a1p[cs * 8 + 4], ah[2], al[2]);
-                split_tf32(a1p[cs * 8 + 8 * C::SG + 4], ah[3], al[3]);
-                split_tf32(W1s[wrow], bh0, bl0);
-                split_tf32(W1s[wrow + 4 * C::SW], bh1, bl1);
-                mma_3x(gu, ah, al, bh0, bh1, bl0, bl1);
-                split_tf32(a2p[cs * 8], ah[0], al[0]);
-                split_tf32(a2p[cs * 8 + 8 * C::SG], ah[1], al[1]);
-                split_tf32(a2p[cs * 8 + 4], ah[2], al[2]);
-                split_tf32(a2p[cs * 8 + 8 * C::SG + 4], ah[3], al[3]);
-                split_tf32(W2s[wrow], bh0, bl0);
-                split_tf32(W2s[wrow + 4 * C::SW], bh1, bl1);
-                mma_3x(gv, ah, al, bh0, bh1, bl0, bl1);
+#pragma unroll
+                for (int mat = 0; mat < 2; ++mat) {
+                    const float* ap = mat == 0 ? a1p : a2p;
+                    const float* Wm = mat == 0 ? W1s : W2s;
+                    uint32_t ah[4], al[4], bh0[C::TPW2], bh1[C::TPW2], bl0[C::TPW2], bl1[C::TPW2];
+                    split_tf32(ap[cs * 8], ah[0], al[0]);
+                    split_tf32(ap[cs * 8 + 8 * C::SG], ah[1], al[1]);
+                    split_tf32(ap[cs * 8 + 4], ah[2], al[2]);
+                    split_tf32(ap[cs * 8 + 8 * C::SG + 4], ah[3], al[3]);
+#pragma unroll
+                    for (int q = 0; q < C::TPW2; ++q) {
+                        const int wrow = (cs * 8 + t) * C::SW + (ntb + q * NSTEP) * 8 + g;  // B[k = c][n = k_in] = W[c][k_in]
+                        split_tf32(Wm[wrow], bh0[q], bl0[q]);
+                        split_tf32(Wm[wrow + 4 * C::SW], bh1[q], bl1[q]);
+                    }
+                    if (mat == 0) {
+#pragma unroll
+                        for (int q = 0; q < C::TPW2; ++q) mma_tf32(gu[q], al, bh0[q], bh1[q]);
+#pragma unroll
+                        for (int q = 0; q < C::TPW2; ++q) mma_tf32(gu[q], ah, bl0[q], bl1[q]);
+#pragma unroll
+                        for (int q = 0; q < C::TPW2; ++q) mma_tf32(gu[q], ah, bh0[q], bh1[q]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < C::TPW2; ++q) mma_tf32(gv[q], al, bh0[q], bh1[q]);
+#pragma unroll
+                        for (int q = 0; q < C::TPW2; ++q) mma_tf32(gv[q], ah, bl0[q], bl1[q]);
+#pragma unroll
+                        for (int q = 0; q < C::TPW2; ++q) mma_tf32(gv[q], ah, bh0[q], bh1[q]);
+                    }
+                }
             }
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int r = mt * 16 + g + 8 * h;
-                const int64_t row = row0 + r;
-                if (row < n) {
-                    const int k = nt * 8 + 2 * t;
-                    const float2 e = *reinterpret_cast<const float2*>(Es + r * C::SE + k);
-                    const float2 s = *reinterpret_cast<const float2*>(Ss + r * C::SE + k);
-                    // u = E + S, v = E * S:  dS = gu + gv * E,  dE = gu + gv * S
-                    *reinterpret_cast<float2*>(g_S + row * DIN + k) =
-                        make_float2(fmaf(gv[2 * h], e.x, gu[2 * h]), fmaf(gv[2 * h + 1], e.y, gu[2 * h + 1]));
-                    *reinterpret_cast<float2*>(g_E + row * DIN + k) =
-                        make_float2(fmaf(gv[2 * h], s.x, gu[2 * h]), fmaf(gv[2 * h + 1], s.y, gu[2 * h + 1]));
+            for (int q = 0; q < C::TPW2; ++q) {
+                const int nt = ntb + q * NSTEP;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = mt * 16 + g + 8 * h;
+                    const int64_t row = row0 + r;
+                    if (row < n) {
+                        const int k = nt * 8 + 2 * t;
+                        const float2 e = *reinterpret_cast<const float2*>(Es + r * C::SE + k);
+                        const float2 s2 = *reinterpret_cast<const float2*>(Ss + r * C::SE + k);
+                        // u = E + S, v = E * S:  dS = gu + gv * E,  dE = gu + gv * S
+                        *reinterpret_cast<float2*>(g_S + row * DIN + k) =
+                            make_float2(fmaf(gv[q][2 * h], e.x, gu[q][2 * h]), fmaf(gv[q][2 * h + 1], e.y, gu[q][2 * h + 1]));
+                        *reinterpret_cast<float2*>(g_E + row * DIN + k) =
+                            make_float2(fmaf(gv[q][2 * h], s2.x, gu[q][2 * h]), fmaf(gv[q][2 * h + 1], s2.y, gu[q][2 * h + 1]));
+                    }
                 }
             }
         }
 
         // ---- phase 3: weight gradients  dW1 += G1^T (E+S),  dW2 += G2^T (E*S)  (M = c, N = k_in, K = rows).
         //      The k index j of an 8-row step maps to row 2j (j<4) / 2(j-4)+1 (j>=4): with strides == 4 mod 32
-        //      this permutation makes both fragment reads bank-conflict free; A and B use the same map. ----
+        //      this permutation makes both fragment reads bank-conflict free; A and B use the same map.
+        //      Tile list: tl = warp + q*WARPS over [mat][nt][mt]; each TF32 term is issued for all of the
+        //      warp's TPW3 accumulators before the next term. ----
+        for (int rs = 0; rs < C::TM / 8; ++rs) {
+            const int ra = rs * 8 + 2 * t;      // k = t      -> row 2t
+            const int rb = rs * 8 + 2 * t + 1;  // k = t + 4  -> row 2t + 1
+            uint32_t ah[C::TPW3][4], al[C::TPW3][4], bh0[C::TPW3], bh1[C::TPW3], bl0[C::TPW3], bl1[C::TPW3];
 #pragma unroll
-        for (int q = 0; q < C::TPW3; ++q) {
-            const int tl = warp + q * C::WARPS;
-            if (tl >= C::TILES3) break;
-            const int mat = tl / (C::MT3 * C::NT3);
-            const int rem = tl % (C::MT3 * C::NT3);
-            const int mt = rem % C::MT3, nt = rem / C::MT3;
-            const float* Gm = mat == 0 ? G1 : G2;
-#pragma unroll 2
-            for (int rs = 0; rs < C::TM / 8; ++rs) {
-                const int ra = rs * 8 + 2 * t;      // k = t      -> row 2t
-                const int rb = rs * 8 + 2 * t + 1;  // k = t + 4  -> row 2t + 1
-                uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
-                split_tf32(Gm[ra * C::SG + mt * 16 + g], ah[0], al[0]);
-                split_tf32(Gm[ra * C::SG + mt * 16 + g + 8], ah[1], al[1]);
-                split_tf32(Gm[rb * C::SG + mt * 16 + g], ah[2], al[2]);
-                split_tf32(Gm[rb * C::SG + mt * 16 + g + 8], ah[3], al[3]);
-                const float e0 = Es[ra * C::SE + nt * 8 + g], s0 = Ss[ra * C::SE + nt * 8 + g];
-                const float e1 = Es[rb * C::SE + nt * 8 + g], s1 = Ss[rb * C::SE + nt * 8 + g];
-                split_tf32(mat == 0 ? e0 + s0 : e0 * s0, bh0, bl0);
-                split_tf32(mat == 0 ? e1 + s1 : e1 * s1, bh1, bl1);
-                mma_3x(aw[q], ah, al, bh0, bh1, bl0, bl1);
+            for (int q = 0; q < C::TPW3; ++q) {
+                const int tl = warp + q * C::WARPS;
+                if (tl < C::TILES3) {
+                    const int mat = tl / (C::MT3 * C::NT3);
+                    const int rem = tl % (C::MT3 * C::NT3);
+                    const int mt = rem % C::MT3, nt = rem / C::MT3;
+                    const float* Gm = mat == 0 ? G1 : G2;
+                    split_tf32(Gm[ra * C::SG + mt * 16 + g], ah[q][0], al[q][0]);
+                    split_tf32(Gm[ra * C::SG + mt * 16 + g + 8], ah[q][1], al[q][1]);
+                    split_tf32(Gm[rb * C::SG + mt * 16 + g], ah[q][2], al[q][2]);
+                    split_tf32(Gm[rb * C::SG + mt * 16 + g + 8], ah[q][3], al[q][3]);
+                    const float e0 = Es[ra * C::SE + nt * 8 + g], s0 = Ss[ra * C::SE + nt * 8 + g];
+                    const float e1 = Es[rb * C::SE + nt * 8 + g], s1 = Ss[rb * C::SE + nt * 8 + g];
+                    split_tf32(mat == 0 ? e0 + s0 : e0 * s0, bh0[q], bl0[q]);
+                    split_tf32(mat == 0 ? e1 + s1 : e1 * s1, bh1[q], bl1[q]);
+                }
             }
+#pragma unroll
+            for (int q = 0; q < C::TPW3; ++q)
+                if (warp + q * C::WARPS < C::TILES3) mma_tf32(aw[q], al[q], bh0[q], bh1[q]);
+#pragma unroll
+            for (int q = 0; q < C::TPW3; ++q)
+                if (warp + q * C::WARPS < C::TILES3) mma_tf32(aw[q], ah[q], bl0[q], bl1[q]);
+#pragma unroll
+            for (int q = 0; q < C::TPW3; ++q)
+                if (warp + q * C::WARPS < C::TILES3) mma_tf32(aw[q], ah[q], bh0[q], bh1[q]);
         }
         if (tid < 2 * DOUT) {
             const float* Gm = tid < DOUT ? G1 : G2;
