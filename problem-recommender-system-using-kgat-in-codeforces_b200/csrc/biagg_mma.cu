@@ -39,17 +39,19 @@ __device__ __forceinline__ void mma_3x(float (&d)[4], const uint32_t (&ah)[4], c
 template <int DIN, int DOUT>
 struct FwdCfg {
     static constexpr bool kBig = (DIN > 64) || (DOUT > 64);
+    static constexpr bool kPreSplit = !kBig;       // weights stored as (hi, lo) TF32 pairs in shared memory
     static constexpr int NT = 256;                 // 8 warps
-    static constexpr int TM = kBig ? 64 : 128;     // rows per CTA tile
+    static constexpr int TM = 64;                  // rows per CTA tile
     static constexpr int WARPS = NT / 32;
     static constexpr int MT = TM / 16;             // m-tiles per CTA tile
     static constexpr int NTL = DOUT / 8;           // n-tiles
-    static constexpr int WPM = WARPS / MT;         // warps sharing one m-tile (1, or 2 for the big shapes)
+    static constexpr int WPM = WARPS / MT;         // warps sharing one m-tile (2): each takes half of the n-tiles
     static constexpr int NTW = NTL / WPM;          // n-tiles per warp
     static constexpr int SE = DIN + 4;             // smem strides == 4 mod 32: conflict-free fragment reads
-    static constexpr int SW = DIN + 4;
-    static_assert(WARPS % MT == 0 && NTL % WPM == 0, "bad warp mapping");
-    static constexpr size_t smem = sizeof(float) * (2 * DOUT * SW + 2 * TM * SE + (WPM > 1 ? TM * WPM : 0));
+    static constexpr int SW = DIN + 4;             // (also == 4 mod 16 for the 8-byte (hi, lo) pairs)
+    static constexpr int WELEM = kPreSplit ? 2 : 1;
+    static_assert(WARPS % MT == 0 && NTL % WPM == 0 && NTW >= 1, "bad warp mapping");
+    static constexpr size_t smem = sizeof(float) * (2 * DOUT * SW * WELEM + 2 * TM * SE + TM * WPM);
 };
 
 template <int DIN, int DOUT>
@@ -61,18 +63,29 @@ __global__ void __launch_bounds__(256) biagg_fwd_mma_kernel(
     using C = FwdCfg<DIN, DOUT>;
     extern __shared__ __align__(16) float smem[];
     if (seed_dev != nullptr) seed += seed_dev[0] * 0x9E3779B97F4A7C15ull;
-    float* W1s = smem;                      // [DOUT][SW]
-    float* W2s = W1s + DOUT * C::SW;
-    float* Us = W2s + DOUT * C::SW;         // [TM][SE]  E + S
+    float* W1s = smem;                      // [DOUT][SW] (x2 when pre-split: (hi, lo) pairs)
+    float* W2s = W1s + DOUT * C::SW * C::WELEM;
+    float* Us = W2s + DOUT * C::SW * C::WELEM;  // [TM][SE]  E + S
     float* Vs = Us + C::TM * C::SE;         // [TM][SE]  E * S
-    float* Red = Vs + C::TM * C::SE;        // [TM][WPM] partial row sums (only when WPM > 1)
+    float* Red = Vs + C::TM * C::SE;        // [TM][WPM] partial row sums
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
 
-    for (int i = tid; i < DOUT * (DIN / 4); i += C::NT) {
-        const int c = i / (DIN / 4), q = i % (DIN / 4);
-        *reinterpret_cast<float4*>(W1s + c * C::SW + q * 4) = __ldg(reinterpret_cast<const float4*>(W1 + c * DIN) + q);
-        *reinterpret_cast<float4*>(W2s + c * C::SW + q * 4) = __ldg(reinterpret_cast<const float4*>(W2 + c * DIN) + q);
+    if (C::kPreSplit) {
+        for (int i = tid; i < DOUT * DIN; i += C::NT) {
+            const int c = i / DIN, k = i % DIN;
+            uint32_t hi, lo;
+            split_tf32(W1[i], hi, lo);
+            reinterpret_cast<uint2*>(W1s)[c * C::SW + k] = make_uint2(hi, lo);
+            split_tf32(W2[i], hi, lo);
+            reinterpret_cast<uint2*>(W2s)[c * C::SW + k] = make_uint2(hi, lo);
+        }
+    } else {
+        for (int i = tid; i < DOUT * (DIN / 4); i += C::NT) {
+            const int c = i / (DIN / 4), q = i % (DIN / 4);
+            *reinterpret_cast<float4*>(W1s + c * C::SW + q * 4) = __ldg(reinterpret_cast<const float4*>(W1 + c * DIN) + q);
+            *reinterpret_cast<float4*>(W2s + c * C::SW + q * 4) = __ldg(reinterpret_cast<const float4*>(W2 + c * DIN) + q);
+        }
     }
     const int mt = warp % C::MT;            // m-tile of this warp
     const int nw = warp / C::MT;            // which slice of the n-tiles
@@ -123,8 +136,14 @@ __global__ void __launch_bounds__(256) biagg_fwd_mma_kernel(
 #pragma unroll
                 for (int j = 0; j < C::NTW; ++j) {
                     const int wrow = ((nt0 + j) * 8 + g) * C::SW + ks * 8 + t;
-                    split_tf32(Wm[wrow], bh0[j], bl0[j]);
-                    split_tf32(Wm[wrow + 4], bh1[j], bl1[j]);
+                    if (C::kPreSplit) {
+                        const uint2 p0 = reinterpret_cast<const uint2*>(Wm)[wrow];
+                        const uint2 p1 = reinterpret_cast<const uint2*>(Wm)[wrow + 4];
+                        bh0[j] = p0.x; bl0[j] = p0.y; bh1[j] = p1.x; bl1[j] = p1.y;
+                    } else {
+                        split_tf32(Wm[wrow], bh0[j], bl0[j]);
+                        split_tf32(Wm[wrow + 4], bh1[j], bl1[j]);
+                    }
                 }
                 if (mat == 0) {
 #pragma unroll
@@ -184,7 +203,7 @@ __global__ void __launch_bounds__(256) biagg_fwd_mma_kernel(
             ss[h] += __shfl_xor_sync(kFull, ss[h], 1);
             ss[h] += __shfl_xor_sync(kFull, ss[h], 2);
         }
-        if (C::WPM > 1) {  // rows are split over WPM warps: combine the partial sums through smem
+        {  // rows are split over WPM warps: combine the partial sums through smem
             if (t == 0) {
                 Red[(mt * 16 + g) * C::WPM + nw] = ss[0];
                 Red[(mt * 16 + g + 8) * C::WPM + nw] = ss[1];
@@ -204,13 +223,14 @@ __global__ void __launch_bounds__(256) biagg_fwd_mma_kernel(
             if (row >= n) continue;
             const float nrm = sqrtf(ss[h]);
             const float denom = fmaxf(nrm, KGAT_NORM_EPS);
+            const float rinv = 1.f / denom;  // one IEEE division per row; x * rinv is within 1 ulp of x / denom
 #pragma unroll
             for (int j = 0; j < C::NTW; ++j) {
                 const int c = (nt0 + j) * 8 + 2 * t;
-                *reinterpret_cast<float2*>(out + row * ld_out + c) = make_float2(x[h][j][0] / denom, x[h][j][1] / denom);
+                *reinterpret_cast<float2*>(out + row * ld_out + c) = make_float2(x[h][j][0] * rinv, x[h][j][1] * rinv);
                 if (flags != nullptr) *reinterpret_cast<uchar2*>(flags + row * DOUT + c) = make_uchar2(f[h][j][0], f[h][j][1]);
             }
-            if (inv_norm != nullptr && t == 0 && nw == 0) inv_norm[row] = nrm < KGAT_NORM_EPS ? -1.f / denom : 1.f / denom;
+            if (inv_norm != nullptr && t == 0 && nw == 0) inv_norm[row] = nrm < KGAT_NORM_EPS ? -rinv : rinv;
         }
     }
 }
@@ -403,7 +423,10 @@ __global__ void __launch_bounds__(BwdCfg<DIN, DOUT>::NT) biagg_bwd_mma_kernel(
         for (int rs = 0; rs < C::TM / 8; ++rs) {
             const int ra = rs * 8 + 2 * t;      // k = t      -> row 2t
             const int rb = rs * 8 + 2 * t + 1;  // k = t + 4  -> row 2t + 1
-            uint32_t ah[C::TPW3][4], al[C::TPW3][4], bh0[C::TPW3], bh1[C::TPW3], bl0[C::TPW3], bl1[C::TPW3];
+            uint32_t bh0[C::TPW3], bh1[C::TPW3], bl0[C::TPW3], bl1[C::TPW3];
+            // the warp's tiles of one matrix share the m-tile when WARPS % MT3 == 0: split G once per matrix
+            constexpr bool kShareA = (C::WARPS % C::MT3 == 0) && (C::TPW3 % 2 == 0) && (C::TILES3 % C::WARPS == 0);
+            uint32_t ah[kShareA ? 2 : C::TPW3][4], al[kShareA ? 2 : C::TPW3][4];
 #pragma unroll
             for (int q = 0; q < C::TPW3; ++q) {
                 const int tl = warp + q * C::WARPS;
@@ -412,10 +435,13 @@ __global__ void __launch_bounds__(BwdCfg<DIN, DOUT>::NT) biagg_bwd_mma_kernel(
                     const int rem = tl % (C::MT3 * C::NT3);
                     const int mt = rem % C::MT3, nt = rem / C::MT3;
                     const float* Gm = mat == 0 ? G1 : G2;
-                    split_tf32(Gm[ra * C::SG + mt * 16 + g], ah[q][0], al[q][0]);
-                    split_tf32(Gm[ra * C::SG + mt * 16 + g + 8], ah[q][1], al[q][1]);
-                    split_tf32(Gm[rb * C::SG + mt * 16 + g], ah[q][2], al[q][2]);
-                    split_tf32(Gm[rb * C::SG + mt * 16 + g + 8], ah[q][3], al[q][3]);
+                    const int ai = kShareA ? (q / (C::TPW3 / 2)) : q;
+                    if (!kShareA || (q % (C::TPW3 / 2)) == 0) {
+                        split_tf32(Gm[ra * C::SG + mt * 16 + g], ah[ai][0], al[ai][0]);
+                        split_tf32(Gm[ra * C::SG + mt * 16 + g + 8], ah[ai][1], al[ai][1]);
+                        split_tf32(Gm[rb * C::SG + mt * 16 + g], ah[ai][2], al[ai][2]);
+                        split_tf32(Gm[rb * C::SG + mt * 16 + g + 8], ah[ai][3], al[ai][3]);
+                    }
                     const float e0 = Es[ra * C::SE + nt * 8 + g], s0 = Ss[ra * C::SE + nt * 8 + g];
                     const float e1 = Es[rb * C::SE + nt * 8 + g], s1 = Ss[rb * C::SE + nt * 8 + g];
                     split_tf32(mat == 0 ? e0 + s0 : e0 * s0, bh0[q], bl0[q]);
@@ -424,13 +450,13 @@ __global__ void __launch_bounds__(BwdCfg<DIN, DOUT>::NT) biagg_bwd_mma_kernel(
             }
 #pragma unroll
             for (int q = 0; q < C::TPW3; ++q)
-                if (warp + q * C::WARPS < C::TILES3) mma_tf32(aw[q], al[q], bh0[q], bh1[q]);
+                if (warp + q * C::WARPS < C::TILES3) mma_tf32(aw[q], al[kShareA ? (q / (C::TPW3 / 2)) : q], bh0[q], bh1[q]);
 #pragma unroll
             for (int q = 0; q < C::TPW3; ++q)
-                if (warp + q * C::WARPS < C::TILES3) mma_tf32(aw[q], ah[q], bl0[q], bl1[q]);
+                if (warp + q * C::WARPS < C::TILES3) mma_tf32(aw[q], ah[kShareA ? (q / (C::TPW3 / 2)) : q], bl0[q], bl1[q]);
 #pragma unroll
             for (int q = 0; q < C::TPW3; ++q)
-                if (warp + q * C::WARPS < C::TILES3) mma_tf32(aw[q], ah[q], bh0[q], bh1[q]);
+                if (warp + q * C::WARPS < C::TILES3) mma_tf32(aw[q], ah[kShareA ? (q / (C::TPW3 / 2)) : q], bh0[q], bh1[q]);
         }
         if (tid < 2 * DOUT) {
             const float* Gm = tid < DOUT ? G1 : G2;
