@@ -237,6 +237,23 @@ int kgat_adam_advance(int64_t* step_dev, double lr, double beta1, double beta2, 
 int kgat_adam_set_hyper(int64_t step, double lr, double beta1, double beta2, double eps, float* hyper_dev, void* stream);
 int kgat_adam_apply(const kgat_adam_tensors_t* t, const float* hyper_dev, void* stream);
 
+/* Lazy but exact Adam for a row-sparse phase (the KG phase: a TransR batch touches <= 3B of the N embedding
+ * rows, while torch.optim.Adam sweeps all N rows every step, model.py:414-419).  Each row carries the number
+ * of phase steps it is current to (row_step, int32, 0 at phase start = optimiser step s0, a device scalar so
+ * that captured graphs survive across phases).  A row is caught
+ * up -- the zero-gradient update replayed step by step with each step's own bias corrections from
+ * `table` ({lr/bc1_s, 1/sqrt(bc2_s)} for s = s0+1 .. s0+n_steps) -- when a batch is about to read it
+ * (catchup, before the forward; cur_step_dev = steps done), gets its real gradient after the backward
+ * (sparse_rows, after kgat_adam_advance; the gradient row is re-zeroed), and all rows are caught up at the
+ * end of the phase (flush).  Bit-identical to the dense sweep.  hyper_dev as written by kgat_adam_advance. */
+int kgat_adam_hyper_table(const int64_t* s0_dev, int32_t n_steps, double lr, double beta1, double beta2, float* table, void* stream);
+int kgat_adam_lazy_catchup(float* param, float* exp_avg, float* exp_avg_sq, int32_t* row_step, const int64_t* ids, int32_t n_ids,
+                           int32_t d, const int64_t* cur_step_dev, const int64_t* s0_dev, const float* table, const float* hyper_dev, void* stream);
+int kgat_adam_sparse_rows(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int32_t* row_step, const int64_t* ids,
+                          int32_t n_ids, int32_t d, const int64_t* cur_step_dev, const int64_t* s0_dev, const float* hyper_dev, void* stream);
+int kgat_adam_lazy_flush(float* param, float* exp_avg, float* exp_avg_sq, int32_t* row_step, int64_t n_rows, int32_t d,
+                         const int64_t* cur_step_dev, const int64_t* s0_dev, const float* table, const float* hyper_dev, void* stream);
+
 /* dst[0..elems) = src[(counter_dev[0] % n_batches) * elems + ...]: selects the current step's pre-sampled
  * id batch from a device-resident epoch array (counter = an optimiser step counter) so that a captured
  * CUDA graph of a training step replays through the whole epoch without host work. */

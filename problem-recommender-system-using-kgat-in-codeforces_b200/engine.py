@@ -67,7 +67,7 @@ class _AdamSlot:
 
 
 class TrainEngine:
-    def __init__(self, model: KGAT, cf_batch: int = CF_BATCH, kg_batch: int = KG_BATCH, use_graphs: bool = True):
+    def __init__(self, model: KGAT, cf_batch: int = CF_BATCH, kg_batch: int = KG_BATCH, use_graphs: bool = True, lazy_kg_adam: bool = True):
         if not hasattr(model, "_cf_optimizer"):
             raise RuntimeError("call model.build_optimizer(...) before creating a TrainEngine")
         self.model = model
@@ -90,6 +90,11 @@ class TrainEngine:
         self.cf_scratch = torch.empty(2 * cf_batch, dtype=f32, device=dev)
         self.kg_scratch = torch.empty(2 * kg_batch, dtype=f32, device=dev)
         self.kg_grads = [torch.zeros_like(p) for p in self.kg_params]
+        # lazy exact Adam for the embedding table in the KG phase (see csrc/adam.cu)
+        self.lazy_kg_adam = lazy_kg_adam
+        self.kg_row_step = torch.zeros(emb.shape[0], dtype=torch.int32, device=dev)
+        self.kg_s0 = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.kg_table = None
         self._resident: EpochData | None = None
         self._graphs: dict = {}
         self._graph_token = None
@@ -130,12 +135,50 @@ class TrainEngine:
         h, r, pt, nt = self.kg_ids[0], self.kg_ids[1], self.kg_ids[2], self.kg_ids[3]
         emb, rel, w = (p.detach() for p in self.kg_params)
         reg = float(m._regularization_params[1])
-        ops.transr_forward(emb, rel, w, h, r, pt, nt, reg, self.kg_loss, self.kg_scratch)
-        for g in self.kg_grads:
-            ops.fill_(g, 0.0)
-        ops.transr_backward(emb, rel, w, h, r, pt, nt, reg, self.kg_scratch, self.one, *self.kg_grads)
-        self.kg_adam.apply(self.kg_grads)
+        ad = self.kg_adam
+        if self.lazy_kg_adam:
+            tails = self.kg_ids[2:4].view(-1)  # positive + negative tails, contiguous
+            # rows this batch reads must first receive the zero-gradient updates they skipped
+            for ids in (h, tails):
+                ops.adam_lazy_catchup(emb, ad.exp_avg[0], ad.exp_avg_sq[0], self.kg_row_step, ids, ad.step_dev, self.kg_s0, self.kg_table, ad.hyper)
+            ops.transr_forward(emb, rel, w, h, r, pt, nt, reg, self.kg_loss, self.kg_scratch)
+            for g in self.kg_grads[1:]:
+                ops.fill_(g, 0.0)  # kg_grads[0] (embedding) stays zero outside the touched rows, re-zeroed by sparse_rows
+            ops.transr_backward(emb, rel, w, h, r, pt, nt, reg, self.kg_scratch, self.one, *self.kg_grads)
+            ops.adam_advance(ad.step_dev, ad.lr, ad.b1, ad.b2, ad.eps, ad.hyper)
+            ops.adam_apply([p.data for p in ad.params[1:]], self.kg_grads[1:], ad.exp_avg[1:], ad.exp_avg_sq[1:], ad.hyper)
+            for ids in (h, tails):
+                ops.adam_sparse_rows(emb, self.kg_grads[0], ad.exp_avg[0], ad.exp_avg_sq[0], self.kg_row_step, ids, ad.step_dev, self.kg_s0, ad.hyper)
+        else:
+            ops.transr_forward(emb, rel, w, h, r, pt, nt, reg, self.kg_loss, self.kg_scratch)
+            for g in self.kg_grads:
+                ops.fill_(g, 0.0)
+            ops.transr_backward(emb, rel, w, h, r, pt, nt, reg, self.kg_scratch, self.one, *self.kg_grads)
+            ad.apply(self.kg_grads)
         self.kg_loss_sum.add_(self.kg_loss)
+
+    def _kg_phase_begin(self, n_kg: int):
+        """Lazy Adam bookkeeping: phase origin = current optimiser step, per-step bias-correction table."""
+        if not self.lazy_kg_adam or n_kg == 0:
+            return
+        ad = self.kg_adam
+        self.kg_s0.copy_(ad.step_dev)
+        self.kg_row_step.zero_()
+        self.kg_grads[0].zero_()
+        need = 2 * (n_kg + 2)  # +2: the capture warm-up may run one extra (undone) step
+        if self.kg_table is None or self.kg_table.numel() < need:
+            self.kg_table = torch.empty(max(need, 2 * 16384), dtype=f32, device=self.dev)
+            self._graphs.pop(("kg", True), None)
+            self._graphs.pop(("kg", False), None)
+        ops.adam_hyper_table(self.kg_s0, self.kg_table.numel() // 2, ad.lr, ad.b1, ad.b2, self.kg_table)
+        ops.adam_set_hyper(1, ad.lr, ad.b1, ad.b2, ad.eps, ad.hyper)  # constants (1-b1, b2, 1-b2, eps) for the first catch-up
+
+    def _kg_phase_end(self, n_kg: int):
+        if not self.lazy_kg_adam or n_kg == 0:
+            return
+        ad = self.kg_adam
+        emb = self.kg_params[0].detach()
+        ops.adam_lazy_flush(emb, ad.exp_avg[0], ad.exp_avg_sq[0], self.kg_row_step, ad.step_dev, self.kg_s0, self.kg_table, ad.hyper)
 
     # ------------------------------------------------------------------------------------------
     # capture / replay
@@ -158,6 +201,7 @@ class TrainEngine:
             adam = self.cf_adam if kind == "cf" else self.kg_adam
             snap = adam.snapshot()
             sums = (self.cf_loss_sum.clone(), self.kg_loss_sum.clone())
+            row_step = self.kg_row_step.clone()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -167,6 +211,9 @@ class TrainEngine:
             adam.restore(snap)
             self.cf_loss_sum.copy_(sums[0])
             self.kg_loss_sum.copy_(sums[1])
+            self.kg_row_step.copy_(row_step)
+            if kind == "kg":
+                self.kg_grads[0].zero_()
             g = torch.cuda.CUDAGraph()
             before = _lib.LaunchCounter.count
             with torch.cuda.graph(g):
@@ -221,6 +268,7 @@ class TrainEngine:
                 cf_host += float(self.cf_loss.item())
                 d2h += 4
         self.cf_adam.sync_host(n_cf)
+        self._kg_phase_begin(n_kg)
         step = self._get("kg", resident) if n_kg else None
         for i in range(n_kg):
             if not resident:
@@ -231,6 +279,7 @@ class TrainEngine:
             if read_loss_every_step:
                 kg_host += float(self.kg_loss.item())
                 d2h += 4
+        self._kg_phase_end(n_kg)
         self.kg_adam.sync_host(n_kg)
         if refresh:
             eh, er, et, ri = src.edges

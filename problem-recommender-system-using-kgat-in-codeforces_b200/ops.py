@@ -468,3 +468,33 @@ def adam_apply(params, grads, exp_avgs, exp_avg_sqs, hyper: torch.Tensor):
             t.exp_avg_sq[j] = _ptr(exp_avg_sqs[i], f32, "exp_avg_sq")
             t.numel[j] = params[i].numel()
         check(lib.kgat_adam_apply(C.byref(t), _ptr(hyper, f32), _stream()), "adam_apply")
+
+
+def adam_hyper_table(s0_dev: torch.Tensor, n_steps: int, lr, beta1, beta2, table: torch.Tensor):
+    lib = _lib.load()
+    if table.numel() < 2 * n_steps:
+        raise KgatLibraryError("adam_hyper_table: table needs 2*n_steps floats")
+    check(lib.kgat_adam_hyper_table(_ptr(s0_dev, i64), int(n_steps), float(lr), float(beta1), float(beta2), _ptr(table, f32), _stream()), "adam_hyper_table")
+
+
+@_timed("adam_lazy_catchup")
+def adam_lazy_catchup(param, exp_avg, exp_avg_sq, row_step, ids, cur_step_dev, s0, table, hyper):
+    lib = _lib.load()
+    check(lib.kgat_adam_lazy_catchup(_ptr(param, f32), _ptr(exp_avg, f32), _ptr(exp_avg_sq, f32), _ptr(row_step, i32), _ptr(ids, i64),
+                                     ids.numel(), param.shape[1], _ptr(cur_step_dev, i64), _ptr(s0, i64), _ptr(table, f32), _ptr(hyper, f32),
+                                     _stream()), "adam_lazy_catchup")
+
+
+@_timed("adam_sparse_rows")
+def adam_sparse_rows(param, grad, exp_avg, exp_avg_sq, row_step, ids, cur_step_dev, s0, hyper):
+    lib = _lib.load()
+    check(lib.kgat_adam_sparse_rows(_ptr(param, f32), _ptr(grad, f32), _ptr(exp_avg, f32), _ptr(exp_avg_sq, f32), _ptr(row_step, i32),
+                                    _ptr(ids, i64), ids.numel(), param.shape[1], _ptr(cur_step_dev, i64), _ptr(s0, i64), _ptr(hyper, f32),
+                                    _stream()), "adam_sparse_rows")
+
+
+def adam_lazy_flush(param, exp_avg, exp_avg_sq, row_step, cur_step_dev, s0, table, hyper):
+    lib = _lib.load()
+    check(lib.kgat_adam_lazy_flush(_ptr(param, f32), _ptr(exp_avg, f32), _ptr(exp_avg_sq, f32), _ptr(row_step, i32), param.shape[0],
+                                   param.shape[1], _ptr(cur_step_dev, i64), _ptr(s0, i64), _ptr(table, f32), _ptr(hyper, f32), _stream()),
+          "adam_lazy_flush")
