@@ -27,6 +27,66 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
+# ---------------------------------------------------------------------------------------------
+# Optional device assist: the sort / unique steps of the assembly dominate
+# at 10^7-10^8 edges (numpy: minutes).  They are pure functions of their input, so running them with
+# torch on a CUDA device gives bit-identical arrays (tested); everything that involves floating point
+# (the 1/deg values) is still computed exactly as the numpy path does.  ``ACCEL`` = "auto" uses the GPU
+# for arrays above ``ACCEL_MIN`` elements when one is visible, "never" / "always" force a path.
+# ---------------------------------------------------------------------------------------------
+ACCEL = "auto"
+ACCEL_MIN = 2_000_000
+
+
+def _use_gpu(n: int) -> bool:
+    if ACCEL == "never":
+        return False
+    try:
+        import torch
+
+        if not torch.cuda.is_available():
+            return False
+    except Exception:  # pragma: no cover
+        return False
+    return ACCEL == "always" or n >= ACCEL_MIN
+
+
+def stable_argsort(keys: np.ndarray) -> np.ndarray:
+    if _use_gpu(keys.shape[0]):
+        import torch
+
+        return torch.sort(torch.from_numpy(np.ascontiguousarray(keys)).cuda(), stable=True).indices.cpu().numpy()
+    return np.argsort(keys, kind="stable")
+
+
+def sorted_unique(keys: np.ndarray, return_index: bool = False):
+    """np.unique(keys[, return_index=True]) (first occurrence index of every unique key, keys need not be sorted)."""
+    if _use_gpu(keys.shape[0]):
+        import torch
+
+        k = torch.from_numpy(np.ascontiguousarray(keys)).cuda()
+        ks, order = torch.sort(k, stable=True)
+        first = torch.ones(ks.shape[0], dtype=torch.bool, device=ks.device)
+        first[1:] = ks[1:] != ks[:-1]
+        uniq = ks[first].cpu().numpy()
+        if return_index:
+            return uniq, order[first].cpu().numpy()
+        return uniq
+    return np.unique(keys, return_index=True) if return_index else np.unique(keys)
+
+
+def lexsort2(minor: np.ndarray, major: np.ndarray) -> np.ndarray:
+    """np.lexsort((minor, major)): stable order by ``major`` then ``minor``."""
+    if _use_gpu(major.shape[0]):
+        import torch
+
+        mi = torch.from_numpy(np.ascontiguousarray(minor)).cuda()
+        ma = torch.from_numpy(np.ascontiguousarray(major)).cuda()
+        o1 = torch.sort(mi, stable=True).indices
+        o2 = torch.sort(ma[o1], stable=True).indices
+        return o1[o2].cpu().numpy()
+    return np.lexsort((minor, major))
+
 
 @dataclass
 class CKG:
@@ -82,9 +142,9 @@ def _laplacian_coo(rows: np.ndarray, cols: np.ndarray, node_num: int):
     vals = (1.0 * s[rows]) * s[rows]
     l_rows, l_cols = cols.astype(np.int64), rows.astype(np.int64)
     key = l_rows * node_num + l_cols
-    order = np.argsort(key, kind="stable")
+    order = stable_argsort(key)
     key, vals = key[order], vals[order]
-    uniq, start = np.unique(key, return_index=True)
+    uniq, start = sorted_unique(key, return_index=True)
     if uniq.size != key.size:  # duplicate adjacency entries: scipy sums them
         vals = np.add.reduceat(vals, start)
     return uniq // node_num, uniq % node_num, vals
@@ -132,12 +192,12 @@ def build_ckg(
     rels = np.concatenate(
         [np.full(l[0].shape[0], rid, dtype=np.int64) for l, rid in zip(lap, adjacency_relations)]
     )
-    order = np.lexsort((tails, heads))  # stable: ties keep Laplacian order
+    order = stable_argsort(heads * n + tails)  # == np.lexsort((tails, heads)); stable: ties keep Laplacian order
     heads, tails, vals, rels = heads[order], tails[order], vals[order], rels[order]
 
     # ---- initial attentive matrix: sum of Laplacians in float64, then float32 ------------------
     key = heads * n + tails  # already (row, col)-sorted
-    uniq, start = np.unique(key, return_index=True)
+    uniq, start = sorted_unique(key, return_index=True)
     if uniq.size != key.size:
         att_vals64 = np.add.reduceat(vals, start)
     else:
@@ -165,7 +225,7 @@ def interaction_dict(pairs: np.ndarray, user_num: int | None = None) -> dict[int
     pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
     out: dict[int, list[int]] = {} if user_num is None else {int(u): [] for u in range(user_num)}
     if pairs.size:
-        order = np.argsort(pairs[:, 0], kind="stable")
+        order = stable_argsort(pairs[:, 0])
         sp = pairs[order]
         users, start = np.unique(sp[:, 0], return_index=True)
         bounds = list(start) + [sp.shape[0]]

@@ -19,7 +19,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .ckg import CKG, build_ckg, interaction_dict
+from .ckg import CKG, build_ckg, interaction_dict, lexsort2, sorted_unique
 
 SEED = 2024
 
@@ -67,7 +67,7 @@ def _unique_pairs(rng, n_target: int, draw, key_mod: int) -> np.ndarray:
     want = n_target
     for _ in range(64):
         a, b = draw(int(want * 1.3) + 16)
-        keys = np.unique(np.concatenate([keys, a.astype(np.int64) * key_mod + b.astype(np.int64)]))
+        keys = sorted_unique(np.concatenate([keys, a.astype(np.int64) * key_mod + b.astype(np.int64)]))
         if keys.size >= n_target:
             break
         want = n_target - keys.size
@@ -94,7 +94,7 @@ def _interactions(rng, shape: Shape, zipf_a: float, zipf_shift: float) -> np.nda
     if missing.size:
         extra = np.stack([missing, item_perm[rng.integers(0, min(64, shape.item_num), size=missing.size)]], axis=1)
         pairs = np.concatenate([pairs, extra])
-        pairs = pairs[np.lexsort((pairs[:, 1], pairs[:, 0]))]
+        pairs = pairs[lexsort2(pairs[:, 1], pairs[:, 0])]
     return pairs
 
 
@@ -152,7 +152,7 @@ def _codeforces_triples(rng, shape: Shape) -> np.ndarray:
 def split_interactions(rng, pairs: np.ndarray, user_num: int):
     """Per-user 72 / 8 / 20 split (at least one training item per user)."""
     jitter = rng.random(pairs.shape[0])
-    order = np.lexsort((jitter, pairs[:, 0]))
+    order = lexsort2(jitter, pairs[:, 0])
     sp = pairs[order]
     counts = np.bincount(sp[:, 0], minlength=user_num)
     starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
@@ -221,6 +221,6 @@ def make_edges_only(node_num: int, nnz: int, relation_num: int, seed: int = SEED
     t = np.concatenate([pr[:, 1], pr[:, 0]])
     r = np.concatenate([rel, rel + relation_num // 2])
     key = h * node_num + t
-    _, first = np.unique(key, return_index=True)
+    _, first = sorted_unique(key, return_index=True)
     h, t, r = h[first], t[first], r[first]
     return h.astype(np.int32), r.astype(np.int64), t.astype(np.int32)
