@@ -123,30 +123,67 @@ int pack_tables(const kgat_tables_t* t, Tables* out) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// TransR:  x = e W_r  (row-vector convention), lane owns output columns lane + 32 m
+// TransR:  x = e W_r  (row-vector convention).  One CTA of 4 warps per sample: the kernels are latency
+// bound (512 samples, a 64-step dependent mat-vec each), so the rows j of W_r are split over the 4 warps
+// and the partial projections are combined through shared memory.  Lane owns output columns lane + 32 m.
 // ---------------------------------------------------------------------------------------------
-template <int DM, int KM>
-__device__ __forceinline__ void transr_project(const float* __restrict__ Wr, const float (&eh)[DM], const float (&ep)[DM],
-                                               const float (&en)[DM], int lane, float (&xh)[KM], float (&xp)[KM], float (&xn)[KM]) {
+constexpr int kTrWarps = 4;
+
+// partial projections of (e_h, e_p, e_n) over this warp's rows [j0, j0 + JW) of W_r
+template <int D, int KM>
+__device__ __forceinline__ void transr_partial(const float* __restrict__ Wr, const float* __restrict__ emb, int64_t h, int64_t p, int64_t n,
+                                               int warp, int lane, float& eh, float& ep, float& en, float (&xh)[KM], float (&xp)[KM],
+                                               float (&xn)[KM]) {
     constexpr int K = KM * 32;
+    constexpr int JW = D / kTrWarps;  // rows of W_r per warp (8, 16 or 32)
+    const int j0 = warp * JW;
+    eh = ep = en = 0.f;
+    if (lane < JW) {
+        eh = __ldg(emb + h * D + j0 + lane);
+        ep = __ldg(emb + p * D + j0 + lane);
+        en = __ldg(emb + n * D + j0 + lane);
+    }
 #pragma unroll
     for (int m = 0; m < KM; ++m) xh[m] = xp[m] = xn[m] = 0.f;
-#pragma unroll
-    for (int jm = 0; jm < DM; ++jm) {
 #pragma unroll 8
-        for (int jj = 0; jj < 32; ++jj) {
-            const float a = __shfl_sync(kFull, eh[jm], jj);
-            const float b = __shfl_sync(kFull, ep[jm], jj);
-            const float c = __shfl_sync(kFull, en[jm], jj);
-            const float* wrow = Wr + (jm * 32 + jj) * K + lane;
+    for (int jj = 0; jj < JW; ++jj) {
+        const float a = __shfl_sync(kFull, eh, jj);
+        const float b = __shfl_sync(kFull, ep, jj);
+        const float c = __shfl_sync(kFull, en, jj);
+        const float* wrow = Wr + (j0 + jj) * K + lane;
 #pragma unroll
-            for (int m = 0; m < KM; ++m) {
-                const float w = __ldg(wrow + 32 * m);
-                xh[m] = fmaf(a, w, xh[m]);
-                xp[m] = fmaf(b, w, xp[m]);
-                xn[m] = fmaf(c, w, xn[m]);
-            }
+        for (int m = 0; m < KM; ++m) {
+            const float w = __ldg(wrow + 32 * m);
+            xh[m] = fmaf(a, w, xh[m]);
+            xp[m] = fmaf(b, w, xp[m]);
+            xn[m] = fmaf(c, w, xn[m]);
         }
+    }
+}
+
+// combine the 4 warps' partials: every warp returns with the full projections
+template <int KM>
+__device__ __forceinline__ void transr_combine(float (*part)[3][KM * 32], int warp, int lane, float (&xh)[KM], float (&xp)[KM],
+                                               float (&xn)[KM]) {
+#pragma unroll
+    for (int m = 0; m < KM; ++m) {
+        part[warp][0][lane + 32 * m] = xh[m];
+        part[warp][1][lane + 32 * m] = xp[m];
+        part[warp][2][lane + 32 * m] = xn[m];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < KM; ++m) {
+        float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+        for (int w = 0; w < kTrWarps; ++w) {
+            a += part[w][0][lane + 32 * m];
+            b += part[w][1][lane + 32 * m];
+            c += part[w][2][lane + 32 * m];
+        }
+        xh[m] = a;
+        xp[m] = b;
+        xn[m] = c;
     }
 }
 
@@ -156,28 +193,23 @@ __global__ void __launch_bounds__(128) transr_fwd_kernel(const float* __restrict
                                                          const int64_t* __restrict__ rels, const int64_t* __restrict__ pt,
                                                          const int64_t* __restrict__ nt, int batch, float* __restrict__ scratch) {
     constexpr int D = DM * 32, K = KM * 32;
-    const int lane = threadIdx.x & 31;
-    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (b >= batch) return;
+    __shared__ float part[kTrWarps][3][K];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x;
     const int64_t h = heads[b], r = rels[b], p = pt[b], n = nt[b];
-    float eh[DM], ep[DM], en[DM], er[KM], xh[KM], xp[KM], xn[KM];
-#pragma unroll
-    for (int m = 0; m < DM; ++m) {
-        eh[m] = __ldg(emb + h * D + lane + 32 * m);
-        ep[m] = __ldg(emb + p * D + lane + 32 * m);
-        en[m] = __ldg(emb + n * D + lane + 32 * m);
-    }
-#pragma unroll
-    for (int m = 0; m < KM; ++m) er[m] = __ldg(rel_emb + r * K + lane + 32 * m);
-    transr_project<DM, KM>(W + r * (int64_t)D * K, eh, ep, en, lane, xh, xp, xn);
+    float eh, ep, en, xh[KM], xp[KM], xn[KM];
+    transr_partial<D, KM>(W + r * (int64_t)D * K, emb, h, p, n, warp, lane, eh, ep, en, xh, xp, xn);
+    transr_combine<KM>(part, warp, lane, xh, xp, xn);
+    if (warp != 0) return;
     float ps = 0.f, ns = 0.f, l2 = 0.f;
 #pragma unroll
     for (int m = 0; m < KM; ++m) {
-        const float dp = xh[m] + er[m] - xp[m];
-        const float dn = xh[m] + er[m] - xn[m];
+        const float er = __ldg(rel_emb + r * K + lane + 32 * m);
+        const float dp = xh[m] + er - xp[m];
+        const float dn = xh[m] + er - xn[m];
         ps = fmaf(dp, dp, ps);
         ns = fmaf(dn, dn, ns);
-        l2 += xh[m] * xh[m] + er[m] * er[m] + xp[m] * xp[m] + xn[m] * xn[m];
+        l2 += xh[m] * xh[m] + er * er + xp[m] * xp[m] + xn[m] * xn[m];
     }
     ps = warp_sum(ps);
     ns = warp_sum(ns);
@@ -197,21 +229,15 @@ __global__ void __launch_bounds__(128) transr_bwd_kernel(const float* __restrict
                                                          float* __restrict__ g_emb, float* __restrict__ g_rel,
                                                          float* __restrict__ g_W) {
     constexpr int D = DM * 32, K = KM * 32;
-    const int lane = threadIdx.x & 31;
-    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (b >= batch) return;
+    constexpr int JW = D / kTrWarps;
+    __shared__ float part[kTrWarps][3][K];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x;
     const int64_t h = heads[b], r = rels[b], p = pt[b], n = nt[b];
-    float eh[DM], ep[DM], en[DM], er[KM], xh[KM], xp[KM], xn[KM];
-#pragma unroll
-    for (int m = 0; m < DM; ++m) {
-        eh[m] = __ldg(emb + h * D + lane + 32 * m);
-        ep[m] = __ldg(emb + p * D + lane + 32 * m);
-        en[m] = __ldg(emb + n * D + lane + 32 * m);
-    }
-#pragma unroll
-    for (int m = 0; m < KM; ++m) er[m] = __ldg(rel_emb + r * K + lane + 32 * m);
     const float* Wr = W + r * (int64_t)D * K;
-    transr_project<DM, KM>(Wr, eh, ep, en, lane, xh, xp, xn);
+    float eh, ep, en, xh[KM], xp[KM], xn[KM];
+    transr_partial<D, KM>(Wr, emb, h, p, n, warp, lane, eh, ep, en, xh, xp, xn);
+    transr_combine<KM>(part, warp, lane, xh, xp, xn);
 
     const float g = g_loss[0] / (float)batch;
     const float s2 = 2.f * sigmoidf_(-scratch[b]) * g;  // loss = -logsigmoid(ns - ps)
@@ -219,50 +245,48 @@ __global__ void __launch_bounds__(128) transr_bwd_kernel(const float* __restrict
     float gxh[KM], gxp[KM], gxn[KM];
 #pragma unroll
     for (int m = 0; m < KM; ++m) {
-        const float dp = xh[m] + er[m] - xp[m];
-        const float dn = xh[m] + er[m] - xn[m];
+        const float er = __ldg(rel_emb + r * K + lane + 32 * m);
+        const float dp = xh[m] + er - xp[m];
+        const float dn = xh[m] + er - xn[m];
         const float gdp = s2 * dp;   // dL/d dpos
         const float gdn = -s2 * dn;  // dL/d dneg
         gxh[m] = gdp + gdn + lam * xh[m];
         gxp[m] = -gdp + lam * xp[m];
         gxn[m] = -gdn + lam * xn[m];
-        atomicAdd(g_rel + r * K + lane + 32 * m, gdp + gdn + lam * er[m]);
+        if (warp == 0) atomicAdd(g_rel + r * K + lane + 32 * m, gdp + gdn + lam * er);
     }
-    float geh[DM], gep[DM], gen[DM];
+    // this warp's rows of W_r: d e[j] = <g_x, W_r[j, :]>, d W_r[j, :] += e[j] * g_x
+    const int j0 = warp * JW;
     float* gWr = g_W + r * (int64_t)D * K;
-#pragma unroll
-    for (int jm = 0; jm < DM; ++jm) {
-        geh[jm] = gep[jm] = gen[jm] = 0.f;
+    float geh = 0.f, gep = 0.f, gen = 0.f;
 #pragma unroll 4
-        for (int jj = 0; jj < 32; ++jj) {
-            const int j = jm * 32 + jj;
-            const float a = __shfl_sync(kFull, eh[jm], jj);
-            const float bb = __shfl_sync(kFull, ep[jm], jj);
-            const float c = __shfl_sync(kFull, en[jm], jj);
-            float ph = 0.f, pp = 0.f, pn = 0.f;
+    for (int jj = 0; jj < JW; ++jj) {
+        const int j = j0 + jj;
+        const float a = __shfl_sync(kFull, eh, jj);
+        const float bb = __shfl_sync(kFull, ep, jj);
+        const float c = __shfl_sync(kFull, en, jj);
+        float ph = 0.f, pp = 0.f, pn = 0.f;
 #pragma unroll
-            for (int m = 0; m < KM; ++m) {
-                const float w = __ldg(Wr + j * K + lane + 32 * m);
-                ph = fmaf(gxh[m], w, ph);
-                pp = fmaf(gxp[m], w, pp);
-                pn = fmaf(gxn[m], w, pn);
-                atomicAdd(gWr + j * K + lane + 32 * m, a * gxh[m] + bb * gxp[m] + c * gxn[m]);
-            }
-            ph = warp_sum(ph);
-            pp = warp_sum(pp);
-            pn = warp_sum(pn);
-            if (lane == jj) {
-                geh[jm] = ph;
-                gep[jm] = pp;
-                gen[jm] = pn;
-            }
+        for (int m = 0; m < KM; ++m) {
+            const float w = __ldg(Wr + j * K + lane + 32 * m);
+            ph = fmaf(gxh[m], w, ph);
+            pp = fmaf(gxp[m], w, pp);
+            pn = fmaf(gxn[m], w, pn);
+            atomicAdd(gWr + j * K + lane + 32 * m, a * gxh[m] + bb * gxp[m] + c * gxn[m]);
+        }
+        ph = warp_sum(ph);
+        pp = warp_sum(pp);
+        pn = warp_sum(pn);
+        if (lane == jj) {
+            geh = ph;
+            gep = pp;
+            gen = pn;
         }
     }
-#pragma unroll
-    for (int m = 0; m < DM; ++m) {
-        atomicAdd(g_emb + h * D + lane + 32 * m, geh[m]);
-        atomicAdd(g_emb + p * D + lane + 32 * m, gep[m]);
-        atomicAdd(g_emb + n * D + lane + 32 * m, gen[m]);
+    if (lane < JW) {
+        atomicAdd(g_emb + h * D + j0 + lane, geh);
+        atomicAdd(g_emb + p * D + j0 + lane, gep);
+        atomicAdd(g_emb + n * D + j0 + lane, gen);
     }
 }
 
@@ -313,7 +337,7 @@ int kgat_transr_forward(const float* emb, const float* rel_emb, const float* W, 
                         float* margin, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (batch <= 0) return KGAT_ERR_INVALID_ARGUMENT;
-    const unsigned blocks = (batch * 32 + 127) / 128;
+    const unsigned blocks = (unsigned)batch;  // one 4-warp CTA per sample
     KGAT_TRANSR_DISPATCH((transr_fwd_kernel<DM, KM><<<blocks, 128, 0, stream>>>(emb, rel_emb, W, heads, rels, pos_tails, neg_tails,
                                                                                batch, margin)));
     loss_reduce_kernel<<<1, 256, 0, stream>>>(margin, batch, reg, loss);
@@ -325,7 +349,7 @@ int kgat_transr_backward(const float* emb, const float* rel_emb, const float* W,
                          const float* margin, const float* g_loss, float* g_emb, float* g_rel_emb, float* g_W, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (batch <= 0) return KGAT_ERR_INVALID_ARGUMENT;
-    const unsigned blocks = (batch * 32 + 127) / 128;
+    const unsigned blocks = (unsigned)batch;  // one 4-warp CTA per sample
     KGAT_TRANSR_DISPATCH((transr_bwd_kernel<DM, KM><<<blocks, 128, 0, stream>>>(emb, rel_emb, W, heads, rels, pos_tails, neg_tails,
                                                                                batch, reg, margin, g_loss, g_emb, g_rel_emb, g_W)));
     return check_launch();
