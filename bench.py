@@ -294,6 +294,7 @@ def main():
         t1.record()
         barrier()
     launches = _lib.LaunchCounter.count
+    phases = dict(engine.last_phase_ms)
     epoch_s = t0.elapsed_time(t1) / 1e3 / max(args.steps, 1)
     clk = clocks.summary()
 
@@ -375,6 +376,8 @@ def main():
         "config": config_dict(g, data, 1),
         "propagation_edges_per_s": edges_per_epoch / epoch_s,
         "cf_loss": losses[0], "kg_loss": losses[1],
+        "phases": {"cf_phase_s": phases["cf"] / 1e3, "kg_phase_s": phases["kg"] / 1e3, "refresh_s": phases["refresh"] / 1e3,
+                   "cf_step_us": 1e3 * phases["cf"] / max(phases["n_cf"], 1), "kg_step_us": 1e3 * phases["kg"] / max(phases["n_kg"], 1)},
         "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         "roofline": roofline, "cpu_baseline": cpu,
         "kernels": {k: {kk: round(vv, 3) if isinstance(vv, float) else vv for kk, vv in v.items()} for k, v in sorted(per_epoch_ms.items(), key=lambda kv: -kv[1]["epoch_ms"])},

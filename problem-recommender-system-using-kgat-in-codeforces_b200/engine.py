@@ -261,7 +261,9 @@ class TrainEngine:
         self.cf_loss_sum.zero_()
         self.kg_loss_sum.zero_()
         cf_host = kg_host = 0.0
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         step = self._get("cf", resident) if n_cf else None
+        ev[0].record()
         for i in range(n_cf):
             if not resident:
                 for j in range(3):
@@ -272,6 +274,7 @@ class TrainEngine:
                 cf_host += float(self.cf_loss.item())
                 d2h += 4
         self.cf_adam.sync_host(n_cf)
+        ev[1].record()
         self._kg_phase_begin(n_kg)
         step = self._get("kg", resident) if n_kg else None
         for i in range(n_kg):
@@ -285,12 +288,17 @@ class TrainEngine:
                 d2h += 4
         self._kg_phase_end(n_kg)
         self.kg_adam.sync_host(n_kg)
+        ev[2].record()
         if refresh:
             eh, er, et, ri = src.edges
             if not eh.is_cuda:
                 h2d += eh.numel() * eh.element_size() + er.numel() * 8 + et.numel() * et.element_size() + ri.numel() * 8
             m(eh, er, et, ri, mode=KGATMode.UPDATE_ATTENTION)
+        ev[3].record()
         if not read_loss_every_step:
             cf_host, kg_host = float(self.cf_loss_sum.item()), float(self.kg_loss_sum.item())
             d2h += 8
+        ev[3].synchronize()
+        self.last_phase_ms = {"cf": ev[0].elapsed_time(ev[1]), "kg": ev[1].elapsed_time(ev[2]), "refresh": ev[2].elapsed_time(ev[3]),
+                              "n_cf": n_cf, "n_kg": n_kg}
         return cf_host / max(n_cf, 1), kg_host / max(n_kg, 1), h2d, d2h
