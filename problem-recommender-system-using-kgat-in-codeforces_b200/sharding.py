@@ -235,11 +235,17 @@ class ShardedPropagation:
 class ShardedEngine:
     """Epoch driver for P ranks: sharded CF phase, replicated KG phase and refresh."""
 
-    def __init__(self, model, part: CyclicPartition):
+    def __init__(self, model, part: CyclicPartition, use_graphs: bool = True):
         from . import ops
         from .engine import TrainEngine
 
         self.model, self.part, self.kops, self.ops = model, part, KernelOps(), ops
+        self.use_graphs = use_graphs
+        self._cf_graph = None
+        self._cf_graph_key = None
+        self._cf_padded = None
+        self._cf_src = None
+        self.cf_ids = None
         self.dev = model._device()
         self.single = TrainEngine(model, use_graphs=True)  # KG phase (replicated) reuses the 1-GPU engine
         self.layers = [tuple(t.detach() for t in grp) for grp in model._layers()]
@@ -300,6 +306,39 @@ class ShardedEngine:
         self.ops.adam_apply(params, grads, ms, vs, self.hyper)
         self.loss_sum.add_(self.loss)
 
+    def _cf_graphed_step(self):
+        """select the current batch (device step counter) + one sharded CF step; captured as ONE CUDA graph
+        including the NCCL all-gathers / all-reduce (all ranks capture the same sequence)."""
+        self.ops.select_batch(self._cf_padded, self.step_dev, self.cf_ids.view(-1))
+        self.cf_step(self.cf_ids[0], self.cf_ids[1], self.cf_ids[2])
+
+    def _cf_runner(self):
+        if not self.use_graphs:
+            return self._cf_graphed_step
+        key = (self._graph_id, id(self._cf_padded), self.model.training)
+        if self._cf_graph is None or key != self._cf_graph_key:
+            # warm-up step (communicators, lazy kernel attributes), undone afterwards
+            e0_loc = self.prop.tables[0][self.part.slice()]
+            snap = [t.clone() for t in [e0_loc, self.e0_m, self.e0_v, self.step_dev, self.loss_sum] + [t for grp in self.layers for t in grp]
+                    + [t for grp in self.layer_m for t in grp] + [t for grp in self.layer_v for t in grp]]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._cf_graphed_step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            live = [e0_loc, self.e0_m, self.e0_v, self.step_dev, self.loss_sum] + [t for grp in self.layers for t in grp] \
+                + [t for grp in self.layer_m for t in grp] + [t for grp in self.layer_v for t in grp]
+            for dst, src in zip(live, snap):
+                dst.copy_(src)
+            if self.part.world > 1:
+                dist.barrier()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._cf_graphed_step()
+            self._cf_graph, self._cf_graph_key = g, key
+        return self._cf_graph.replay
+
     def run_epoch(self, data, n_cf=None, n_kg=None, refresh=True):
         """``data``: EpochData on the device (cf [n,3,B], kg [n,4,B] stacked, as TrainEngine.bind_resident)."""
         m = self.model
@@ -311,10 +350,14 @@ class ShardedEngine:
         n_cf = data.cf.shape[0] if n_cf is None else n_cf
         n_kg = data.kg.shape[0] if n_kg is None else n_kg
         self.loss_sum.zero_()
-        cf_padded = self.part.to_padded(data.cf[:n_cf])  # batch ids -> rows of the padded cyclic layout, once per epoch
+        if self._cf_src is not data.cf:  # batch ids -> rows of the padded cyclic layout, once per bound epoch array
+            self._cf_padded = self.part.to_padded(data.cf).contiguous()
+            self._cf_src = data.cf
+            self.cf_ids = torch.zeros(3, data.cf.shape[2], dtype=torch.int64, device=self.dev)
+            self.scratch = torch.empty(2 * data.cf.shape[2], device=self.dev)
+        step = self._cf_runner() if n_cf else None
         for i in range(n_cf):
-            b = cf_padded[i]
-            self.cf_step(b[0], b[1], b[2])
+            step()
         cf_loss = float(self.loss_sum.item()) / max(n_cf, 1)
         self.gather_to_model()
         for grp in m._layers():  # aggregator weights were updated in place (they are the model's tensors)
