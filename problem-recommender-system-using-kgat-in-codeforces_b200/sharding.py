@@ -393,8 +393,14 @@ def bench_main(args, metric, unit, workload, make_workload, config_dict, ClockSa
     from .engine import TrainEngine
     from .trainer import build_model
 
+    import sys
+
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    # NCCL prints its version banner on stdout: keep stdout clean for the single JSON line
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     g, data = make_workload(workload)
     model = build_model(g, dev)
     part = CyclicPartition(g.node_num, world, rank)
@@ -433,5 +439,12 @@ def bench_main(args, metric, unit, workload, make_workload, config_dict, ClockSa
             "note": "CF phase row-sharded (cyclic) with 7 all-gathers + 1 all-reduce per step over NCCL; KG phase and the refresh are replicated; "
                     "timed on the device, max over ranks",
         }
-        print(json.dumps(line))
-    dist.destroy_process_group()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    # tear-down: drop the captured graphs (they hold NCCL work) before the communicator, and do not let a
+    # wedged communicator destructor hang the process after the result is out
+    eng._cf_graph = None
+    eng.single._graphs.clear()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stderr.flush()
+    os._exit(0)
