@@ -177,3 +177,68 @@ class KGLossFunction(torch.autograd.Function):
         g_emb, g_rel, g_w = torch.zeros_like(embd), torch.zeros_like(reld), torch.zeros_like(wd)
         ops.transr_backward(embd, reld, wd, heads, rels, pos_t, neg_t, ctx.reg, scratch, g_loss, g_emb, g_rel, g_w)
         return (None, None, None, None, None, g_emb, g_rel, g_w)
+
+
+# ----------------------------------------------------------------------------------------------
+# CUDA-graph fast path behind the reference-facing API (model(...), loss.backward())
+# ----------------------------------------------------------------------------------------------
+class GraphedStep:
+    """Forward and backward of one training mode captured as two CUDA graphs over static buffers.
+
+    The reference driver always runs ``loss = model(...); loss.backward(); model.update_*_weights()``
+    (main.py:306-314, 334-343); an epoch is ~15 k such steps whose Python / launch overhead exceeds
+    their GPU time.  ``replay_forward`` copies the step's ids into static buffers and replays the
+    forward graph; ``GraphedLoss`` hands autograd a node whose backward replays the backward graph and
+    returns *views* of the static gradient buffers (autograd adopts them as ``.grad`` without a copy).
+    """
+
+    def __init__(self, params, batch: int, n_ids: int, body_fwd, body_bwd):
+        dev = params[0].device
+        self.params = params
+        self.ids = torch.zeros(n_ids, batch, dtype=torch.int64, device=dev)
+        self.loss = torch.zeros(1, dtype=f32, device=dev)
+        self.g_loss = torch.ones(1, dtype=f32, device=dev)
+        self.scratch = torch.empty(2 * batch, dtype=f32, device=dev)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)  # forward calls so far (dropout stream)
+        self.serial = 0
+        self.grads = None
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # eager warm-up (no parameter is modified by forward / backward)
+            body_fwd(self)
+            body_bwd(self)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph_f = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_f):
+            body_fwd(self)
+        self.graph_b = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_b, pool=self.graph_f.pool()):
+            self.grads = body_bwd(self)
+
+    def replay_forward(self, ids):
+        for dst, src in zip(self.ids, ids):
+            dst.copy_(src, non_blocking=True)
+        self.graph_f.replay()
+        self.serial += 1
+
+
+class GraphedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, step: GraphedStep, *params):
+        ctx.step, ctx.serial = step, step.serial
+        return step.loss.reshape(()).clone()
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        step = ctx.step
+        if ctx.serial != step.serial:
+            raise RuntimeError(
+                "kgat_b200: backward() of a loss whose forward buffers were reused by a later model(...) call. "
+                "The API fast path assumes forward -> backward -> update per step (as the reference driver does); "
+                "set model.api_graphs = False for free-form autograd use."
+            )
+        step.g_loss.copy_(g_loss.reshape(1))
+        step.graph_b.replay()
+        adopt = all(p.grad is None for p in step.params)  # accumulation into an existing .grad must not alias our buffers
+        return (None, *[g.view_as(g) if adopt else g.clone() for g in step.grads])

@@ -31,7 +31,8 @@ from torch import nn
 from . import ops
 from ._lib import KgatLibraryError
 from .aggregator import Aggregator, AggregatorArgs
-from .functions import CFLossFunction, DropoutSpec, KGLossFunction, PropagateFunction, propagate_forward
+from .functions import (CFLossFunction, DropoutSpec, GraphedLoss, GraphedStep, KGLossFunction, PropagateFunction, propagate_backward,
+                        propagate_forward)
 from .graph import AttentiveGraph, EdgeIndex
 from .multi_head_attention import MultiHeadAttention
 from .optim import FusedAdam
@@ -114,6 +115,9 @@ class KGAT(nn.Module):
         self._injected_message_keep_bits: list | None = None  # per layer int32 [N, ceil(d_out/32)]
         self._injected_head_bits: torch.Tensor | None = None  # uint8 [n_edges], input edge order
         self.spmm_chunk = 256
+        # CUDA-graph fast path behind model(...) / loss.backward() for the two training modes (functions.GraphedStep)
+        self.api_graphs = True
+        self._api_steps: dict = {}
 
     # ------------------------------------------------------------------------------------------
     # plumbing
@@ -131,6 +135,8 @@ class KGAT(nn.Module):
         return dev
 
     def _ids(self, t: Any) -> torch.Tensor:
+        if isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.int64 and t.is_contiguous():
+            return t
         t = torch.as_tensor(t)
         return t.to(device=self._device(), dtype=torch.int64, non_blocking=True).contiguous()
 
@@ -150,6 +156,7 @@ class KGAT(nn.Module):
     def _invalidate(self) -> None:
         self._graph_cache = self._graph_key = None
         self._table_cache = self._table_key = None
+        self._api_steps = {}
 
     def _graph(self) -> AttentiveGraph:
         """CSR / CSC containers of the current ``attentive_matrix`` (rebuilt when it is replaced)."""
@@ -205,9 +212,56 @@ class KGAT(nn.Module):
     # ------------------------------------------------------------------------------------------
     # A5 / A6: losses
     # ------------------------------------------------------------------------------------------
+    def _use_api_graphs(self, params) -> bool:
+        return (self.api_graphs and torch.is_grad_enabled() and all(p.requires_grad for p in params)
+                and self._injected_message_keep_bits is None and not torch.cuda.is_current_stream_capturing())
+
+    def _api_step(self, kind: str, batch: int, params, extra_key, n_ids, make_bodies) -> GraphedStep:
+        key = (kind, batch, self.training, tuple(p.data_ptr() for p in params), extra_key)
+        step = self._api_steps.get(key)
+        if step is None:
+            if len(self._api_steps) > 8:
+                self._api_steps.clear()
+            body_fwd, body_bwd = make_bodies()
+            step = self._api_steps[key] = GraphedStep(params, batch, n_ids, body_fwd, body_bwd)
+        return step
+
     def _calc_cf_loss(self, user_ids, positive_item_ids, negative_item_ids) -> torch.Tensor:
         graph = self._graph()
         flat = [t for grp in self._layers() for t in grp]
+        params = [self._user_entity_embedding.weight, *flat]
+        if self._use_api_graphs(params):
+            ids = [self._ids(user_ids), self._ids(positive_item_ids), self._ids(negative_item_ids)]
+
+            def make_bodies():
+                reg = float(self._regularization_params[0])
+                layers = [tuple(t.detach() for t in grp) for grp in self._layers()]
+                ps = [float(a.message_dropout.p) if self.training else 0.0 for a in self._aggregator_layers]
+                seed = int(torch.randint(0, 2**62, (1,)).item()) if any(p > 0 for p in ps) else 0
+
+                def body_fwd(st):
+                    st.counter.add_(1)
+                    drop = DropoutSpec(ps=ps, seed=seed, seed_dev=st.counter)
+                    st.prop = propagate_forward(graph, params[0].detach(), layers, drop, save=True)
+                    ops.bpr_forward(st.prop.tables, st.ids[0], st.ids[1], st.ids[2], reg, st.loss, st.scratch)
+
+                def body_bwd(st):
+                    n_tab = len(st.prop.tables)
+
+                    def inject(l, buf):
+                        grads = [None] * n_tab
+                        grads[l] = buf
+                        ops.bpr_backward(st.prop.tables, grads, st.ids[0], st.ids[1], st.ids[2], reg, st.scratch, st.g_loss)
+
+                    g_last = torch.zeros_like(st.prop.tables[-1])
+                    inject(n_tab - 1, g_last)
+                    g_e0, pgrads = propagate_backward(graph, st.prop, layers, g_last, inject)
+                    return [g_e0] + [t for grp in pgrads for t in grp]
+                return body_fwd, body_bwd
+
+            step = self._api_step("cf", ids[0].numel(), params, (id(graph), graph.vals.data_ptr(), graph.t_vals.data_ptr()), 3, make_bodies)
+            step.replay_forward(ids)
+            return GraphedLoss.apply(step, *params)
         return CFLossFunction.apply(
             graph, self._ids(user_ids), self._ids(positive_item_ids), self._ids(negative_item_ids),
             float(self._regularization_params[0]), self._drop_spec(), self._user_entity_embedding.weight, *flat,
@@ -215,6 +269,29 @@ class KGAT(nn.Module):
 
     def _calc_kg_loss(self, heads, relations, positive_tails, negative_tails) -> torch.Tensor:
         self._device()
+        params = [self._user_entity_embedding.weight, self._relation_embedding.weight, self._trans_matrix]
+        if self._use_api_graphs(params):
+            ids = [self._ids(heads), self._ids(relations), self._ids(positive_tails), self._ids(negative_tails)]
+
+            def make_bodies():
+                reg = float(self._regularization_params[1])
+                emb, rel, w = (p.detach() for p in params)
+
+                def body_fwd(st):
+                    ops.transr_forward(emb, rel, w, st.ids[0], st.ids[1], st.ids[2], st.ids[3], reg, st.loss, st.scratch)
+
+                def body_bwd(st):
+                    if st.grads is None:
+                        st.kg_grads = [torch.zeros_like(p) for p in (emb, rel, w)]
+                    for g in st.kg_grads:
+                        ops.fill_(g, 0.0)
+                    ops.transr_backward(emb, rel, w, st.ids[0], st.ids[1], st.ids[2], st.ids[3], reg, st.scratch, st.g_loss, *st.kg_grads)
+                    return st.kg_grads
+                return body_fwd, body_bwd
+
+            step = self._api_step("kg", ids[0].numel(), params, None, 4, make_bodies)
+            step.replay_forward(ids)
+            return GraphedLoss.apply(step, *params)
         return KGLossFunction.apply(
             self._ids(heads), self._ids(relations), self._ids(positive_tails), self._ids(negative_tails),
             float(self._regularization_params[1]), self._user_entity_embedding.weight, self._relation_embedding.weight,
