@@ -15,16 +15,63 @@ from . import ops
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, use_graphs: bool = True):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self._hyper: dict[int, torch.Tensor] = {}
+        # When the same (parameter, gradient-buffer) set shows up step after step -- the model's API fast path hands
+        # autograd static gradient buffers -- the whole update (bias-correction scalars from a device step counter +
+        # the multi-tensor kernel) is captured once as a CUDA graph and replayed.
+        self.use_graphs = use_graphs
+        self._plans: dict = {}
+        self._seen: set = set()
+
+    def _graphed_step(self, group, ps) -> bool:
+        if not self.use_graphs or not ps or torch.cuda.is_current_stream_capturing():
+            return False
+        steps = {self.state[p]["step"] if self.state[p] else 0 for p in ps}
+        if len(steps) != 1 or not all(p.is_cuda for p in ps):
+            return False
+        cur = steps.pop()
+        beta1, beta2 = group["betas"]
+        key = (tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps), group["lr"], beta1, beta2, group["eps"])
+        plan = self._plans.get(key)
+        if plan is None:
+            if key not in self._seen or cur == 0:  # first sighting: take the generic path (also warms the kernels up)
+                if len(self._seen) > 64:
+                    self._seen.clear()
+                self._seen.add(key)
+                return False
+            if len(self._plans) > 8:
+                self._plans.clear()
+            dev = ps[0].device
+            plan = {"step_dev": torch.full((1,), cur, dtype=torch.int64, device=dev), "hyper": torch.empty(8, dtype=torch.float32, device=dev),
+                    "count": cur, "graph": torch.cuda.CUDAGraph()}
+            params, grads = [p.data for p in ps], [p.grad for p in ps]
+            ms, vs = [self.state[p]["exp_avg"] for p in ps], [self.state[p]["exp_avg_sq"] for p in ps]
+            torch.cuda.synchronize()
+            with torch.cuda.graph(plan["graph"]):
+                ops.adam_advance(plan["step_dev"], group["lr"], beta1, beta2, group["eps"], plan["hyper"])
+                ops.adam_apply(params, grads, ms, vs, plan["hyper"])
+            self._plans[key] = plan
+        if plan["count"] != cur:  # someone else advanced these parameters: resynchronise the device counter
+            plan["step_dev"].fill_(cur)
+            plan["count"] = cur
+        plan["graph"].replay()
+        plan["count"] += 1
+        for p in ps:
+            self.state[p]["step"] += 1
+            torch.autograd.graph.increment_version(p)
+        return True
 
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         for group in self.param_groups:
+            with_grad = [p for p in group["params"] if p.grad is not None]
+            if all(not p.grad.is_sparse and p.grad.is_contiguous() for p in with_grad) and self._graphed_step(group, with_grad):
+                continue
             by_step: dict[int, list] = {}
-            for p in group["params"]:
+            for p in with_grad:
                 if p.grad is None:
                     continue
                 if p.grad.is_sparse:

@@ -65,13 +65,20 @@ class EpochData:
         return cls(cf=s.cf_batches(n_cf, CF_BATCH), kg=s.kg_batches(n_kg, KG_BATCH), edges=edges)
 
     def tensors(self, device=None, pin: bool = False):
+        """Torch views of the epoch.  Host tensors keep each step's ids in one [k, B] block (steps stacked as
+        [n, k, B]) so a step's inputs travel in ONE host->device copy; ``cf[j][i]`` / ``kg[j][i]`` are views of it."""
         def conv(a):
             t = torch.from_numpy(np.ascontiguousarray(a))
             if device is not None:
                 return t.to(device)
             return t.pin_memory() if pin else t
 
-        return EpochData(cf=tuple(conv(a) for a in self.cf), kg=tuple(conv(a) for a in self.kg), edges=tuple(conv(a) for a in self.edges))
+        out = EpochData(cf=None, kg=None, edges=tuple(conv(a) for a in self.edges))
+        out.cf_block = conv(np.stack(self.cf, axis=1))  # [n_cf, 3, B]
+        out.kg_block = conv(np.stack(self.kg, axis=1))  # [n_kg, 4, B]
+        out.cf = tuple(out.cf_block[:, j] for j in range(3))
+        out.kg = tuple(out.kg_block[:, j] for j in range(4))
+        return out
 
 
 def run_epoch(model: KGAT, data: EpochData, read_loss_every_step: bool = False, n_cf: int | None = None, n_kg: int | None = None,
@@ -90,8 +97,13 @@ def run_epoch(model: KGAT, data: EpochData, read_loss_every_step: bool = False, 
     model.train()
     cf_sum = torch.zeros((), device=dev)
     cf_host = 0.0
+    cf_block, kg_block = getattr(data, "cf_block", None), getattr(data, "kg_block", None)
     for i in range(n_cf):
-        u, p, n = (t[i] for t in data.cf)
+        if cf_block is not None and not cf_block.is_cuda:  # one pinned [3, B] block per step -> one H2D copy
+            u, p, n = cf_block[i].to(dev, non_blocking=True).unbind(0)
+            h2d += 3 * u.numel() * 8
+        else:
+            u, p, n = (t[i] for t in data.cf)
         if not u.is_cuda:
             u, p, n = u.to(dev, non_blocking=True), p.to(dev, non_blocking=True), n.to(dev, non_blocking=True)
             h2d += 3 * u.numel() * 8
@@ -106,7 +118,11 @@ def run_epoch(model: KGAT, data: EpochData, read_loss_every_step: bool = False, 
     kg_sum = torch.zeros((), device=dev)
     kg_host = 0.0
     for i in range(n_kg):
-        h, r, pt, nt = (t[i] for t in data.kg)
+        if kg_block is not None and not kg_block.is_cuda:
+            h, r, pt, nt = kg_block[i].to(dev, non_blocking=True).unbind(0)
+            h2d += 4 * h.numel() * 8
+        else:
+            h, r, pt, nt = (t[i] for t in data.kg)
         if not h.is_cuda:
             h, r, pt, nt = (x.to(dev, non_blocking=True) for x in (h, r, pt, nt))
             h2d += 4 * h.numel() * 8
