@@ -324,8 +324,13 @@ def main():
 
     # ---- per-kernel split + roofline of the dominant kernel (live CUDA events, same process) ----
     n_probe_cf, n_probe_kg = 30, 60
+    # eager (un-captured) launches so that every kernel can be bracketed by its own pair of CUDA events
+    model.api_graphs = False
+    model._cf_optimizer.use_graphs = model._kg_optimizer.use_graphs = False
     with ops.KernelTimer() as kt:
         run_epoch(model, dev_data, n_cf=n_probe_cf, n_kg=n_probe_kg, refresh=False)
+    model.api_graphs = True
+    model._cf_optimizer.use_graphs = model._kg_optimizer.use_graphs = True
     ksum = kt.summary()
     per_epoch_ms = {}
     for name, (cnt, ms) in ksum.items():
