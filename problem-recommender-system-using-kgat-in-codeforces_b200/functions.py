@@ -219,7 +219,10 @@ class GraphedStep:
     def replay_forward(self, ids):
         b = self.ids.shape[1]
         first = ids[0]
-        if all(t.data_ptr() == first.data_ptr() + i * b * 8 for i, t in enumerate(ids)) and first.numel() == b:
+        st0 = first.untyped_storage()
+        if (first.numel() == b and all(t.data_ptr() == first.data_ptr() + i * b * 8 and t.untyped_storage().data_ptr() == st0.data_ptr()
+                                       for i, t in enumerate(ids))
+                and st0.nbytes() >= (first.storage_offset() + len(ids) * b) * 8):
             # the id tensors are consecutive rows of one [n_ids, B] block (one H2D copy upstream): one copy here too
             self.ids.copy_(first.as_strided((len(ids), b), (b, 1)), non_blocking=True)
         else:
