@@ -235,6 +235,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-hbm-regime", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -366,6 +367,37 @@ def main():
         d = int(top.split("_d")[1])
         roofline["gather_gbs"] = (abytes + 4.0 * graph.nnz * d) / (per_epoch_ms[top]["avg_us"] * 1e-6) / 1e9
 
+    # ---- the same SpMM kernel where HBM, not L2, is the binding roofline: C5-style graph (configs[4] scaled 5x down:
+    #      2.2 M nodes, 40 M edges, d = 128 -> 1.1 GB table >> 126 MB L2, every neighbour row is fetched from HBM) ----
+    hbm_regime = None
+    if not args.no_hbm_regime:
+        from kgat_b200 import synthetic
+        from kgat_b200.graph import AttentiveGraph
+
+        n5, d5 = 2_200_000, 128
+        h5, _, t5 = synthetic.make_edges_only(n5, 40_000_000, 64)
+        deg5 = np.bincount(h5, minlength=n5).astype(np.float32)
+        g5 = AttentiveGraph.from_coo(torch.from_numpy(h5.astype(np.int64)).to(dev), torch.from_numpy(t5.astype(np.int64)).to(dev),
+                                     torch.from_numpy((1.0 / deg5[h5]).astype(np.float32)).to(dev), n5)
+        x5 = torch.randn(n5, d5, device=dev)
+        y5 = torch.empty_like(x5)
+        for _ in range(3):
+            g5.matmul(x5, out=y5)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            g5.matmul(x5, out=y5)
+        e1.record()
+        torch.cuda.synchronize()
+        t5s = e0.elapsed_time(e1) / 1e3 / reps
+        b_gather = 8.0 * g5.nnz + 16.0 * g5.plan.n_tasks + 4.0 * g5.nnz * d5 + 4.0 * n5 * d5  # edges + one 512 B row per edge + output
+        hbm_regime = {"kernel": "spmm_d128", "nodes": n5, "nnz": g5.nnz, "d": d5, "table_bytes": 4.0 * n5 * d5, "ms": t5s * 1e3,
+                      "algorithmic_bytes": b_gather, "achieved": b_gather / t5s / 1e9, "peak": peak, "unit": "GB/s",
+                      "frac": b_gather / t5s / 1e9 / peak, "edges_per_s": g5.nnz / t5s,
+                      "model": "B_gather (SURVEY.md 8d: the table is 9x the L2, so one neighbour-row read per edge is compulsory HBM traffic)"}
+        del g5, x5, y5
+
     # ---- CPU baseline (oracle port, bounded sample) ----
     cpu = None
     if not args.no_cpu_baseline:
@@ -384,7 +416,7 @@ def main():
         "phases": {"cf_phase_s": phases["cf"] / 1e3, "kg_phase_s": phases["kg"] / 1e3, "refresh_s": phases["refresh"] / 1e3,
                    "cf_step_us": 1e3 * phases["cf"] / max(phases["n_cf"], 1), "kg_step_us": 1e3 * phases["kg"] / max(phases["n_kg"], 1)},
         "e2e": e2e, "gpu_launches": launches, "clocks": clk,
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "roofline_hbm_regime": hbm_regime, "cpu_baseline": cpu,
         "kernels": {k: {kk: round(vv, 3) if isinstance(vv, float) else vv for kk, vv in v.items()} for k, v in sorted(per_epoch_ms.items(), key=lambda kv: -kv[1]["epoch_ms"])},
     }
     print(json.dumps(line))
