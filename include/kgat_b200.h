@@ -88,9 +88,10 @@ int kgat_ids64_to_i32(const int64_t* in, int64_t n, int64_t bound, int32_t* out,
  * Y: n_rows x d (ldy); optional addend Z (ldz) or NULL.  d must be a multiple of 4, <= 256.
  * tasks: n_tasks x {row, begin, end, partial_slot}; a row longer than the plan's chunk is split into
  * several tasks with partial_slot >= 0 whose sums go to `partials` (n_partials x d floats) and are
- * reduced in chunk order for heavy_rows[h] = {row, first_partial_slot, n_chunks, 0} (deterministic,
- * no atomics).  The plan is host logic (graph.py: spmm_plan). */
-int kgat_spmm_csr(const int32_t* tasks, int64_t n_tasks, const int32_t* heavy_rows, int64_t n_heavy,
+ * reduced in chunk order for heavy_rows[h] = {row, first_partial_slot, n_chunks, arrival counter}
+ * by the warp that finishes the row's last chunk (deterministic, no float atomics; the counter column is
+ * scratch owned by the kernel: zero on entry, zero on exit).  The plan is host logic (graph.py: spmm_plan). */
+int kgat_spmm_csr(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_rows, int64_t n_heavy,
                   const int32_t* col_idx, const float* vals, const float* X, int64_t n_cols, int64_t ldx, float* Y,
                   int64_t ldy, const float* Z, int64_t ldz, int32_t d, float* partials, void* stream);
 

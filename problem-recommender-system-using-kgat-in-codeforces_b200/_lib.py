@@ -127,10 +127,8 @@ def _counted(fn, name: str):
     k = KERNELS_PER_CALL.get(name, 0)
     if k == 0:
         return fn
-    spmm = name == "kgat_spmm_csr"
-
     def call(*args):
-        LaunchCounter.count += k + (1 if spmm and args[3] > 0 else 0)  # + heavy-row reduce kernel
+        LaunchCounter.count += k
         return fn(*args)
 
     return call

@@ -24,6 +24,39 @@ __device__ __forceinline__ float ld_stream_f32(const float* p) {
     return r;
 }
 
+// A long row is split into chunks (one task each) whose partial sums land in `partials`.  The warp that
+// finishes the LAST chunk of a row (device-wide arrival counter in heavy[h].w) adds the partials up in chunk
+// order -- deterministic, no float atomics -- and resets the counter for the next launch.
+template <int D>
+__device__ __forceinline__ void finish_heavy_row(int slot, float* __restrict__ partials, int4* __restrict__ heavy, int n_heavy,
+                                                 float* __restrict__ Y, int64_t ldy, const float* __restrict__ Z, int64_t ldz, int lane) {
+    int lo = 0, hi = n_heavy - 1;  // heavy rows are sorted by first_slot: find the one owning `slot`
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (heavy[mid].y <= slot) lo = mid; else hi = mid - 1;
+    }
+    const int row = heavy[lo].x, first = heavy[lo].y, n_chunks = heavy[lo].z;
+    __threadfence();  // this warp's partial is visible device-wide before it is counted
+    int prev = 0;
+    if (lane == 0) prev = atomicAdd(&heavy[lo].w, 1);
+    prev = __shfl_sync(kFull, prev, 0);
+    if (prev != n_chunks - 1) return;
+    __threadfence();
+    for (int f = lane * 4; f < D; f += 128) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < n_chunks; ++c) {
+            const float4 p = __ldcg(reinterpret_cast<const float4*>(partials + (int64_t)(first + c) * D + f));
+            a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+        }
+        if (Z != nullptr) {
+            const float4 z = ld_stream4(Z + (int64_t)row * ldz + f);
+            a.x += z.x; a.y += z.y; a.z += z.z; a.w += z.w;
+        }
+        *reinterpret_cast<float4*>(Y + (int64_t)row * ldy + f) = a;
+    }
+    if (lane == 0) heavy[lo].w = 0;
+}
+
 // One warp per task.  The (byte offset, weight) pairs of 32 consecutive edges are staged in a
 // per-warp slab of shared memory (one coalesced global read + one STS.64 per lane), so the hot loop
 // per edge group is: LDS.64 (broadcast), LDG.128 (gather of the neighbour row), 4 FFMA -- no
@@ -34,7 +67,7 @@ __global__ void __launch_bounds__(128) spmm_task_kernel(const int4* __restrict__
                                                         const int32_t* __restrict__ col_idx, const float* __restrict__ vals,
                                                         const float* __restrict__ X, int64_t ldx, float* __restrict__ Y,
                                                         int64_t ldy, const float* __restrict__ Z, int64_t ldz,
-                                                        float* __restrict__ partials) {
+                                                        float* __restrict__ partials, int4* __restrict__ heavy, int n_heavy) {
     constexpr int LPE = D / 4;        // lanes per edge
     constexpr int EPW = 32 / LPE;     // edges per warp step
     constexpr int EPI = EPW * U;      // edges per unrolled iteration (divides 32)
@@ -104,6 +137,7 @@ __global__ void __launch_bounds__(128) spmm_task_kernel(const int4* __restrict__
             *reinterpret_cast<float4*>(partials + (int64_t)t.w * D + sub * 4) = acc;
         }
     }
+    if (t.w >= 0) finish_heavy_row<D>(t.w, partials, heavy, n_heavy, Y, ldy, Z, ldz, lane);
 }
 
 // any d % 4 == 0, d <= 256: a whole warp per edge, up to two float4 per lane
@@ -181,7 +215,7 @@ __global__ void __launch_bounds__(128) spmm_heavy_reduce_kernel(const int4* __re
 
 using namespace kgat;
 
-extern "C" int kgat_spmm_csr(const int32_t* tasks, int64_t n_tasks, const int32_t* heavy_rows, int64_t n_heavy,
+extern "C" int kgat_spmm_csr(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_rows, int64_t n_heavy,
                              const int32_t* col_idx, const float* vals, const float* X, int64_t n_cols, int64_t ldx, float* Y, int64_t ldy,
                              const float* Z, int64_t ldz, int32_t d, float* partials, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -194,10 +228,13 @@ extern "C" int kgat_spmm_csr(const int32_t* tasks, int64_t n_tasks, const int32_
     const int threads = 128;
     const unsigned blocks = (unsigned)((n_tasks * 32 + threads - 1) / threads);
     const int4* t4 = reinterpret_cast<const int4*>(tasks);
+    int4* h4 = reinterpret_cast<int4*>(heavy_rows);
+    bool fused_reduce = false;  // the templated kernels reduce heavy rows themselves (last chunk to arrive)
 #define KGAT_SPMM_LAUNCH(DD, UU)                                                                                              \
     do {                                                                                                                      \
-        if (use_wide) spmm_task_kernel<DD, UU, true><<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials); \
-        else spmm_task_kernel<DD, UU, false><<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials);        \
+        if (use_wide) spmm_task_kernel<DD, UU, true><<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, h4, (int)n_heavy); \
+        else spmm_task_kernel<DD, UU, false><<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, h4, (int)n_heavy);        \
+        fused_reduce = true;                                                                                                  \
     } while (0)
     switch (d) {
         case 16: KGAT_SPMM_LAUNCH(16, 2); break;
@@ -208,7 +245,7 @@ extern "C" int kgat_spmm_csr(const int32_t* tasks, int64_t n_tasks, const int32_
             spmm_task_kernel_generic<<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, d);
     }
 #undef KGAT_SPMM_LAUNCH
-    if (n_heavy > 0) {
+    if (n_heavy > 0 && !fused_reduce) {
         const unsigned hb = (unsigned)((n_heavy * 32 + threads - 1) / threads);
         spmm_heavy_reduce_kernel<<<hb, threads, 0, stream>>>(reinterpret_cast<const int4*>(heavy_rows), n_heavy, partials, Y, ldy, Z,
                                                              ldz, d);
