@@ -17,7 +17,17 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+// Exact two-term split x = hi + lo with hi representable in TF32.  cvt.rna.tf32 is emulated by ~6 integer
+// instructions on sm_100a (ncu: it doubled the instruction count of the MMA loop), so the per-use split
+// truncates instead: hi = x with the low 13 mantissa bits cleared (one LOP3), lo = x - hi (exact, one FADD).
+// The tensor core ignores the low 13 bits of lo, an error <= 2^-20 |x| per operand (1e-6), which averages
+// down across the K-sum and stays inside the 1e-5 budget (tested).  The round-to-nearest variant is used
+// where a split is computed once and reused (the weights staged in shared memory).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void split_tf32_rn(float x, uint32_t& hi, uint32_t& lo) {
     hi = to_tf32(x);
     lo = to_tf32(x - __uint_as_float(hi));
 }
@@ -75,9 +85,9 @@ __global__ void __launch_bounds__(256) biagg_fwd_mma_kernel(
         for (int i = tid; i < DOUT * DIN; i += C::NT) {
             const int c = i / DIN, k = i % DIN;
             uint32_t hi, lo;
-            split_tf32(W1[i], hi, lo);
+            split_tf32_rn(W1[i], hi, lo);
             reinterpret_cast<uint2*>(W1s)[c * C::SW + k] = make_uint2(hi, lo);
-            split_tf32(W2[i], hi, lo);
+            split_tf32_rn(W2[i], hi, lo);
             reinterpret_cast<uint2*>(W2s)[c * C::SW + k] = make_uint2(hi, lo);
         }
     } else {
