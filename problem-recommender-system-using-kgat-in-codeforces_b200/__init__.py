@@ -13,7 +13,8 @@ Layout
     model.py               KGAT, KGATArgs, KGATMode  (drop-in for src.model.KGAT.model)
     aggregator.py, multi_head_attention.py, optim.py
     ckg.py, synthetic.py   host-side CKG assembly and the seeded synthetic graphs of BASELINE.json
-    engine.py              CUDA-graph training engine, epoch driver
+    engine.py, trainer.py  CUDA-graph training engine, epoch driver
+    metrics.py             device-side evaluate loop (top-K + precision / recall / nDCG)
     sharding.py            row-sharded multi-GPU propagation (NCCL all-gather per layer)
 """
 
@@ -23,7 +24,7 @@ from .aggregator import Aggregator, AggregatorArgs  # noqa: F401
 from .model import KGAT, KGATArgs, KGATMode  # noqa: F401
 from .multi_head_attention import MultiHeadAttention  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
-from . import functions, graph, model, ops, optim  # noqa: F401,E402
+from . import engine, functions, graph, metrics, model, ops, optim, sampler, sharding, trainer  # noqa: F401,E402
 
 __all__ = [
     "KGAT", "KGATArgs", "KGATMode", "Aggregator", "AggregatorArgs", "MultiHeadAttention", "FusedAdam",
