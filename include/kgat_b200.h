@@ -261,6 +261,20 @@ int kgat_adam_lazy_flush(float* param, float* exp_avg, float* exp_avg_sq, int32_
 int kgat_select_batch_i64(const int64_t* src, int64_t n_batches, int64_t elems, const int64_t* counter_dev, int64_t* dst,
                           void* stream);
 
+/* ------------------------------------------------------------------------------------------- */
+/* P5: batch samplers on the device       reference preprocess.py:328-415 (CF), 417-530 (KG)   */
+/* ------------------------------------------------------------------------------------------- */
+/* CF batch: `batch` distinct users out of active_users (with replacement only if batch > n_active), one uniform
+ * positive item of the user, one uniform item not among the user's items (rejection, items sorted per user).
+ * out = [users | pos | neg], 3 x batch int64.  Randomness = Philox(seed, step_dev[0], sample index). */
+int kgat_sample_cf_batch(const int32_t* user_ptr, const int32_t* user_items, const int32_t* active_users, int32_t n_active,
+                         int32_t item_num, int32_t batch, uint64_t seed, const int64_t* step_dev, int64_t* out, void* stream);
+/* KG batch: `batch` distinct heads, one uniform (relation, tail) edge of the head, one uniform node that is not a
+ * tail of (head, relation) (edges sorted by (head, tail)).  out = [heads | rels | pos tails | neg tails], 4 x batch. */
+int kgat_sample_kg_batch(const int32_t* head_ptr, const int32_t* edge_rel, const int32_t* edge_tail, const int32_t* active_heads,
+                         int32_t n_active, int32_t node_num, int32_t batch, uint64_t seed, const int64_t* step_dev, int64_t* out,
+                         void* stream);
+
 /* utility: fill used by the host glue so no torch kernel sits on the hot path */
 int kgat_fill_f32(float* p, int64_t n, float value, void* stream);
 

@@ -101,6 +101,8 @@ SIGNATURES: dict[str, tuple] = {
     "kgat_adam_lazy_flush": (_I32, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P]),
     "kgat_fill_f32": (_I32, [_P, _I64, _F, _P]),
     "kgat_select_batch_i64": (_I32, [_P, _I64, _I64, _P, _P, _P]),
+    "kgat_sample_cf_batch": (_I32, [_P, _P, _P, _I32, _I32, _I32, _U64, _P, _P, _P]),
+    "kgat_sample_kg_batch": (_I32, [_P, _P, _P, _P, _I32, _I32, _I32, _U64, _P, _P, _P]),
 }
 
 _lib = None
@@ -113,7 +115,7 @@ KERNELS_PER_CALL = {
     "kgat_transr_backward": 1, "kgat_att_pair_scores": 1, "kgat_att_edge_scores_dropout": 1, "kgat_att_row_softmax": 1,
     "kgat_att_edge_weights": 1, "kgat_gather_concat": 1, "kgat_sgemm_nt": 1, "kgat_mask_scores": 1, "kgat_topk_rows": 1,
     "kgat_adam_advance": 1, "kgat_adam_set_hyper": 1, "kgat_adam_apply": 1, "kgat_adam_hyper_table": 1, "kgat_adam_lazy_catchup": 1, "kgat_adam_sparse_rows": 1,
-    "kgat_adam_lazy_flush": 1, "kgat_fill_f32": 1, "kgat_select_batch_i64": 1,
+    "kgat_adam_lazy_flush": 1, "kgat_fill_f32": 1, "kgat_select_batch_i64": 1, "kgat_sample_cf_batch": 1, "kgat_sample_kg_batch": 1,
 }
 
 

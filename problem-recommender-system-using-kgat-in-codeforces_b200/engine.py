@@ -100,6 +100,7 @@ class TrainEngine:
         self.kg_s0 = torch.zeros(1, dtype=torch.int64, device=dev)
         self.kg_table = None
         self._resident: EpochData | None = None
+        self.device_sampler = None  # sampler.DeviceSampler: draw every batch on the device inside the captured step
         self._graphs: dict = {}
         self._graph_token = None
 
@@ -108,7 +109,9 @@ class TrainEngine:
     # ------------------------------------------------------------------------------------------
     def _cf_body(self, select: bool):
         m = self.model
-        if select:
+        if select and self.device_sampler is not None:
+            self.device_sampler.cf_batch(self.cf_adam.step_dev, self.cf_ids)
+        elif select:
             ops.select_batch(self._resident.cf, self.cf_adam.step_dev, self.cf_ids.view(-1))
         u, p, n = self.cf_ids[0], self.cf_ids[1], self.cf_ids[2]
         graph = m._graph()
@@ -134,7 +137,9 @@ class TrainEngine:
 
     def _kg_body(self, select: bool):
         m = self.model
-        if select:
+        if select and self.device_sampler is not None:
+            self.device_sampler.kg_batch(self.kg_adam.step_dev, self.kg_ids)
+        elif select:
             ops.select_batch(self._resident.kg, self.kg_adam.step_dev, self.kg_ids.view(-1))
         h, r, pt, nt = self.kg_ids[0], self.kg_ids[1], self.kg_ids[2], self.kg_ids[3]
         emb, rel, w = (p.detach() for p in self.kg_params)
@@ -189,7 +194,7 @@ class TrainEngine:
     # ------------------------------------------------------------------------------------------
     def _token(self):
         g = self.model._graph()
-        return (id(g), g.vals.data_ptr(), g.t_vals.data_ptr(), self.model.training, id(self._resident))
+        return (id(g), g.vals.data_ptr(), g.t_vals.data_ptr(), self.model.training, id(self._resident), id(self.device_sampler))
 
     def _get(self, kind: str, select: bool):
         """Returns a callable running one step (a captured graph replay when graphs are enabled)."""

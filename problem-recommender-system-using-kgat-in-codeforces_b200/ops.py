@@ -498,3 +498,20 @@ def adam_lazy_flush(param, exp_avg, exp_avg_sq, row_step, cur_step_dev, s0, tabl
     check(lib.kgat_adam_lazy_flush(_ptr(param, f32), _ptr(exp_avg, f32), _ptr(exp_avg_sq, f32), _ptr(row_step, i32), param.shape[0],
                                    param.shape[1], _ptr(cur_step_dev, i64), _ptr(s0, i64), _ptr(table, f32), _ptr(hyper, f32), _stream()),
           "adam_lazy_flush")
+
+
+def sample_cf_batch(user_ptr, user_items, active_users, item_num: int, seed: int, step_dev, out):
+    """out: int64 [3, B] <- (users, pos, neg), drawn on the device (csrc/sampler.cu)."""
+    lib = _lib.load()
+    check(lib.kgat_sample_cf_batch(_ptr(user_ptr, i32), _ptr(user_items, i32), _ptr(active_users, i32), active_users.numel(), int(item_num),
+                                   out.shape[1], int(seed), _ptr(step_dev, i64), _ptr(out, i64), _stream()), "sample_cf_batch")
+    return out
+
+
+def sample_kg_batch(head_ptr, edge_rel, edge_tail, active_heads, node_num: int, seed: int, step_dev, out):
+    """out: int64 [4, B] <- (heads, rels, pos tails, neg tails), drawn on the device."""
+    lib = _lib.load()
+    check(lib.kgat_sample_kg_batch(_ptr(head_ptr, i32), _ptr(edge_rel, i32), _ptr(edge_tail, i32), _ptr(active_heads, i32),
+                                   active_heads.numel(), int(node_num), out.shape[1], int(seed), _ptr(step_dev, i64), _ptr(out, i64),
+                                   _stream()), "sample_kg_batch")
+    return out

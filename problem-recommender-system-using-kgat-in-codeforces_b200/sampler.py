@@ -80,3 +80,35 @@ class BatchSampler:
                 break
             neg[bad] = rng.integers(0, n, size=int(bad.sum()))
         return heads, rels, pos, neg
+
+
+class DeviceSampler:
+    """Device-resident sampling structures + the sampling kernels (csrc/sampler.cu): user -> sorted items CSR for
+    the BPR sampler, head -> (relation, tail) edges sorted by tail for the KG sampler."""
+
+    def __init__(self, g: CKG, device, seed: int = 2024):
+        import torch
+
+        from . import ops
+
+        self._ops, self.g, self.seed = ops, g, int(seed)
+        tr = g.train_interactions
+        order = np.lexsort((tr[:, 1], tr[:, 0]))
+        tr = tr[order]
+        counts = np.bincount(tr[:, 0], minlength=g.user_num)
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a.astype(np.int32))).to(device)  # noqa: E731
+        self.user_ptr = to(np.concatenate([[0], np.cumsum(counts)]))
+        self.user_items = to(tr[:, 1])
+        self.active_users = to(np.nonzero(counts)[0])
+        hcounts = np.bincount(g.heads, minlength=g.node_num)
+        self.head_ptr = to(np.concatenate([[0], np.cumsum(hcounts)]))
+        self.edge_rel = to(g.relations)  # edge list is sorted by (head, tail)
+        self.edge_tail = to(g.tails)
+        self.active_heads = to(np.nonzero(hcounts)[0])
+
+    def cf_batch(self, step_dev, out):
+        return self._ops.sample_cf_batch(self.user_ptr, self.user_items, self.active_users, self.g.item_num, self.seed, step_dev, out)
+
+    def kg_batch(self, step_dev, out):
+        return self._ops.sample_kg_batch(self.head_ptr, self.edge_rel, self.edge_tail, self.active_heads, self.g.node_num, self.seed + 1,
+                                         step_dev, out)
