@@ -32,9 +32,11 @@ extern "C" {
 #define KGAT_ERR_UNSUPPORTED (-3)
 #define KGAT_ERR_WORKSPACE (-4)
 
-#define KGAT_ABI_VERSION 1
+#define KGAT_ABI_VERSION 2
 #define KGAT_MAX_LAYERS 8   /* embedding table + up to 7 propagation layers */
 #define KGAT_MAX_TENSORS 24 /* tensors per multi-tensor Adam launch */
+#define KGAT_MAX_PEERS 31   /* other ranks of a row-sharded propagation */
+#define KGAT_PEER_HANDLE_BYTES 64
 
 /* ------------------------------------------------------------------------------------------- */
 /* misc                                                                                        */
@@ -103,21 +105,24 @@ int kgat_spmm_csr(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_rows, in
  * keep_bits (packed, (d_out+31)/32 words per row, bit=1 keeps) when non-NULL, else from the Philox
  * counter RNG (seed, offset) when p > 0; seed_dev (nullable device u64, e.g. the optimiser's step
  * counter) is mixed into the seed so a replayed CUDA graph draws a fresh mask every step.  Saved for backward: inv_norm[n] (1/max(||x||,eps); negative
- * when the eps clamp was active) and flags[n x d_out] (bit0: z1 > 0, bit1: z2 > 0, bit2: kept). */
+ * when the eps clamp was active) and flags[n x d_out] (bit0: z1 > 0, bit1: z2 > 0, bit2: kept).
+ * Row-sharded use: with n_peers > 0 the output rows are ALSO stored at the same row offset behind each of the
+ * n_peers device pointers in the DEVICE array peer_out (the peers' copies of the table, kgat_peer_import), tile by
+ * tile from the kernel's epilogue, so the exchange overlaps the computation; (NULL, 0) otherwise. */
 int kgat_biagg_forward(const float* E, const float* S, int64_t n, int32_t d_in, int32_t d_out, const float* W1,
                        const float* b1, const float* W2, const float* b2, float dropout_p, uint64_t seed,
                        uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits, float* out, int64_t ld_out,
-                       float* inv_norm, uint8_t* flags, void* stream);
+                       float* inv_norm, uint8_t* flags, float* const* peer_out, int32_t n_peers, void* stream);
 
 /* Backward of the above.  g_out: n x d_out (ld_gout).  Produces g_S and g_E_direct (n x d_in) and
  * per-CTA partial parameter gradients in `partials` (n_ctas x (2*d_out*d_in + 2*d_out) floats,
  * n_ctas from kgat_biagg_backward_ctas), which kgat_biagg_reduce_param_grads sums in a fixed order
- * into gW1, gb1, gW2, gb2 (accumulate = 0 overwrites, 1 adds). */
+ * into gW1, gb1, gW2, gb2 (accumulate = 0 overwrites, 1 adds).  peer_gS / n_peers: as peer_out above, for g_S. */
 int kgat_biagg_backward_ctas(int64_t n, int32_t d_in, int32_t d_out);
 int kgat_biagg_backward(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm,
                         const uint8_t* flags, const float* E, const float* S, int64_t n, int32_t d_in, int32_t d_out,
                         const float* W1, const float* W2, float dropout_p, float* g_S, float* g_E, float* partials,
-                        int32_t n_ctas, void* stream);
+                        int32_t n_ctas, float* const* peer_gS, int32_t n_peers, void* stream);
 int kgat_biagg_reduce_param_grads(const float* partials, int32_t n_ctas, int32_t d_in, int32_t d_out, float* gW1,
                                   float* gb1, float* gW2, float* gb2, int32_t accumulate, void* stream);
 
@@ -228,6 +233,10 @@ typedef struct {
     float* exp_avg[KGAT_MAX_TENSORS];
     float* exp_avg_sq[KGAT_MAX_TENSORS];
     int64_t numel[KGAT_MAX_TENSORS];
+    /* row-sharded use: the updated values of tensor 0 (this rank's embedding rows) are also stored at the same
+     * offset behind each of the n_peers device pointers of the DEVICE array peer_param0; (NULL, 0) otherwise */
+    float* const* peer_param0;
+    int32_t n_peers;
 } kgat_adam_tensors_t;
 /* One torch.optim.Adam step (no weight decay, no amsgrad) over all listed tensors in one launch,
  * split in two so a captured CUDA graph replays correctly: kgat_adam_advance increments the device
@@ -274,6 +283,28 @@ int kgat_sample_cf_batch(const int32_t* user_ptr, const int32_t* user_items, con
 int kgat_sample_kg_batch(const int32_t* head_ptr, const int32_t* edge_rel, const int32_t* edge_tail, const int32_t* active_heads,
                          int32_t n_active, int32_t node_num, int32_t batch, uint64_t seed, const int64_t* step_dev, int64_t* out,
                          void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* (e) multi-GPU: row exchange over NVLink peer memory.  No counterpart in the reference (single   */
+/* device); replaces the all-gather that follows every propagation layer of the row-sharded       */
+/* aggregator.py:54-65 / its backward.  See csrc/peer.cu for the protocol.                        */
+/* ------------------------------------------------------------------------------------------- */
+/* The only entry points that allocate: an IPC-exportable, zero-filled device allocation, its 64-byte handle,
+ * and the mapping of a peer's handle into this process (same node, NVLink / PCIe peer access). */
+int kgat_peer_alloc(int64_t bytes, void** ptr);
+int kgat_peer_free(void* ptr);
+int kgat_peer_export(const void* ptr, void* handle64);
+int kgat_peer_import(const void* handle64, void** ptr);
+int kgat_peer_close(void* ptr);
+/* Copy n_floats (multiple of 4, 16-byte aligned) from src to peer_dst[q] for q < n_peers.  peer_dst is a DEVICE
+ * array of n_peers device pointers into the peers' mapped allocations. */
+int kgat_peer_push(const float* src, float* const* peer_dst, int32_t n_peers, int64_t n_floats, void* stream);
+/* Channel handshake: seq[0] += 1; store it to *peer_flags[q] (my slot in peer q's flag pad) and wait until
+ * my_flags[q] (written by peer q) has reached it, for every q < n_peers.  After it returns, everything the peers
+ * stored into this rank's memory before *their* matching call is visible.  A wait longer than timeout_cycles SM
+ * clocks sets status[0] = 1 and gives up (no hang).  peer_flags: DEVICE array of device pointers. */
+int kgat_peer_signal_wait(int32_t* const* peer_flags, const int32_t* my_flags, int32_t n_peers, int32_t* seq, int32_t* status,
+                          int64_t timeout_cycles, void* stream);
 
 /* utility: fill used by the host glue so no torch kernel sits on the hot path */
 int kgat_fill_f32(float* p, int64_t n, float value, void* stream);

@@ -13,7 +13,7 @@ from pathlib import Path
 
 KGAT_MAX_LAYERS = 8
 KGAT_MAX_TENSORS = 24
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("KGAT_B200_LIB", _PKG_DIR / "lib" / "libkgat_b200.so"))
@@ -53,6 +53,8 @@ class AdamTensorsT(C.Structure):
         ("exp_avg", C.c_void_p * KGAT_MAX_TENSORS),
         ("exp_avg_sq", C.c_void_p * KGAT_MAX_TENSORS),
         ("numel", C.c_int64 * KGAT_MAX_TENSORS),
+        ("peer_param0", C.c_void_p),
+        ("n_peers", C.c_int32),
     ]
 
 
@@ -76,9 +78,9 @@ SIGNATURES: dict[str, tuple] = {
     "kgat_gather_f32": (_I32, [_P, _P, _I64, _P, _P]),
     "kgat_ids64_to_i32": (_I32, [_P, _I64, _I64, _P, _P, _P]),
     "kgat_spmm_csr": (_I32, [_P, _I64, _P, _I64, _P, _P, _P, _I64, _I64, _P, _I64, _P, _I64, _I32, _P, _P]),
-    "kgat_biagg_forward": (_I32, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _F, _U64, _U64, _P, _P, _P, _I64, _P, _P, _P]),
+    "kgat_biagg_forward": (_I32, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _F, _U64, _U64, _P, _P, _P, _I64, _P, _P, _P, _I32, _P]),
     "kgat_biagg_backward_ctas": (_I32, [_I64, _I32, _I32]),
-    "kgat_biagg_backward": (_I32, [_P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _F, _P, _P, _P, _I32, _P]),
+    "kgat_biagg_backward": (_I32, [_P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _F, _P, _P, _P, _I32, _P, _I32, _P]),
     "kgat_biagg_reduce_param_grads": (_I32, [_P, _I32, _I32, _I32, _P, _P, _P, _P, _I32, _P]),
     "kgat_bpr_forward": (_I32, [C.POINTER(TablesT), _P, _P, _P, _I32, _F, _P, _P, _P]),
     "kgat_bpr_backward": (_I32, [C.POINTER(TablesT), C.POINTER(TablesT), _P, _P, _P, _I32, _F, _P, _P, _P]),
@@ -103,6 +105,13 @@ SIGNATURES: dict[str, tuple] = {
     "kgat_select_batch_i64": (_I32, [_P, _I64, _I64, _P, _P, _P]),
     "kgat_sample_cf_batch": (_I32, [_P, _P, _P, _I32, _I32, _I32, _U64, _P, _P, _P]),
     "kgat_sample_kg_batch": (_I32, [_P, _P, _P, _P, _I32, _I32, _I32, _U64, _P, _P, _P]),
+    "kgat_peer_alloc": (_I32, [_I64, _P]),
+    "kgat_peer_free": (_I32, [_P]),
+    "kgat_peer_export": (_I32, [_P, _P]),
+    "kgat_peer_import": (_I32, [_P, _P]),
+    "kgat_peer_close": (_I32, [_P]),
+    "kgat_peer_push": (_I32, [_P, _P, _I32, _I64, _P]),
+    "kgat_peer_signal_wait": (_I32, [_P, _P, _I32, _P, _P, _I64, _P]),
 }
 
 _lib = None
@@ -116,6 +125,7 @@ KERNELS_PER_CALL = {
     "kgat_att_edge_weights": 1, "kgat_gather_concat": 1, "kgat_sgemm_nt": 1, "kgat_mask_scores": 1, "kgat_topk_rows": 1,
     "kgat_adam_advance": 1, "kgat_adam_set_hyper": 1, "kgat_adam_apply": 1, "kgat_adam_hyper_table": 1, "kgat_adam_lazy_catchup": 1, "kgat_adam_sparse_rows": 1,
     "kgat_adam_lazy_flush": 1, "kgat_fill_f32": 1, "kgat_select_batch_i64": 1, "kgat_sample_cf_batch": 1, "kgat_sample_kg_batch": 1,
+    "kgat_peer_push": 1, "kgat_peer_signal_wait": 1,
 }
 
 

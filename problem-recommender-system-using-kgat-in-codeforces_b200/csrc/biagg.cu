@@ -429,11 +429,13 @@ namespace kgat {
 // tensor-core (3xTF32 mma.sync) implementation, biagg_mma.cu
 int biagg_mma_forward(const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* b1, const float* W2,
                       const float* b2, float p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits,
-                      float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, cudaStream_t stream);
+                      float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, float* const* peer_out, int n_peers, cudaStream_t stream);
 int biagg_mma_backward_ctas(int64_t n, int d_in, int d_out);
 int biagg_mma_backward(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm, const uint8_t* flags,
                        const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* W2, float p, float* g_S,
-                       float* g_E, float* partials, int n_ctas, cudaStream_t stream);
+                       float* g_E, float* partials, int n_ctas, float* const* peer_gS, int n_peers, cudaStream_t stream);
+// peer.cu: copy n_floats to the same offset behind every peer pointer
+int peer_push_launch(const float* src, float* const* peer_dst, int n_peers, int64_t n_floats, cudaStream_t stream);
 
 // KGAT_BIAGG_IMPL=ffma selects the CUDA-core kernels of this file (A/B comparison); default: tensor cores
 static bool use_mma() {
@@ -468,14 +470,21 @@ extern "C" {
 
 int kgat_biagg_forward(const float* E, const float* S, int64_t n, int32_t d_in, int32_t d_out, const float* W1, const float* b1,
                        const float* W2, const float* b2, float dropout_p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev,
-                       const uint32_t* keep_bits, float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, void* stream) {
-    if (n < 0 || dropout_p < 0.f || dropout_p >= 1.f || (ld_out & 3)) return KGAT_ERR_INVALID_ARGUMENT;
+                       const uint32_t* keep_bits, float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, float* const* peer_out,
+                       int32_t n_peers, void* stream) {
+    if (n < 0 || dropout_p < 0.f || dropout_p >= 1.f || (ld_out & 3) || n_peers < 0 || n_peers > KGAT_MAX_PEERS || (n_peers && !peer_out))
+        return KGAT_ERR_INVALID_ARGUMENT;
     if (n == 0) return KGAT_OK;
     if (use_mma())
         return biagg_mma_forward(E, S, n, d_in, d_out, W1, b1, W2, b2, dropout_p, seed, offset, seed_dev, keep_bits, out, ld_out, inv_norm,
-                                 flags, (cudaStream_t)stream);
-    KGAT_DISPATCH_DIMS(d_in, d_out, return (launch_fwd<DI, DO>(E, S, n, W1, b1, W2, b2, dropout_p, seed, offset, seed_dev, keep_bits, out, ld_out,
-                                                               inv_norm, flags, (cudaStream_t)stream)));
+                                 flags, peer_out, n_peers, (cudaStream_t)stream);
+    if (n_peers > 0 && ld_out != d_out) return KGAT_ERR_UNSUPPORTED;
+    const int rc = [&]() -> int {
+        KGAT_DISPATCH_DIMS(d_in, d_out, return (launch_fwd<DI, DO>(E, S, n, W1, b1, W2, b2, dropout_p, seed, offset, seed_dev, keep_bits, out,
+                                                                   ld_out, inv_norm, flags, (cudaStream_t)stream)));
+    }();
+    if (rc != KGAT_OK || n_peers == 0) return rc;
+    return peer_push_launch(out, peer_out, n_peers, n * d_out, (cudaStream_t)stream);  // CUDA-core path: unfused push
 }
 
 int kgat_biagg_backward_ctas(int64_t n, int32_t d_in, int32_t d_out) {
@@ -486,13 +495,19 @@ int kgat_biagg_backward_ctas(int64_t n, int32_t d_in, int32_t d_out) {
 
 int kgat_biagg_backward(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm,
                         const uint8_t* flags, const float* E, const float* S, int64_t n, int32_t d_in, int32_t d_out, const float* W1,
-                        const float* W2, float dropout_p, float* g_S, float* g_E, float* partials, int32_t n_ctas, void* stream) {
-    if (n <= 0 || n_ctas <= 0 || (ld_gout & 3) || (ld_out & 3)) return KGAT_ERR_INVALID_ARGUMENT;
+                        const float* W2, float dropout_p, float* g_S, float* g_E, float* partials, int32_t n_ctas, float* const* peer_gS,
+                        int32_t n_peers, void* stream) {
+    if (n <= 0 || n_ctas <= 0 || (ld_gout & 3) || (ld_out & 3) || n_peers < 0 || n_peers > KGAT_MAX_PEERS || (n_peers && !peer_gS))
+        return KGAT_ERR_INVALID_ARGUMENT;
     if (use_mma())
         return biagg_mma_backward(g_out, ld_gout, out, ld_out, inv_norm, flags, E, S, n, d_in, d_out, W1, W2, dropout_p, g_S, g_E, partials,
-                                  n_ctas, (cudaStream_t)stream);
-    KGAT_DISPATCH_DIMS(d_in, d_out, return (launch_bwd<DI, DO>(g_out, ld_gout, out, ld_out, inv_norm, flags, E, S, n, W1, W2, dropout_p,
-                                                               g_S, g_E, partials, n_ctas, (cudaStream_t)stream)));
+                                  n_ctas, peer_gS, n_peers, (cudaStream_t)stream);
+    const int rc = [&]() -> int {
+        KGAT_DISPATCH_DIMS(d_in, d_out, return (launch_bwd<DI, DO>(g_out, ld_gout, out, ld_out, inv_norm, flags, E, S, n, W1, W2, dropout_p,
+                                                                   g_S, g_E, partials, n_ctas, (cudaStream_t)stream)));
+    }();
+    if (rc != KGAT_OK || n_peers == 0) return rc;
+    return peer_push_launch(g_S, peer_gS, n_peers, n * d_in, (cudaStream_t)stream);
 }
 
 int kgat_biagg_reduce_param_grads(const float* partials, int32_t n_ctas, int32_t d_in, int32_t d_out, float* gW1, float* gb1,

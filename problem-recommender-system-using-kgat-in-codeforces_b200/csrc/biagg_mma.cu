@@ -69,8 +69,10 @@ __global__ void __launch_bounds__(256) biagg_fwd_mma_kernel(
     const float* __restrict__ E, const float* __restrict__ S, int64_t n, const float* __restrict__ W1,
     const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2, float dropout_p,
     uint64_t seed, uint64_t offset, const uint64_t* __restrict__ seed_dev, const uint32_t* __restrict__ keep_bits,
-    float* __restrict__ out, int64_t ld_out, float* __restrict__ inv_norm, uint8_t* __restrict__ flags) {
+    float* __restrict__ out, int64_t ld_out, float* __restrict__ inv_norm, uint8_t* __restrict__ flags,
+    float* const* __restrict__ peer_out, int n_peers) {
     using C = FwdCfg<DIN, DOUT>;
+    static_assert(DOUT <= DIN, "the output tile is staged in the E+S tile for the peer stores");
     extern __shared__ __align__(16) float smem[];
     if (seed_dev != nullptr) seed += seed_dev[0] * 0x9E3779B97F4A7C15ull;
     float* W1s = smem;                      // [DOUT][SW] (x2 when pre-split: (hi, lo) pairs)
@@ -237,10 +239,25 @@ __global__ void __launch_bounds__(256) biagg_fwd_mma_kernel(
 #pragma unroll
             for (int j = 0; j < C::NTW; ++j) {
                 const int c = (nt0 + j) * 8 + 2 * t;
-                *reinterpret_cast<float2*>(out + row * ld_out + c) = make_float2(x[h][j][0] * rinv, x[h][j][1] * rinv);
+                const float2 o = make_float2(x[h][j][0] * rinv, x[h][j][1] * rinv);
+                *reinterpret_cast<float2*>(out + row * ld_out + c) = o;
+                // every warp is past its MMA loop (barrier above): the E+S tile is free to stage the output rows
+                if (n_peers > 0) *reinterpret_cast<float2*>(Us + (mt * 16 + g + 8 * h) * C::SE + c) = o;
                 if (flags != nullptr) *reinterpret_cast<uchar2*>(flags + row * DOUT + c) = make_uchar2(f[h][j][0], f[h][j][1]);
             }
             if (inv_norm != nullptr && t == 0 && nw == 0) inv_norm[row] = nrm < KGAT_NORM_EPS ? -rinv : rinv;
+        }
+        if (n_peers > 0) {
+            // row-sharded propagation: the finished rows also go into every peer's copy of the table (NVLink peer
+            // stores, 512 B per warp instruction), overlapping the next tile's loads and MMAs
+            __syncthreads();
+            for (int i = tid; i < C::TM * (DOUT / 4); i += C::NT) {
+                const int r = i / (DOUT / 4), q4 = i % (DOUT / 4);
+                if (row0 + r < n) {
+                    const float4 v = *reinterpret_cast<const float4*>(Us + r * C::SE + q4 * 4);
+                    for (int q = 0; q < n_peers; ++q) *reinterpret_cast<float4*>(peer_out[q] + (row0 + r) * ld_out + q4 * 4) = v;
+                }
+            }
         }
     }
 }
@@ -279,7 +296,7 @@ __global__ void __launch_bounds__(BwdCfg<DIN, DOUT>::NT) biagg_bwd_mma_kernel(
     const float* __restrict__ g_out, int64_t ld_gout, const float* __restrict__ out, int64_t ld_out,
     const float* __restrict__ inv_norm, const uint8_t* __restrict__ flags, const float* __restrict__ E,
     const float* __restrict__ S, int64_t n, const float* __restrict__ W1, const float* __restrict__ W2, float dropout_p,
-    float* __restrict__ g_S, float* __restrict__ g_E, float* __restrict__ partials) {
+    float* __restrict__ g_S, float* __restrict__ g_E, float* __restrict__ partials, float* const* __restrict__ peer_gS, int n_peers) {
     using C = BwdCfg<DIN, DOUT>;
     extern __shared__ __align__(16) float smem[];
     float* W1s = smem;                    // [DOUT][SW]
@@ -416,8 +433,9 @@ __global__ void __launch_bounds__(BwdCfg<DIN, DOUT>::NT) biagg_bwd_mma_kernel(
                         const float2 e = *reinterpret_cast<const float2*>(Es + r * C::SE + k);
                         const float2 s2 = *reinterpret_cast<const float2*>(Ss + r * C::SE + k);
                         // u = E + S, v = E * S:  dS = gu + gv * E,  dE = gu + gv * S
-                        *reinterpret_cast<float2*>(g_S + row * DIN + k) =
-                            make_float2(fmaf(gv[q][2 * h], e.x, gu[q][2 * h]), fmaf(gv[q][2 * h + 1], e.y, gu[q][2 * h + 1]));
+                        const float2 gs = make_float2(fmaf(gv[q][2 * h], e.x, gu[q][2 * h]), fmaf(gv[q][2 * h + 1], e.y, gu[q][2 * h + 1]));
+                        *reinterpret_cast<float2*>(g_S + row * DIN + k) = gs;
+                        for (int pq = 0; pq < n_peers; ++pq) *reinterpret_cast<float2*>(peer_gS[pq] + row * DIN + k) = gs;
                         *reinterpret_cast<float2*>(g_E + row * DIN + k) =
                             make_float2(fmaf(gv[q][2 * h], s2.x, gu[q][2 * h]), fmaf(gv[q][2 * h + 1], s2.y, gu[q][2 * h + 1]));
                     }
@@ -507,7 +525,7 @@ inline int grid_for(int64_t n, int tm, size_t smem_bytes) {
 template <int DIN, int DOUT>
 int launch_fwd(const float* E, const float* S, int64_t n, const float* W1, const float* b1, const float* W2, const float* b2,
                float p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits, float* out, int64_t ld_out,
-               float* inv_norm, uint8_t* flags, cudaStream_t stream) {
+               float* inv_norm, uint8_t* flags, float* const* peer_out, int n_peers, cudaStream_t stream) {
     using C = FwdCfg<DIN, DOUT>;
     static bool configured = false;
     if (!configured) {
@@ -515,14 +533,15 @@ int launch_fwd(const float* E, const float* S, int64_t n, const float* W1, const
         configured = true;
     }
     biagg_fwd_mma_kernel<DIN, DOUT><<<grid_for(n, C::TM, C::smem), C::NT, C::smem, stream>>>(E, S, n, W1, b1, W2, b2, p, seed, offset, seed_dev,
-                                                                                         keep_bits, out, ld_out, inv_norm, flags);
+                                                                                         keep_bits, out, ld_out, inv_norm, flags, peer_out,
+                                                                                         n_peers);
     return check_launch();
 }
 
 template <int DIN, int DOUT>
 int launch_bwd(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm, const uint8_t* flags,
                const float* E, const float* S, int64_t n, const float* W1, const float* W2, float p, float* g_S, float* g_E,
-               float* partials, int n_ctas, cudaStream_t stream) {
+               float* partials, int n_ctas, float* const* peer_gS, int n_peers, cudaStream_t stream) {
     using C = BwdCfg<DIN, DOUT>;
     static bool configured = false;
     if (!configured) {
@@ -530,7 +549,7 @@ int launch_bwd(const float* g_out, int64_t ld_gout, const float* out, int64_t ld
         configured = true;
     }
     biagg_bwd_mma_kernel<DIN, DOUT><<<n_ctas, C::NT, C::smem, stream>>>(g_out, ld_gout, out, ld_out, inv_norm, flags, E, S, n, W1, W2, p, g_S,
-                                                                    g_E, partials);
+                                                                    g_E, partials, peer_gS, n_peers);
     return check_launch();
 }
 
@@ -554,9 +573,9 @@ int launch_bwd(const float* g_out, int64_t ld_gout, const float* out, int64_t ld
 
 int biagg_mma_forward(const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* b1, const float* W2,
                       const float* b2, float p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits,
-                      float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, cudaStream_t stream) {
+                      float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, float* const* peer_out, int n_peers, cudaStream_t stream) {
     KGAT_MMA_DISPATCH(d_in, d_out, return (mma::launch_fwd<DI, DO>(E, S, n, W1, b1, W2, b2, p, seed, offset, seed_dev, keep_bits, out, ld_out,
-                                                                   inv_norm, flags, stream)));
+                                                                   inv_norm, flags, peer_out, n_peers, stream)));
 }
 
 int biagg_mma_backward_ctas(int64_t n, int d_in, int d_out) {
@@ -565,9 +584,9 @@ int biagg_mma_backward_ctas(int64_t n, int d_in, int d_out) {
 
 int biagg_mma_backward(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm, const uint8_t* flags,
                        const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* W2, float p, float* g_S,
-                       float* g_E, float* partials, int n_ctas, cudaStream_t stream) {
+                       float* g_E, float* partials, int n_ctas, float* const* peer_gS, int n_peers, cudaStream_t stream) {
     KGAT_MMA_DISPATCH(d_in, d_out, return (mma::launch_bwd<DI, DO>(g_out, ld_gout, out, ld_out, inv_norm, flags, E, S, n, W1, W2, p, g_S, g_E,
-                                                                   partials, n_ctas, stream)));
+                                                                   partials, n_ctas, peer_gS, n_peers, stream)));
 }
 
 }  // namespace kgat

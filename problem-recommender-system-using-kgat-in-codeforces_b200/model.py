@@ -378,12 +378,10 @@ class KGAT(nn.Module):
         self._kg_optimizer = FusedAdam(params=self.parameters(), lr=kg_lr)
 
     def update_cf_weights(self) -> None:
-        self._cf_optimizer.step()
-        self._cf_optimizer.zero_grad()
+        self._cf_optimizer.step_and_zero()
 
     def update_kg_weights(self) -> None:
-        self._kg_optimizer.step()
-        self._kg_optimizer.zero_grad()
+        self._kg_optimizer.step_and_zero()
 
     # ------------------------------------------------------------------------------------------
     # A2: dispatch

@@ -213,7 +213,9 @@ def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.
 
 
 @_timed(lambda E, S, W1, *a, **k: f"biagg_fwd_{E.shape[1]}x{W1.shape[0]}")
-def biagg_forward(E, S, W1, b1, W2, b2, out, inv_norm, flags, dropout_p=0.0, seed=0, offset=0, keep_bits=None, seed_dev=None):
+def biagg_forward(E, S, W1, b1, W2, b2, out, inv_norm, flags, dropout_p=0.0, seed=0, offset=0, keep_bits=None, seed_dev=None,
+                  peer_out=None):
+    """``peer_out``: int64 device tensor of pointers to this rank's rows in every peer's copy of ``out`` (peer.PeerArena)."""
     lib = _lib.load()
     n, d_in = E.shape
     d_out = W1.shape[0]
@@ -223,7 +225,8 @@ def biagg_forward(E, S, W1, b1, W2, b2, out, inv_norm, flags, dropout_p=0.0, see
             float(dropout_p), int(seed), int(offset), _ptr(seed_dev, i64) if seed_dev is not None else None,
             _ptr(keep_bits, i32) if keep_bits is not None else None,
             _ptr(out, f32, "out"), out.stride(0), _ptr(inv_norm, f32) if inv_norm is not None else None,
-            _ptr(flags, u8) if flags is not None else None, _stream(),
+            _ptr(flags, u8) if flags is not None else None,
+            _ptr(peer_out, i64) if peer_out is not None else None, peer_out.numel() if peer_out is not None else 0, _stream(),
         ),
         f"biagg_forward({d_in}->{d_out})",
     )
@@ -235,7 +238,7 @@ def biagg_backward_ctas(n: int, d_in: int, d_out: int) -> int:
 
 
 @_timed(lambda g_out, out, inv_norm, flags, E, S, W1, *a, **k: f"biagg_bwd_{E.shape[1]}x{W1.shape[0]}")
-def biagg_backward(g_out, out, inv_norm, flags, E, S, W1, W2, dropout_p, g_S, g_E, partials, n_ctas):
+def biagg_backward(g_out, out, inv_norm, flags, E, S, W1, W2, dropout_p, g_S, g_E, partials, n_ctas, peer_out=None):
     lib = _lib.load()
     n, d_in = E.shape
     d_out = W1.shape[0]
@@ -245,7 +248,8 @@ def biagg_backward(g_out, out, inv_norm, flags, E, S, W1, W2, dropout_p, g_S, g_
         lib.kgat_biagg_backward(
             _ptr(g_out, f32, "g_out"), g_out.stride(0), _ptr(out, f32), out.stride(0), _ptr(inv_norm, f32), _ptr(flags, u8),
             _ptr(E, f32), _ptr(S, f32), n, d_in, d_out, _ptr(W1, f32), _ptr(W2, f32), float(dropout_p), _ptr(g_S, f32),
-            _ptr(g_E, f32), _ptr(partials, f32), n_ctas, _stream(),
+            _ptr(g_E, f32), _ptr(partials, f32), n_ctas,
+            _ptr(peer_out, i64) if peer_out is not None else None, peer_out.numel() if peer_out is not None else 0, _stream(),
         ),
         f"biagg_backward({d_in}->{d_out})",
     )
@@ -454,7 +458,8 @@ def adam_advance(step_dev: torch.Tensor, lr, beta1, beta2, eps, hyper: torch.Ten
 
 
 @_timed("adam_apply")
-def adam_apply(params, grads, exp_avgs, exp_avg_sqs, hyper: torch.Tensor):
+def adam_apply(params, grads, exp_avgs, exp_avg_sqs, hyper: torch.Tensor, peer_param0=None):
+    """``peer_param0``: int64 device tensor of pointers; the updated ``params[0]`` is mirrored behind each of them."""
     lib = _lib.load()
     n = len(params)
     for start in range(0, n, _lib.KGAT_MAX_TENSORS):
@@ -467,6 +472,8 @@ def adam_apply(params, grads, exp_avgs, exp_avg_sqs, hyper: torch.Tensor):
             t.exp_avg[j] = _ptr(exp_avgs[i], f32, "exp_avg")
             t.exp_avg_sq[j] = _ptr(exp_avg_sqs[i], f32, "exp_avg_sq")
             t.numel[j] = params[i].numel()
+        if start == 0 and peer_param0 is not None:
+            t.peer_param0, t.n_peers = _ptr(peer_param0, i64), peer_param0.numel()
         check(lib.kgat_adam_apply(C.byref(t), _ptr(hyper, f32), _stream()), "adam_apply")
 
 

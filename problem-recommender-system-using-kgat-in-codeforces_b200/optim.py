@@ -66,6 +66,27 @@ class FusedAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        self._step_impl()
+        return loss
+
+    def step_and_zero(self) -> None:
+        """``step()`` followed by ``zero_grad()`` (set to None) -- what the reference's ``update_*_weights`` do
+        (model.py:407-419) -- without torch.optim's per-call hook / profiler wrappers, which cost more host time than
+        the 80 us of GPU work of a KG step.  Falls back to the wrapped methods as soon as any hook is registered."""
+        from torch.optim import optimizer as _o
+
+        if (self._optimizer_step_pre_hooks or self._optimizer_step_post_hooks or _o._global_optimizer_pre_hooks
+                or _o._global_optimizer_post_hooks):
+            self.step()
+            self.zero_grad()
+            return
+        with torch.no_grad():
+            self._step_impl()
+        for group in self.param_groups:
+            for p in group["params"]:
+                p.grad = None
+
+    def _step_impl(self) -> None:
         for group in self.param_groups:
             with_grad = [p for p in group["params"] if p.grad is not None]
             if all(not p.grad.is_sparse and p.grad.is_contiguous() for p in with_grad) and self._graphed_step(group, with_grad):
@@ -99,4 +120,3 @@ class FusedAdam(torch.optim.Optimizer):
                 )
                 for p in ps:  # the kernel wrote through raw pointers: tell autograd the data changed
                     torch.autograd.graph.increment_version(p)
-        return loss

@@ -122,19 +122,19 @@ class KernelOps:
             self._partials = torch.empty(need, dtype=torch.float32, device=x_full.device)
         return self.ops.spmm(plan, lg["col_idx"], lg["vals"], x_full, out, addend, self._partials)
 
-    def biagg_forward(self, e, s, layer, out, p, seed, offset, seed_dev=None):
+    def biagg_forward(self, e, s, layer, out, p, seed, offset, seed_dev=None, peer_out=None):
         n, d_out = e.shape[0], layer[0].shape[0]
         inv = torch.empty(n, dtype=torch.float32, device=e.device)
         flags = torch.empty(n, d_out, dtype=torch.uint8, device=e.device)
-        self.ops.biagg_forward(e, s, *layer, out, inv, flags, dropout_p=p, seed=seed, offset=offset, seed_dev=seed_dev)
+        self.ops.biagg_forward(e, s, *layer, out, inv, flags, dropout_p=p, seed=seed, offset=offset, seed_dev=seed_dev, peer_out=peer_out)
         return inv, flags
 
-    def biagg_backward(self, g_out, out, inv, flags, e, s, layer, p, g_s, g_e):
+    def biagg_backward(self, g_out, out, inv, flags, e, s, layer, p, g_s, g_e, peer_out=None):
         w1, b1, w2, b2 = layer
         n, d_in, d_out = e.shape[0], e.shape[1], w1.shape[0]
         n_ctas = self.ops.biagg_backward_ctas(n, d_in, d_out)
         partials = torch.empty(n_ctas * (2 * d_in * d_out + 2 * d_out), dtype=torch.float32, device=e.device)
-        self.ops.biagg_backward(g_out, out, inv, flags, e, s, w1, w2, p, g_s, g_e, partials, n_ctas)
+        self.ops.biagg_backward(g_out, out, inv, flags, e, s, w1, w2, p, g_s, g_e, partials, n_ctas, peer_out=peer_out)
         grads = [torch.empty_like(t) for t in (w1, b1, w2, b2)]
         self.ops.biagg_reduce_param_grads(partials, n_ctas, d_in, d_out, *grads)
         return grads
@@ -154,6 +154,92 @@ def all_gather_rows(full: torch.Tensor, part: CyclicPartition):
     dist.all_gather_into_tensor(full, mine)
 
 
+class CollectiveExchange:
+    """Row exchange through ``torch.distributed`` collectives (NCCL all-gather on GPUs, gloo in the CPU tests).
+    Channels: ("t", l) = layer table l, ("g", l) = side gradient of layer l."""
+
+    fused = False
+
+    def __init__(self, part: CyclicPartition, dims, device):
+        pad = part.padded
+        self.part = part
+        self.tables = [torch.zeros(pad, d, dtype=torch.float32, device=device) for d in dims]
+        self.gs_full = [torch.zeros(pad, d, dtype=torch.float32, device=device) for d in dims[:-1]]
+
+    def _buf(self, kind, l):
+        return self.tables[l] if kind == "t" else self.gs_full[l]
+
+    def peer_out(self, kind, l):
+        return None
+
+    def gather(self, kind, l, pushed=False):
+        all_gather_rows(self._buf(kind, l), self.part)
+
+    def all_reduce_flat(self, flat):
+        dist.all_reduce(flat)
+        return flat
+
+    def barrier(self):
+        pass
+
+    def check(self):
+        pass
+
+    def close(self):
+        pass
+
+
+class PeerExchange:
+    """Row exchange over NVLink peer memory (peer.py / csrc/peer.cu): the tables live in an IPC arena mapped by
+    every rank; producers store their rows into every peer's table (from the bi-interaction kernels' own epilogue
+    when ``fused``, else with one push kernel) and a flag handshake replaces the collective.  The parameter-gradient
+    all-reduce is the same pattern: every rank deposits its partial in slot ``rank`` of every peer and all ranks
+    add the slots in rank order (bit-identical results on every rank)."""
+
+    def __init__(self, part: CyclicPartition, dims, device, n_flat: int, fused: bool = True):
+        from .peer import PeerArena
+
+        self.part, self.fused = part, fused
+        pad = part.padded
+        spec = {f"t{l}": (pad, d) for l, d in enumerate(dims)}
+        spec.update({f"g{l}": (pad, d) for l, d in enumerate(dims[:-1])})
+        self.n_flat = (n_flat + 3) // 4 * 4
+        spec["flat"] = (part.world, self.n_flat)
+        self._chan = {name: i for i, name in enumerate(spec)}
+        self._chan["barrier"] = len(spec)
+        self.arena = PeerArena(part.rank, part.world, device, spec, n_channels=len(spec) + 1)
+        self.tables = [self.arena.table(f"t{l}") for l in range(len(dims))]
+        self.gs_full = [self.arena.table(f"g{l}") for l in range(len(dims) - 1)]
+        self._row0 = part.rank * part.max_rows
+
+    def peer_out(self, kind, l):
+        """Device pointer array: this rank's slice of the table in every peer's arena (for fused epilogue stores)."""
+        return self.arena.peer_ptrs(f"{kind}{l}", self._row0) if self.fused and self.part.world > 1 else None
+
+    def gather(self, kind, l, pushed=False):
+        name = f"{kind}{l}"
+        if not pushed:
+            self.arena.push(name, self._row0, self.part.max_rows)
+        self.arena.signal_wait(self._chan[name])
+
+    def all_reduce_flat(self, flat):
+        slots = self.arena.table("flat")
+        slots[self.part.rank, : flat.numel()].copy_(flat)
+        self.arena.push("flat", self.part.rank, 1)
+        self.arena.signal_wait(self._chan["flat"])
+        torch.sum(slots[:, : flat.numel()], dim=0, out=flat)
+        return flat
+
+    def barrier(self):
+        self.arena.signal_wait(self._chan["barrier"])
+
+    def check(self):
+        self.arena.check()
+
+    def close(self):
+        self.arena.close()
+
+
 # ----------------------------------------------------------------------------------------------
 # sharded CF step
 # ----------------------------------------------------------------------------------------------
@@ -163,20 +249,23 @@ class ShardedPropagation:
     ``layers``: list of (W1, b1, W2, b2) replicated on every rank.  ``e0_full``: [padded, d0] table
     in padded layout whose own slice holds the current local embedding rows."""
 
-    def __init__(self, part: CyclicPartition, local_a, local_at, ops: "KernelOps", dims, device):
+    def __init__(self, part: CyclicPartition, local_a, local_at, ops: "KernelOps", dims, device, exchange=None):
         self.part, self.a, self.at, self.ops = part, local_a, local_at, ops
         self.dims = list(dims)  # [d0, d1, ..., dL]
         pad = part.padded
-        self.tables = [torch.zeros(pad, d, dtype=torch.float32, device=device) for d in self.dims]
+        self.ex = exchange if exchange is not None else CollectiveExchange(part, self.dims, device)
+        self.tables = self.ex.tables
+        self.gs_full = self.ex.gs_full
         self.g_tables = [torch.zeros(pad, d, dtype=torch.float32, device=device) for d in self.dims]
-        self.gs_full = [torch.zeros(pad, d, dtype=torch.float32, device=device) for d in self.dims[:-1]]
         self.device = device
         self.saved = None
 
     def forward(self, layers, ps, seed, u, p, n, reg, loss, scratch, seed_dev=None):
         part = self.part
         sl = part.slice()
-        all_gather_rows(self.tables[0], part)
+        # the embedding rows: mirrored into the peers' tables by the Adam kernel of the previous step when the exchange
+        # is fused (the tables start out complete: scatter_from_model), so only the handshake is left
+        self.ex.gather("t", 0, pushed=self.ex.fused)
         saved = []
         for l, layer in enumerate(layers):
             x_full = self.tables[l]
@@ -185,8 +274,10 @@ class ShardedPropagation:
             self.ops.spmm(self.a, x_full, s_loc)
             out_loc = self.tables[l + 1][sl]
             # each rank draws its rows' dropout decisions from its own Philox stream (seed + rank)
-            inv, flags = self.ops.biagg_forward(x_loc, s_loc, layer, out_loc, ps[l], seed + 7919 * part.rank, (l + 1) << 40, seed_dev)
-            all_gather_rows(self.tables[l + 1], part)
+            peer_out = self.ex.peer_out("t", l + 1)
+            inv, flags = self.ops.biagg_forward(x_loc, s_loc, layer, out_loc, ps[l], seed + 7919 * part.rank, (l + 1) << 40, seed_dev,
+                                                **({"peer_out": peer_out} if peer_out is not None else {}))
+            self.ex.gather("t", l + 1, pushed=peer_out is not None)
             saved.append((s_loc, inv, flags))
         self.ops.bpr_forward(self.tables, u, p, n, reg, loss, scratch)
         self.saved = (saved, (u, p, n), reg, scratch, ps)
@@ -213,14 +304,14 @@ class ShardedPropagation:
             x_loc = self.tables[l - 1][sl]
             g_s_loc = self.gs_full[l - 1][sl]
             g_e_loc = torch.empty(part.count(), self.dims[l - 1], dtype=torch.float32, device=self.device)
+            peer_out = self.ex.peer_out("g", l - 1)
             pgrads[l - 1] = self.ops.biagg_backward(self.g_tables[l][sl], self.tables[l][sl], inv, flags, x_loc, s_loc, layers[l - 1], ps[l - 1],
-                                                    g_s_loc, g_e_loc)
-            all_gather_rows(self.gs_full[l - 1], part)
+                                                    g_s_loc, g_e_loc, **({"peer_out": peer_out} if peer_out is not None else {}))
+            self.ex.gather("g", l - 1, pushed=peer_out is not None)
             self.ops.spmm(self.at, self.gs_full[l - 1], self.g_tables[l - 1][sl], addend=g_e_loc)
             inject(l - 1)
         if part.world > 1:
-            flat = torch.cat([t.reshape(-1) for grp in pgrads for t in grp])
-            dist.all_reduce(flat)
+            flat = self.ex.all_reduce_flat(torch.cat([t.reshape(-1) for grp in pgrads for t in grp]))
             off = 0
             for grp in pgrads:
                 for t in grp:
@@ -235,12 +326,22 @@ class ShardedPropagation:
 class ShardedEngine:
     """Epoch driver for P ranks: sharded CF phase, replicated KG phase and refresh."""
 
-    def __init__(self, model, part: CyclicPartition, use_graphs: bool = True):
+    def __init__(self, model, part: CyclicPartition, use_graphs: bool = True, exchange: str | None = None):
+        """``exchange``: "peer" (default; rows stored into the peers' tables from the producing kernels' epilogues),
+        "peer-push" (same protocol, separate push kernel) or "nccl" (all-gather / all-reduce collectives, the
+        baseline the peer path is measured against).  Environment override: KGAT_EXCHANGE."""
+        import os
+
         from . import ops
         from .engine import TrainEngine
 
         self.model, self.part, self.kops, self.ops = model, part, KernelOps(), ops
         self.use_graphs = use_graphs
+        self.exchange_kind = exchange or os.environ.get("KGAT_EXCHANGE", "peer")
+        if self.exchange_kind not in ("peer", "peer-push", "nccl"):
+            raise ValueError(f"unknown exchange {self.exchange_kind!r}")
+        self.exchange = None
+        self._cf_kernels = 0
         self._cf_graph = None
         self._cf_graph_key = None
         self._cf_padded = None
@@ -250,6 +351,9 @@ class ShardedEngine:
         self.single = TrainEngine(model, use_graphs=True)  # KG phase (replicated) reuses the 1-GPU engine
         self.layers = [tuple(t.detach() for t in grp) for grp in model._layers()]
         dims = [model._cf_embedding_dim, *model._layer_dims]
+        if part.world > 1 and self.exchange_kind != "nccl":
+            n_flat = sum(t.numel() for grp in self.layers for t in grp)
+            self.exchange = PeerExchange(part, dims, self.dev, n_flat, fused=self.exchange_kind == "peer")
         self._build_graph(dims)
         n_loc = part.count()
         d0 = dims[0]
@@ -272,7 +376,7 @@ class ShardedEngine:
         tp, ti = g.t_ptr.cpu().numpy(), g.t_idx.cpu().numpy()
         self.a = self.kops.make_local_graph(*shard_csr(rp, ci, self.part), self.dev)
         self.at = self.kops.make_local_graph(*shard_csr(tp, ti, self.part), self.dev)
-        self.prop = ShardedPropagation(self.part, self.a, self.at, self.kops, dims, self.dev)
+        self.prop = ShardedPropagation(self.part, self.a, self.at, self.kops, dims, self.dev, exchange=self.exchange)
         self.refresh_values()
 
     def refresh_values(self):
@@ -283,9 +387,10 @@ class ShardedEngine:
     def scatter_from_model(self):
         w = self.model._user_entity_embedding.weight.detach()
         self.prop.tables[0].copy_(self.part.scatter_rows(w))
+        self.prop.ex.barrier()  # nobody stores rows into a table its owner is still overwriting
 
     def gather_to_model(self):
-        all_gather_rows(self.prop.tables[0], self.part)
+        self.prop.ex.gather("t", 0)
         self.model._user_entity_embedding.weight.data.copy_(self.part.gather_rows(self.prop.tables[0]))
         torch.autograd.graph.increment_version(self.model._user_entity_embedding.weight)
 
@@ -303,7 +408,8 @@ class ShardedEngine:
         grads = [g_e0.contiguous()] + [t for grp in pgrads for t in grp]
         ms = [self.e0_m] + [t for grp in self.layer_m for t in grp]
         vs = [self.e0_v] + [t for grp in self.layer_v for t in grp]
-        self.ops.adam_apply(params, grads, ms, vs, self.hyper)
+        peer_e0 = self.prop.ex.peer_out("t", 0)
+        self.ops.adam_apply(params, grads, ms, vs, self.hyper, **({"peer_param0": peer_e0} if peer_e0 is not None else {}))
         self.loss_sum.add_(self.loss)
 
     def _cf_graphed_step(self):
@@ -331,13 +437,26 @@ class ShardedEngine:
                 + [t for grp in self.layer_m for t in grp] + [t for grp in self.layer_v for t in grp]
             for dst, src in zip(live, snap):
                 dst.copy_(src)
+            self.prop.ex.gather("t", 0)  # the peers' mirrors of my embedding rows go back to the restored values too
             if self.part.world > 1:
                 dist.barrier()
+            from . import _lib
+
             g = torch.cuda.CUDAGraph()
+            before = _lib.LaunchCounter.count
             with torch.cuda.graph(g):
                 self._cf_graphed_step()
+            self._cf_kernels = _lib.LaunchCounter.count - before
+            _lib.LaunchCounter.count = before
             self._cf_graph, self._cf_graph_key = g, key
-        return self._cf_graph.replay
+
+        def replay(g=self._cf_graph, kernels=self._cf_kernels):
+            from . import _lib
+
+            _lib.LaunchCounter.count += kernels
+            g.replay()
+
+        return replay
 
     def run_epoch(self, data, n_cf=None, n_kg=None, refresh=True):
         """``data``: EpochData on the device (cf [n,3,B], kg [n,4,B] stacked, as TrainEngine.bind_resident)."""
@@ -359,6 +478,8 @@ class ShardedEngine:
         for i in range(n_cf):
             step()
         cf_loss = float(self.loss_sum.item()) / max(n_cf, 1)
+        if self.exchange is not None:
+            self.exchange.check()
         self.gather_to_model()
         for grp in m._layers():  # aggregator weights were updated in place (they are the model's tensors)
             for t in grp:
@@ -446,5 +567,7 @@ def bench_main(args, metric, unit, workload, make_workload, config_dict, ClockSa
     eng.single._graphs.clear()
     torch.cuda.synchronize()
     dist.barrier()
+    if eng.exchange is not None:
+        eng.exchange.close()
     sys.stderr.flush()
     os._exit(0)
