@@ -163,11 +163,18 @@ int kgat_transr_forward(const float* emb, const float* rel_emb, const float* W, 
                         const int64_t* heads, const int64_t* rels, const int64_t* pos_tails, const int64_t* neg_tails,
                         int32_t batch, float reg, float* loss, float* margin, void* stream);
 /* Accumulates (atomicAdd) into g_emb (n_nodes x d), g_rel_emb (n_rel x k), g_W (n_rel x d x k);
- * the caller zeroes them. */
+ * the caller zeroes them.  With row_slot != NULL, g_emb is instead a compact 3*batch x d buffer and node i
+ * accumulates into row row_slot[i] (kgat_transr_claim_rows). */
 int kgat_transr_backward(const float* emb, const float* rel_emb, const float* W, int32_t d, int32_t k,
                          const int64_t* heads, const int64_t* rels, const int64_t* pos_tails,
                          const int64_t* neg_tails, int32_t batch, float reg, const float* margin, const float* g_loss,
-                         float* g_emb, float* g_rel_emb, float* g_W, void* stream);
+                         float* g_emb, float* g_rel_emb, float* g_W,
+                         const int32_t* row_slot, void* stream);
+/* One slot per distinct node of a TransR batch: row_slot (n_nodes int32, -1 = free) gets, for every node among
+ * heads / pos_tails / neg_tails, the index in [0, 3*batch) of its first claimant; g_rows (3*batch x d) is zeroed.
+ * kgat_adam_apply (row_slot0) consumes the rows and frees the slots. */
+int kgat_transr_claim_rows(const int64_t* heads, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, int32_t d,
+                           int32_t* row_slot, float* g_rows, void* stream);
 
 /* ------------------------------------------------------------------------------------------- */
 /* K6-K8: attention refresh                  reference model.py:263-366,                         */
@@ -237,6 +244,11 @@ typedef struct {
      * offset behind each of the n_peers device pointers of the DEVICE array peer_param0; (NULL, 0) otherwise */
     float* const* peer_param0;
     int32_t n_peers;
+    /* row-sparse gradient for tensor 0 (the embedding table in the KG phase): when row_slot0 != NULL, grad[0] holds
+     * compact rows [n_slots x row_dim0] and row r of tensor 0 uses row row_slot0[r] of it (g = 0 where the slot is
+     * -1); the kernel resets the used slots to -1.  See kgat_transr_claim_rows. */
+    int32_t* row_slot0;
+    int32_t row_dim0;
 } kgat_adam_tensors_t;
 /* One torch.optim.Adam step (no weight decay, no amsgrad) over all listed tensors in one launch,
  * split in two so a captured CUDA graph replays correctly: kgat_adam_advance increments the device

@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(128) transr_bwd_kernel(const float* __restrict
                                                          const int64_t* __restrict__ nt, int batch, float reg,
                                                          const float* __restrict__ scratch, const float* __restrict__ g_loss,
                                                          float* __restrict__ g_emb, float* __restrict__ g_rel,
-                                                         float* __restrict__ g_W) {
+                                                         float* __restrict__ g_W, const int32_t* __restrict__ row_slot) {
     constexpr int D = DM * 32, K = KM * 32;
     constexpr int JW = D / kTrWarps;
     __shared__ float part[kTrWarps][3][K];
@@ -284,9 +284,24 @@ __global__ void __launch_bounds__(128) transr_bwd_kernel(const float* __restrict
         }
     }
     if (lane < JW) {
-        atomicAdd(g_emb + h * D + j0 + lane, geh);
-        atomicAdd(g_emb + p * D + j0 + lane, gep);
-        atomicAdd(g_emb + n * D + j0 + lane, gen);
+        // dense gradient table indexed by node, or compact rows indexed through row_slot (kgat_transr_claim_rows)
+        const int64_t gh = row_slot ? row_slot[h] : h, gp = row_slot ? row_slot[p] : p, gn = row_slot ? row_slot[n] : n;
+        atomicAdd(g_emb + gh * D + j0 + lane, geh);
+        atomicAdd(g_emb + gp * D + j0 + lane, gep);
+        atomicAdd(g_emb + gn * D + j0 + lane, gen);
+    }
+}
+
+// Compact gradient rows for the embedding table: the 3B ids of a batch claim a slot per DISTINCT node
+// (row_slot[node] = index of the first claimant, -1 = untouched; the Adam kernel resets the claims), and the
+// 3B x d gradient rows are zeroed -- instead of zeroing and re-reading an n_nodes x d gradient table per step.
+__global__ void transr_claim_rows_kernel(const int64_t* __restrict__ heads, const int64_t* __restrict__ pt, const int64_t* __restrict__ nt,
+                                         int batch, int d, int32_t* __restrict__ row_slot, float4* __restrict__ g_rows) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3 * batch * (d / 4)) g_rows[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < 3 * batch) {
+        const int64_t id = i < batch ? heads[i] : (i < 2 * batch ? pt[i - batch] : nt[i - 2 * batch]);
+        atomicCAS(row_slot + id, -1, i);
     }
 }
 
@@ -346,12 +361,23 @@ int kgat_transr_forward(const float* emb, const float* rel_emb, const float* W, 
 
 int kgat_transr_backward(const float* emb, const float* rel_emb, const float* W, int32_t d, int32_t k, const int64_t* heads,
                          const int64_t* rels, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, float reg,
-                         const float* margin, const float* g_loss, float* g_emb, float* g_rel_emb, float* g_W, void* stream_) {
+                         const float* margin, const float* g_loss, float* g_emb, float* g_rel_emb, float* g_W, const int32_t* row_slot,
+                         void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (batch <= 0) return KGAT_ERR_INVALID_ARGUMENT;
     const unsigned blocks = (unsigned)batch;  // one 4-warp CTA per sample
     KGAT_TRANSR_DISPATCH((transr_bwd_kernel<DM, KM><<<blocks, 128, 0, stream>>>(emb, rel_emb, W, heads, rels, pos_tails, neg_tails,
-                                                                               batch, reg, margin, g_loss, g_emb, g_rel_emb, g_W)));
+                                                                               batch, reg, margin, g_loss, g_emb, g_rel_emb, g_W,
+                                                                               row_slot)));
+    return check_launch();
+}
+
+int kgat_transr_claim_rows(const int64_t* heads, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, int32_t d,
+                           int32_t* row_slot, float* g_rows, void* stream_) {
+    if (batch <= 0 || d <= 0 || (d & 3) || !row_slot || !g_rows) return KGAT_ERR_INVALID_ARGUMENT;
+    const int n = 3 * batch * (d / 4);
+    transr_claim_rows_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(heads, pos_tails, neg_tails, batch, d, row_slot,
+                                                                              reinterpret_cast<float4*>(g_rows));
     return check_launch();
 }
 

@@ -47,9 +47,9 @@ class _AdamSlot:
         self.exp_avg = [opt.state[p]["exp_avg"] for p in self.params]
         self.exp_avg_sq = [opt.state[p]["exp_avg_sq"] for p in self.params]
 
-    def apply(self, grads):
+    def apply(self, grads, row_slot0=None):
         ops.adam_advance(self.step_dev, self.lr, self.b1, self.b2, self.eps, self.hyper)
-        ops.adam_apply([p.data for p in self.params], grads, self.exp_avg, self.exp_avg_sq, self.hyper)
+        ops.adam_apply([p.data for p in self.params], grads, self.exp_avg, self.exp_avg_sq, self.hyper, row_slot0=row_slot0)
 
     def sync_host(self, n_steps: int):
         for p in self.params:
@@ -90,6 +90,10 @@ class TrainEngine:
         self.cf_scratch = torch.empty(2 * cf_batch, dtype=f32, device=dev)
         self.kg_scratch = torch.empty(2 * kg_batch, dtype=f32, device=dev)
         self.kg_grads = [torch.zeros_like(p) for p in self.kg_params]
+        # KG phase: the embedding-table gradient of a TransR batch lives in <= 3B compact rows (one slot per distinct
+        # node, csrc/losses.cu: transr_claim_rows) instead of a zero-filled N x d table that Adam would re-read
+        self.kg_row_slot = torch.full((emb.shape[0],), -1, dtype=torch.int32, device=dev)
+        self.kg_grad_rows = torch.zeros(3 * kg_batch, emb.shape[1], dtype=f32, device=dev)
         # Opt-in: lazy exact Adam for the embedding table in the KG phase (see csrc/adam.cu).  Bit-identical to the
         # dense sweep but MEASURED SLOWER at the C3 shape (12.5 s vs 4.4 s per epoch): every row-step must still
         # be replayed once, and the replay (IEEE sqrt + division per element-step, serial per row) is
@@ -160,10 +164,12 @@ class TrainEngine:
                 ops.adam_sparse_rows(emb, self.kg_grads[0], ad.exp_avg[0], ad.exp_avg_sq[0], self.kg_row_step, ids, ad.step_dev, self.kg_s0, ad.hyper)
         else:
             ops.transr_forward(emb, rel, w, h, r, pt, nt, reg, self.kg_loss, self.kg_scratch)
-            for g in self.kg_grads:
+            ops.transr_claim_rows(h, pt, nt, emb.shape[1], self.kg_row_slot, self.kg_grad_rows)
+            for g in self.kg_grads[1:]:
                 ops.fill_(g, 0.0)
-            ops.transr_backward(emb, rel, w, h, r, pt, nt, reg, self.kg_scratch, self.one, *self.kg_grads)
-            ad.apply(self.kg_grads)
+            ops.transr_backward(emb, rel, w, h, r, pt, nt, reg, self.kg_scratch, self.one, self.kg_grad_rows, *self.kg_grads[1:],
+                                row_slot=self.kg_row_slot)
+            ad.apply([self.kg_grad_rows] + self.kg_grads[1:], row_slot0=self.kg_row_slot)
         self.kg_loss_sum.add_(self.kg_loss)
 
     def _kg_phase_begin(self, n_kg: int):

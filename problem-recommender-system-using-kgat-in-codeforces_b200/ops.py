@@ -316,12 +316,23 @@ def transr_forward(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, loss, scratc
 
 
 @_timed("transr_bwd")
-def transr_backward(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, scratch, g_loss, g_emb, g_rel, g_W):
+def transr_claim_rows(heads, pos_t, neg_t, d: int, row_slot, g_rows):
+    """Compact gradient rows for a TransR batch: one slot per distinct node in ``row_slot`` (int32 [n_nodes], -1 = free),
+    ``g_rows`` (3B x d) zeroed."""
+    lib = _lib.load()
+    if g_rows.numel() < 3 * heads.numel() * d:
+        raise KgatLibraryError("transr_claim_rows: g_rows needs 3 * batch * d floats")
+    check(lib.kgat_transr_claim_rows(_ptr(heads, i64), _ptr(pos_t, i64), _ptr(neg_t, i64), heads.numel(), int(d), _ptr(row_slot, i32),
+                                     _ptr(g_rows, f32), _stream()), "transr_claim_rows")
+
+
+def transr_backward(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, scratch, g_loss, g_emb, g_rel, g_W, row_slot=None):
     lib = _lib.load()
     check(
         lib.kgat_transr_backward(_ptr(emb, f32), _ptr(rel_emb, f32), _ptr(W, f32), emb.shape[1], rel_emb.shape[1], _ptr(heads, i64),
                                  _ptr(rels, i64), _ptr(pos_t, i64), _ptr(neg_t, i64), heads.numel(), float(reg), _ptr(scratch, f32),
-                                 _ptr(g_loss, f32), _ptr(g_emb, f32), _ptr(g_rel, f32), _ptr(g_W, f32), _stream()),
+                                 _ptr(g_loss, f32), _ptr(g_emb, f32), _ptr(g_rel, f32), _ptr(g_W, f32),
+                                 _ptr(row_slot, i32) if row_slot is not None else None, _stream()),
         "transr_backward",
     )
 
@@ -458,8 +469,9 @@ def adam_advance(step_dev: torch.Tensor, lr, beta1, beta2, eps, hyper: torch.Ten
 
 
 @_timed("adam_apply")
-def adam_apply(params, grads, exp_avgs, exp_avg_sqs, hyper: torch.Tensor, peer_param0=None):
-    """``peer_param0``: int64 device tensor of pointers; the updated ``params[0]`` is mirrored behind each of them."""
+def adam_apply(params, grads, exp_avgs, exp_avg_sqs, hyper: torch.Tensor, peer_param0=None, row_slot0=None):
+    """``peer_param0``: int64 device tensor of pointers; the updated ``params[0]`` is mirrored behind each of them.
+    ``row_slot0``: int32 [rows of params[0]]; ``grads[0]`` then holds compact rows (ops.transr_claim_rows)."""
     lib = _lib.load()
     n = len(params)
     for start in range(0, n, _lib.KGAT_MAX_TENSORS):
@@ -469,11 +481,17 @@ def adam_apply(params, grads, exp_avgs, exp_avg_sqs, hyper: torch.Tensor, peer_p
         for j, i in enumerate(chunk):
             t.param[j] = _ptr(params[i], f32, "param")
             t.grad[j] = _ptr(grads[i], f32, "grad")
+            if grads[i].numel() != params[i].numel() and not (i == 0 and row_slot0 is not None):
+                raise KgatLibraryError("adam_apply: gradient / parameter size mismatch")
             t.exp_avg[j] = _ptr(exp_avgs[i], f32, "exp_avg")
             t.exp_avg_sq[j] = _ptr(exp_avg_sqs[i], f32, "exp_avg_sq")
             t.numel[j] = params[i].numel()
         if start == 0 and peer_param0 is not None:
             t.peer_param0, t.n_peers = _ptr(peer_param0, i64), peer_param0.numel()
+        if start == 0 and row_slot0 is not None:
+            if row_slot0.numel() * params[0].shape[-1] != params[0].numel():
+                raise KgatLibraryError("adam_apply: row_slot0 needs one entry per row of params[0]")
+            t.row_slot0, t.row_dim0 = _ptr(row_slot0, i32), params[0].shape[-1]
         check(lib.kgat_adam_apply(C.byref(t), _ptr(hyper, f32), _stream()), "adam_apply")
 
 
