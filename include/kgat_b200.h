@@ -309,8 +309,12 @@ int kgat_peer_export(const void* ptr, void* handle64);
 int kgat_peer_import(const void* handle64, void** ptr);
 int kgat_peer_close(void* ptr);
 /* Copy n_floats (multiple of 4, 16-byte aligned) from src to peer_dst[q] for q < n_peers.  peer_dst is a DEVICE
- * array of n_peers device pointers into the peers' mapped allocations. */
-int kgat_peer_push(const float* src, float* const* peer_dst, int32_t n_peers, int64_t n_floats, void* stream);
+ * array of n_peers device pointers into the peers' mapped allocations.  max_ctas > 0 bounds the grid (a push that
+ * runs beside compute kernels on another stream needs few SMs to fill the links); 0 = 8 CTAs per SM. */
+int kgat_peer_push(const float* src, float* const* peer_dst, int32_t n_peers, int64_t n_floats, int32_t max_ctas, void* stream);
+/* The same transfer on a copy engine (cudaMemcpyAsync into a peer mapping): no SM is involved, so it can run on a
+ * side stream beside compute kernels without slowing them down.  One destination per call. */
+int kgat_peer_copy(void* dst, const void* src, int64_t bytes, void* stream);
 /* Channel handshake: seq[0] += 1; store it to *peer_flags[q] (my slot in peer q's flag pad) and wait until
  * my_flags[q] (written by peer q) has reached it, for every q < n_peers.  After it returns, everything the peers
  * stored into this rank's memory before *their* matching call is visible.  A wait longer than timeout_cycles SM

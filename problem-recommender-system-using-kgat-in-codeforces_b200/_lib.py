@@ -113,7 +113,8 @@ SIGNATURES: dict[str, tuple] = {
     "kgat_peer_export": (_I32, [_P, _P]),
     "kgat_peer_import": (_I32, [_P, _P]),
     "kgat_peer_close": (_I32, [_P]),
-    "kgat_peer_push": (_I32, [_P, _P, _I32, _I64, _P]),
+    "kgat_peer_push": (_I32, [_P, _P, _I32, _I64, _I32, _P]),
+    "kgat_peer_copy": (_I32, [_P, _P, _I64, _P]),
     "kgat_peer_signal_wait": (_I32, [_P, _P, _I32, _P, _P, _I64, _P]),
 }
 

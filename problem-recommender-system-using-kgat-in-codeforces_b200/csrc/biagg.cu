@@ -435,7 +435,7 @@ int biagg_mma_backward(const float* g_out, int64_t ld_gout, const float* out, in
                        const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* W2, float p, float* g_S,
                        float* g_E, float* partials, int n_ctas, float* const* peer_gS, int n_peers, cudaStream_t stream);
 // peer.cu: copy n_floats to the same offset behind every peer pointer
-int peer_push_launch(const float* src, float* const* peer_dst, int n_peers, int64_t n_floats, cudaStream_t stream);
+int peer_push_launch(const float* src, float* const* peer_dst, int n_peers, int64_t n_floats, cudaStream_t stream, int max_ctas = 0);
 
 // KGAT_BIAGG_IMPL=ffma selects the CUDA-core kernels of this file (A/B comparison); default: tensor cores
 static bool use_mma() {

@@ -67,12 +67,13 @@ __global__ void peer_signal_wait_kernel(int32_t* const* __restrict__ peer_flags 
 
 }  // namespace
 
-int peer_push_launch(const float* src, float* const* peer_dst, int n_peers, int64_t n_floats, cudaStream_t stream) {
+int peer_push_launch(const float* src, float* const* peer_dst, int n_peers, int64_t n_floats, cudaStream_t stream, int max_ctas) {
     if (n_peers < 0 || n_floats < 0 || (n_floats & 3) || (reinterpret_cast<uintptr_t>(src) & 15)) return KGAT_ERR_INVALID_ARGUMENT;
     if (n_peers == 0 || n_floats == 0) return KGAT_OK;
     const int64_t n_vec = n_floats / 4;
     const int64_t want = (n_vec + 255) / 256;
-    const int grid = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
+    const int64_t cap = max_ctas > 0 ? max_ctas : (int64_t)sm_count() * 8;
+    const int grid = (int)(want < cap ? want : cap);
     peer_push_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4* const*>(peer_dst), n_peers,
                                                n_vec);
     return check_launch();
@@ -116,8 +117,15 @@ int kgat_peer_close(void* ptr) {
     return KGAT_OK;
 }
 
-int kgat_peer_push(const float* src, float* const* peer_dst, int32_t n_peers, int64_t n_floats, void* stream) {
-    return peer_push_launch(src, peer_dst, n_peers, n_floats, (cudaStream_t)stream);
+int kgat_peer_push(const float* src, float* const* peer_dst, int32_t n_peers, int64_t n_floats, int32_t max_ctas, void* stream) {
+    return peer_push_launch(src, peer_dst, n_peers, n_floats, (cudaStream_t)stream, max_ctas);
+}
+
+int kgat_peer_copy(void* dst, const void* src, int64_t bytes, void* stream) {
+    if (bytes < 0 || (bytes && (!dst || !src))) return KGAT_ERR_INVALID_ARGUMENT;
+    if (bytes == 0) return KGAT_OK;
+    KGAT_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return KGAT_OK;
 }
 
 int kgat_peer_signal_wait(int32_t* const* peer_flags, const int32_t* my_flags, int32_t n_peers, int32_t* seq, int32_t* status,

@@ -84,14 +84,22 @@ class PeerArena:
             self._ptr_cache[key] = torch.tensor(ptrs or [0], dtype=torch.int64, device=self.device)
         return self._ptr_cache[key]
 
-    def push(self, name: str, row_offset: int, n_rows: int) -> None:
+    def push(self, name: str, row_offset: int, n_rows: int, max_ctas: int = 0) -> None:
         """Copy rows [row_offset, row_offset + n_rows) of my table to the same rows of every peer's table."""
         if not self.peers:
             return
         t = self._views[name]
         src = t[row_offset : row_offset + n_rows]
         check(self.lib.kgat_peer_push(src.data_ptr(), self.peer_ptrs(name, row_offset).data_ptr(), len(self.peers), src.numel(),
-                                      torch.cuda.current_stream().cuda_stream), "peer_push")
+                                      int(max_ctas), torch.cuda.current_stream().cuda_stream), "peer_push")
+
+    def copy(self, name: str, row_offset: int, n_rows: int) -> None:
+        """Same transfer as ``push`` on the copy engines (one cudaMemcpyAsync per peer): no SM involved."""
+        d = self._shape[name][1]
+        off = 4 * (self._off[name] + row_offset * d)
+        stream = torch.cuda.current_stream().cuda_stream
+        for q in self.peers:
+            check(self.lib.kgat_peer_copy(self.peer_base[q] + off, self.base + off, 4 * n_rows * d, stream), "peer_copy")
 
     def signal_wait(self, channel: int) -> None:
         """All peers' stores of this channel have landed here once this (stream-ordered) call has run."""

@@ -81,10 +81,12 @@ class CyclicPartition:
         return padded_table[self.to_padded(idx)]
 
 
-def shard_csr(row_ptr: np.ndarray, col_idx: np.ndarray, part: CyclicPartition):
-    """Local CSR of the rows owned by ``part.rank``: (row_ptr_local, col_idx in padded layout,
-    slot_ids = positions of the local non-zeros in the global value array)."""
+def shard_csr(row_ptr: np.ndarray, col_idx: np.ndarray, part: CyclicPartition, local_range: tuple[int, int] | None = None):
+    """Local CSR of the rows owned by ``part.rank`` (or of the sub-range ``local_range`` of them): (row_ptr_local,
+    col_idx in padded layout, slot_ids = positions of the local non-zeros in the global value array)."""
     rows = part.local_rows()
+    if local_range is not None:
+        rows = rows[local_range[0] : local_range[1]]
     lens = (row_ptr[rows + 1] - row_ptr[rows]).astype(np.int64)
     lp = np.concatenate([[0], np.cumsum(lens)])
     starts = np.repeat(row_ptr[rows].astype(np.int64), lens)
@@ -129,14 +131,14 @@ class KernelOps:
         self.ops.biagg_forward(e, s, *layer, out, inv, flags, dropout_p=p, seed=seed, offset=offset, seed_dev=seed_dev, peer_out=peer_out)
         return inv, flags
 
-    def biagg_backward(self, g_out, out, inv, flags, e, s, layer, p, g_s, g_e, peer_out=None):
+    def biagg_backward(self, g_out, out, inv, flags, e, s, layer, p, g_s, g_e, peer_out=None, accumulate_into=None):
         w1, b1, w2, b2 = layer
         n, d_in, d_out = e.shape[0], e.shape[1], w1.shape[0]
         n_ctas = self.ops.biagg_backward_ctas(n, d_in, d_out)
         partials = torch.empty(n_ctas * (2 * d_in * d_out + 2 * d_out), dtype=torch.float32, device=e.device)
         self.ops.biagg_backward(g_out, out, inv, flags, e, s, w1, w2, p, g_s, g_e, partials, n_ctas, peer_out=peer_out)
-        grads = [torch.empty_like(t) for t in (w1, b1, w2, b2)]
-        self.ops.biagg_reduce_param_grads(partials, n_ctas, d_in, d_out, *grads)
+        grads = accumulate_into if accumulate_into is not None else [torch.empty_like(t) for t in (w1, b1, w2, b2)]
+        self.ops.biagg_reduce_param_grads(partials, n_ctas, d_in, d_out, *grads, accumulate=accumulate_into is not None)
         return grads
 
     def bpr_forward(self, tables, u, p, n, reg, loss, scratch):
@@ -169,7 +171,9 @@ class CollectiveExchange:
     def _buf(self, kind, l):
         return self.tables[l] if kind == "t" else self.gs_full[l]
 
-    def peer_out(self, kind, l):
+    can_push = False
+
+    def peer_out(self, kind, l, row0=0):
         return None
 
     def gather(self, kind, l, pushed=False):
@@ -196,10 +200,16 @@ class PeerExchange:
     all-reduce is the same pattern: every rank deposits its partial in slot ``rank`` of every peer and all ranks
     add the slots in rank order (bit-identical results on every rank)."""
 
-    def __init__(self, part: CyclicPartition, dims, device, n_flat: int, fused: bool = True):
+    def __init__(self, part: CyclicPartition, dims, device, n_flat: int, fused=("t",)):
+        """``fused``: which producers store into the peers' tables from their own epilogue -- "t" the bi-interaction
+        forward (layer tables), "g" its backward (side gradients), "e" Adam (embedding rows).  Measured at the C3
+        shape: the forward kernel is tensor-pipe bound and hides the NVLink stores (2 GPUs: 126 us fused vs 103 + 47
+        us kernel + push); the backward's 8-byte fragment stores and the HBM-bound Adam sweep do not (4 GPUs: 319 vs
+        127 + 100 us, 69 vs 20 + 40 us), so by default those rows go out with the push kernel."""
         from .peer import PeerArena
 
-        self.part, self.fused = part, fused
+        self.part, self.fused_kinds = part, tuple(fused)
+        self.fused = "e" in self.fused_kinds
         pad = part.padded
         spec = {f"t{l}": (pad, d) for l, d in enumerate(dims)}
         spec.update({f"g{l}": (pad, d) for l, d in enumerate(dims[:-1])})
@@ -212,9 +222,21 @@ class PeerExchange:
         self.gs_full = [self.arena.table(f"g{l}") for l in range(len(dims) - 1)]
         self._row0 = part.rank * part.max_rows
 
-    def peer_out(self, kind, l):
-        """Device pointer array: this rank's slice of the table in every peer's arena (for fused epilogue stores)."""
-        return self.arena.peer_ptrs(f"{kind}{l}", self._row0) if self.fused and self.part.world > 1 else None
+    can_push = True
+
+    def peer_out(self, kind, l, row0=0):
+        """Device pointer array: row ``row0`` of this rank's slice of the table in every peer's arena (for fused
+        epilogue stores); None when this producer is not fused."""
+        k = "e" if (kind, l) == ("t", 0) else kind
+        return self.arena.peer_ptrs(f"{kind}{l}", self._row0 + row0) if k in self.fused_kinds and self.part.world > 1 else None
+
+    def push_rows(self, kind, l, row0, n_rows, max_ctas=0):
+        """Rows [row0, row0 + n_rows) of this rank's slice -> every peer's table, on the current stream: push kernel, or
+        (max_ctas < 0) the copy engines."""
+        if max_ctas < 0:
+            self.arena.copy(f"{kind}{l}", self._row0 + row0, n_rows)
+        else:
+            self.arena.push(f"{kind}{l}", self._row0 + row0, n_rows, max_ctas)
 
     def gather(self, kind, l, pushed=False):
         name = f"{kind}{l}"
@@ -249,8 +271,14 @@ class ShardedPropagation:
     ``layers``: list of (W1, b1, W2, b2) replicated on every rank.  ``e0_full``: [padded, d0] table
     in padded layout whose own slice holds the current local embedding rows."""
 
-    def __init__(self, part: CyclicPartition, local_a, local_at, ops: "KernelOps", dims, device, exchange=None):
-        self.part, self.a, self.at, self.ops = part, local_a, local_at, ops
+    def __init__(self, part: CyclicPartition, local_a, local_at, ops: "KernelOps", dims, device, exchange=None, chunk_bounds=None):
+        """``local_a``: the local rows of A as one graph, or a list of graphs over consecutive sub-ranges
+        ``chunk_bounds`` = [(start, stop), ...] of the local rows.  With several chunks (and a peer exchange) the rows a
+        chunk has produced travel to the peers on a side stream while the next chunk is being computed."""
+        self.part, self.at, self.ops = part, local_at, ops
+        self.a = list(local_a) if isinstance(local_a, (list, tuple)) else [local_a]
+        self.bounds = list(chunk_bounds) if chunk_bounds is not None else [(0, part.count())]
+        assert len(self.a) == len(self.bounds)
         self.dims = list(dims)  # [d0, d1, ..., dL]
         pad = part.padded
         self.ex = exchange if exchange is not None else CollectiveExchange(part, self.dims, device)
@@ -259,26 +287,60 @@ class ShardedPropagation:
         self.g_tables = [torch.zeros(pad, d, dtype=torch.float32, device=device) for d in self.dims]
         self.device = device
         self.saved = None
+        self.side = None
+        if self.ex.can_push and len(self.bounds) > 1:
+            self.side = torch.cuda.Stream(device=device, priority=-1)
+        self._side_busy = False
+        import os
+
+        # side-stream transfers: -1 = copy engines (no SM taken from the compute kernels), > 0 = push kernel with that many CTAs
+        self.push_ctas = int(os.environ.get("KGAT_PUSH_CTAS", "-1"))
+
+    # rows [r0, r1) of this rank's slice of table (kind, l) have just been produced on the current stream
+    def _send(self, kind, l, r0, r1, fused):
+        if fused or not self.ex.can_push:
+            return
+        if self.side is None:
+            self.ex.push_rows(kind, l, r0, r1 - r0)
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            self.ex.push_rows(kind, l, r0, r1 - r0, self.push_ctas)
+        self._side_busy = True
+
+    def _complete(self, kind, l):
+        if self._side_busy:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self._side_busy = False
+        self.ex.gather(kind, l, pushed=self.ex.can_push)
 
     def forward(self, layers, ps, seed, u, p, n, reg, loss, scratch, seed_dev=None):
         part = self.part
         sl = part.slice()
-        # the embedding rows: mirrored into the peers' tables by the Adam kernel of the previous step when the exchange
-        # is fused (the tables start out complete: scatter_from_model), so only the handshake is left
+        # the embedding rows: mirrored into the peers' tables by the Adam kernel of the previous step when that is
+        # fused (the tables start out complete: scatter_from_model), so only the handshake is left
         self.ex.gather("t", 0, pushed=self.ex.fused)
         saved = []
         for l, layer in enumerate(layers):
             x_full = self.tables[l]
             x_loc = x_full[sl]
             s_loc = torch.empty(part.count(), self.dims[l], dtype=torch.float32, device=self.device)
-            self.ops.spmm(self.a, x_full, s_loc)
             out_loc = self.tables[l + 1][sl]
-            # each rank draws its rows' dropout decisions from its own Philox stream (seed + rank)
-            peer_out = self.ex.peer_out("t", l + 1)
-            inv, flags = self.ops.biagg_forward(x_loc, s_loc, layer, out_loc, ps[l], seed + 7919 * part.rank, (l + 1) << 40, seed_dev,
-                                                **({"peer_out": peer_out} if peer_out is not None else {}))
-            self.ex.gather("t", l + 1, pushed=peer_out is not None)
-            saved.append((s_loc, inv, flags))
+            invs, flagss = [], []
+            for a_c, (r0, r1) in zip(self.a, self.bounds):
+                self.ops.spmm(a_c, x_full, s_loc[r0:r1])
+                # each rank draws its rows' dropout decisions from its own Philox stream (seed + rank); the counter
+                # advances by at most 32 per row, so chunk c starts at 32 * r0
+                peer_out = self.ex.peer_out("t", l + 1, r0)
+                inv, flags = self.ops.biagg_forward(x_loc[r0:r1], s_loc[r0:r1], layer, out_loc[r0:r1], ps[l], seed + 7919 * part.rank,
+                                                    ((l + 1) << 40) + 32 * r0, seed_dev, **({"peer_out": peer_out} if peer_out is not None else {}))
+                self._send("t", l + 1, r0, r1, peer_out is not None)
+                invs.append(inv)
+                flagss.append(flags)
+            self._complete("t", l + 1)
+            saved.append((s_loc, invs, flagss))
         self.ops.bpr_forward(self.tables, u, p, n, reg, loss, scratch)
         self.saved = (saved, (u, p, n), reg, scratch, ps)
         return loss
@@ -300,14 +362,20 @@ class ShardedPropagation:
         inject(L)
         pgrads = [None] * L
         for l in range(L, 0, -1):
-            s_loc, inv, flags = saved[l - 1]
+            s_loc, invs, flagss = saved[l - 1]
             x_loc = self.tables[l - 1][sl]
             g_s_loc = self.gs_full[l - 1][sl]
             g_e_loc = torch.empty(part.count(), self.dims[l - 1], dtype=torch.float32, device=self.device)
-            peer_out = self.ex.peer_out("g", l - 1)
-            pgrads[l - 1] = self.ops.biagg_backward(self.g_tables[l][sl], self.tables[l][sl], inv, flags, x_loc, s_loc, layers[l - 1], ps[l - 1],
-                                                    g_s_loc, g_e_loc, **({"peer_out": peer_out} if peer_out is not None else {}))
-            self.ex.gather("g", l - 1, pushed=peer_out is not None)
+            g_out_loc, out_loc = self.g_tables[l][sl], self.tables[l][sl]
+            for c, (r0, r1) in enumerate(self.bounds):
+                peer_out = self.ex.peer_out("g", l - 1, r0)
+                kw = {"peer_out": peer_out} if peer_out is not None else {}
+                if c > 0:
+                    kw["accumulate_into"] = pgrads[l - 1]
+                pgrads[l - 1] = self.ops.biagg_backward(g_out_loc[r0:r1], out_loc[r0:r1], invs[c], flagss[c], x_loc[r0:r1], s_loc[r0:r1],
+                                                        layers[l - 1], ps[l - 1], g_s_loc[r0:r1], g_e_loc[r0:r1], **kw)
+                self._send("g", l - 1, r0, r1, peer_out is not None)
+            self._complete("g", l - 1)
             self.ops.spmm(self.at, self.gs_full[l - 1], self.g_tables[l - 1][sl], addend=g_e_loc)
             inject(l - 1)
         if part.world > 1:
@@ -327,9 +395,10 @@ class ShardedEngine:
     """Epoch driver for P ranks: sharded CF phase, replicated KG phase and refresh."""
 
     def __init__(self, model, part: CyclicPartition, use_graphs: bool = True, exchange: str | None = None):
-        """``exchange``: "peer" (default; rows stored into the peers' tables from the producing kernels' epilogues),
-        "peer-push" (same protocol, separate push kernel) or "nccl" (all-gather / all-reduce collectives, the
-        baseline the peer path is measured against).  Environment override: KGAT_EXCHANGE."""
+        """``exchange``: "peer" (default; NVLink peer memory: the bi-interaction forward stores its rows into the peers'
+        tables from its own epilogue, the other rows go out with a push kernel), "peer-all" (every producer fused),
+        "peer-push" (no producer fused) or "nccl" (all-gather / all-reduce collectives, the baseline the peer path is
+        measured against).  Environment override: KGAT_EXCHANGE."""
         import os
 
         from . import ops
@@ -338,10 +407,16 @@ class ShardedEngine:
         self.model, self.part, self.kops, self.ops = model, part, KernelOps(), ops
         self.use_graphs = use_graphs
         self.exchange_kind = exchange or os.environ.get("KGAT_EXCHANGE", "peer")
-        if self.exchange_kind not in ("peer", "peer-push", "nccl"):
+        if self.exchange_kind not in ("peer", "peer-all", "peer-push", "nccl"):
             raise ValueError(f"unknown exchange {self.exchange_kind!r}")
         self.exchange = None
         self._cf_kernels = 0
+        # Row chunks per layer: chunk c's rows travel to the peers (side stream, copy engines) while chunk c + 1 is
+        # computed.  Off by default: at the C3 shape the per-rank kernels are already 10-60 us, and splitting them costs
+        # more (ramp-up, per-CTA weight staging) than the hidden transfer saves -- 4 GPUs: 795 us per CF step
+        # unchunked, 1,095 us with 2 chunks, 1,215 us with 4 (tools/prof_sharded.py).  For tables that do not fit one
+        # GPU (C5) the kernels are 100x longer and the trade flips.
+        self.n_chunks = max(1, int(os.environ.get("KGAT_SHARD_CHUNKS", "1")))
         self._cf_graph = None
         self._cf_graph_key = None
         self._cf_padded = None
@@ -353,7 +428,8 @@ class ShardedEngine:
         dims = [model._cf_embedding_dim, *model._layer_dims]
         if part.world > 1 and self.exchange_kind != "nccl":
             n_flat = sum(t.numel() for grp in self.layers for t in grp)
-            self.exchange = PeerExchange(part, dims, self.dev, n_flat, fused=self.exchange_kind == "peer")
+            fused = {"peer": ("t",), "peer-all": ("t", "g", "e"), "peer-push": ()}[self.exchange_kind]
+            self.exchange = PeerExchange(part, dims, self.dev, n_flat, fused=fused)
         self._build_graph(dims)
         n_loc = part.count()
         d0 = dims[0]
@@ -374,14 +450,20 @@ class ShardedEngine:
         self._graph_id = (id(g), g.vals.data_ptr())
         rp, ci = g.row_ptr.cpu().numpy(), g.col_idx.cpu().numpy()
         tp, ti = g.t_ptr.cpu().numpy(), g.t_idx.cpu().numpy()
-        self.a = self.kops.make_local_graph(*shard_csr(rp, ci, self.part), self.dev)
+        n_loc = self.part.count()
+        n_chunks = self.n_chunks if self.exchange is not None else 1
+        cuts = [n_loc * c // n_chunks for c in range(n_chunks + 1)]
+        self.bounds = [(cuts[c], cuts[c + 1]) for c in range(n_chunks) if cuts[c + 1] > cuts[c]]
+        self.a = [self.kops.make_local_graph(*shard_csr(rp, ci, self.part, b), self.dev) for b in self.bounds]
         self.at = self.kops.make_local_graph(*shard_csr(tp, ti, self.part), self.dev)
-        self.prop = ShardedPropagation(self.part, self.a, self.at, self.kops, dims, self.dev, exchange=self.exchange)
+        self.prop = ShardedPropagation(self.part, self.a, self.at, self.kops, dims, self.dev, exchange=self.exchange,
+                                       chunk_bounds=self.bounds)
         self.refresh_values()
 
     def refresh_values(self):
         g = self.model._graph()
-        self.kops.refresh_values(self.a, g.vals)
+        for a_c in self.a:
+            self.kops.refresh_values(a_c, g.vals)
         self.kops.refresh_values(self.at, g.t_vals)
 
     def scatter_from_model(self):
