@@ -425,6 +425,10 @@ int bwd_ctas(int64_t n) {
 }  // namespace
 }  // namespace kgat
 
+#ifndef KGAT_BIAGG_DEFAULT_IMPL
+#define KGAT_BIAGG_DEFAULT_IMPL 2
+#endif
+
 namespace kgat {
 // tensor-core (3xTF32 mma.sync) implementation, biagg_mma.cu
 int biagg_mma_forward(const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* b1, const float* W2,
@@ -437,15 +441,23 @@ int biagg_mma_backward(const float* g_out, int64_t ld_gout, const float* out, in
 // peer.cu: copy n_floats to the same offset behind every peer pointer
 int peer_push_launch(const float* src, float* const* peer_dst, int n_peers, int64_t n_floats, cudaStream_t stream, int max_ctas = 0);
 
-// KGAT_BIAGG_IMPL=ffma selects the CUDA-core kernels of this file (A/B comparison); default: tensor cores
-static bool use_mma() {
+// tcgen05 forward (TMEM accumulators), biagg_tc5.cu
+bool biagg_tc5_supported(int d_in, int d_out);
+int biagg_tc5_forward(const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* b1, const float* W2,
+                      const float* b2, float p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits,
+                      float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, float* const* peer_out, int n_peers, cudaStream_t stream);
+
+// KGAT_BIAGG_IMPL selects the implementation (A/B comparison): "ffma" = the CUDA-core kernels of this file,
+// "mma" = warp-level mma.sync (biagg_mma.cu), "tc5" = tcgen05 forward + mma.sync backward.
+static int biagg_impl() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("KGAT_BIAGG_IMPL");
-        v = (e != nullptr && e[0] == 'f') ? 0 : 1;
+        v = (e == nullptr) ? KGAT_BIAGG_DEFAULT_IMPL : (e[0] == 'f' ? 0 : (e[0] == 't' ? 2 : 1));
     }
-    return v == 1;
+    return v;
 }
+static bool use_mma() { return biagg_impl() >= 1; }
 }  // namespace kgat
 
 using namespace kgat;
@@ -475,6 +487,9 @@ int kgat_biagg_forward(const float* E, const float* S, int64_t n, int32_t d_in, 
     if (n < 0 || dropout_p < 0.f || dropout_p >= 1.f || (ld_out & 3) || n_peers < 0 || n_peers > KGAT_MAX_PEERS || (n_peers && !peer_out))
         return KGAT_ERR_INVALID_ARGUMENT;
     if (n == 0) return KGAT_OK;
+    if (biagg_impl() == 2 && biagg_tc5_supported(d_in, d_out))
+        return biagg_tc5_forward(E, S, n, d_in, d_out, W1, b1, W2, b2, dropout_p, seed, offset, seed_dev, keep_bits, out, ld_out, inv_norm,
+                                 flags, peer_out, n_peers, (cudaStream_t)stream);
     if (use_mma())
         return biagg_mma_forward(E, S, n, d_in, d_out, W1, b1, W2, b2, dropout_p, seed, offset, seed_dev, keep_bits, out, ld_out, inv_norm,
                                  flags, peer_out, n_peers, (cudaStream_t)stream);

@@ -4,9 +4,10 @@
 // (1e-3) would break.  Same interface, same saved tensors and the same staging / fusion as the FFMA
 // kernels in biagg.cu (which remain as the reference implementation, KGAT_BIAGG_IMPL=ffma).
 //
-// Why mma.sync and not tcgen05 here: after the switch the kernels are bound by staging and HBM, not
-// by the tensor pipe (2.6 GFLOP x 3 per layer-forward against 120 MB of traffic), so the simpler
-// register-fragment path already reaches the memory-side limit; see DESIGN.md section 4.
+// The forward of the shapes with d_in, d_out <= 64 runs on tcgen05 by default (biagg_tc5.cu, TMEM accumulators);
+// these warp-level kernels serve the backward, the wider shapes and KGAT_BIAGG_IMPL=mma.  Either way the time
+// goes into operand preparation and the epilogue on the CUDA cores, not into the tensor pipe (2.6 GFLOP x 3 per
+// layer-forward against 120 MB of traffic); see DESIGN.md section 4.
 #include "common.cuh"
 
 namespace kgat {
