@@ -170,6 +170,15 @@ int kgat_transr_backward(const float* emb, const float* rel_emb, const float* W,
                          const int64_t* neg_tails, int32_t batch, float reg, const float* margin, const float* g_loss,
                          float* g_emb, float* g_rel_emb, float* g_W,
                          const int32_t* row_slot, void* stream);
+/* The whole TransR part of a KG training step in three launches (model.py:204-261 forward + its autograd backward):
+ * (1) claim compact gradient rows (kgat_transr_claim_rows) and zero g_rows, g_rel_emb (n_rel x k), g_W in the same
+ * launch; (2) forward and backward in one pass -- the backward recomputes the projections anyway -- with
+ * d loss = 1, gradients into g_rows (through row_slot), g_rel_emb, g_W; (3) loss[0] = batch loss, and
+ * loss_sum[0] += loss[0] when loss_sum != NULL.  margin: 2 * batch floats of scratch. */
+int kgat_transr_step(const float* emb, const float* rel_emb, const float* W, int32_t d, int32_t k, int32_t n_rel,
+                     const int64_t* heads, const int64_t* rels, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch,
+                     float reg, float* loss, float* loss_sum, float* margin, int32_t* row_slot, float* g_rows, float* g_rel_emb,
+                     float* g_W, void* stream);
 /* One slot per distinct node of a TransR batch: row_slot (n_nodes int32, -1 = free) gets, for every node among
  * heads / pos_tails / neg_tails, the index in [0, 3*batch) of its first claimant; g_rows (3*batch x d) is zeroed.
  * kgat_adam_apply (row_slot0) consumes the rows and frees the slots. */

@@ -9,7 +9,7 @@ namespace {
 
 // loss = mean_b(-logsigmoid(margin_b)) + reg * mean_b(l2_b);   scratch = [margin (B)][l2 (B)]
 __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ scratch, int batch, float reg,
-                                                          float* __restrict__ loss) {
+                                                          float* __restrict__ loss, float* __restrict__ loss_sum = nullptr) {
     __shared__ float sh_a[8], sh_b[8];
     float a = 0.f, b = 0.f;
     for (int i = threadIdx.x; i < batch; i += 256) {
@@ -29,7 +29,9 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restric
             ta += sh_a[w];
             tb += sh_b[w];
         }
-        loss[0] = ta / (float)batch + reg * (tb / (float)batch);
+        const float l = ta / (float)batch + reg * (tb / (float)batch);
+        loss[0] = l;
+        if (loss_sum != nullptr) loss_sum[0] += l;
     }
 }
 
@@ -220,12 +222,15 @@ __global__ void __launch_bounds__(128) transr_fwd_kernel(const float* __restrict
     }
 }
 
-template <int DM, int KM>
+// FUSED: forward and backward in one pass (the backward recomputes the projections anyway): the kernel derives the
+// sample's margin itself, records it (and the L2 term) in `scratch` for the loss reduction that follows, and uses
+// d loss / d batch-loss = 1.
+template <int DM, int KM, bool FUSED = false>
 __global__ void __launch_bounds__(128) transr_bwd_kernel(const float* __restrict__ emb, const float* __restrict__ rel_emb,
                                                          const float* __restrict__ W, const int64_t* __restrict__ heads,
                                                          const int64_t* __restrict__ rels, const int64_t* __restrict__ pt,
                                                          const int64_t* __restrict__ nt, int batch, float reg,
-                                                         const float* __restrict__ scratch, const float* __restrict__ g_loss,
+                                                         float* __restrict__ scratch, const float* __restrict__ g_loss,
                                                          float* __restrict__ g_emb, float* __restrict__ g_rel,
                                                          float* __restrict__ g_W, const int32_t* __restrict__ row_slot) {
     constexpr int D = DM * 32, K = KM * 32;
@@ -239,8 +244,31 @@ __global__ void __launch_bounds__(128) transr_bwd_kernel(const float* __restrict
     transr_partial<D, KM>(Wr, emb, h, p, n, warp, lane, eh, ep, en, xh, xp, xn);
     transr_combine<KM>(part, warp, lane, xh, xp, xn);
 
-    const float g = g_loss[0] / (float)batch;
-    const float s2 = 2.f * sigmoidf_(-scratch[b]) * g;  // loss = -logsigmoid(ns - ps)
+    float margin;
+    if (FUSED) {
+        float ps = 0.f, ns = 0.f, l2 = 0.f;
+#pragma unroll
+        for (int m = 0; m < KM; ++m) {
+            const float er = __ldg(rel_emb + r * K + lane + 32 * m);
+            const float dp = xh[m] + er - xp[m];
+            const float dn = xh[m] + er - xn[m];
+            ps = fmaf(dp, dp, ps);
+            ns = fmaf(dn, dn, ns);
+            l2 += xh[m] * xh[m] + er * er + xp[m] * xp[m] + xn[m] * xn[m];
+        }
+        ps = warp_sum(ps);
+        ns = warp_sum(ns);
+        l2 = warp_sum(l2);
+        margin = ns - ps;
+        if (warp == 0 && lane == 0) {
+            scratch[b] = margin;
+            scratch[batch + b] = 0.5f * l2;
+        }
+    } else {
+        margin = scratch[b];
+    }
+    const float g = (FUSED ? 1.f : g_loss[0]) / (float)batch;
+    const float s2 = 2.f * sigmoidf_(-margin) * g;  // loss = -logsigmoid(ns - ps)
     const float lam = reg * g;
     float gxh[KM], gxp[KM], gxn[KM];
 #pragma unroll
@@ -296,9 +324,13 @@ __global__ void __launch_bounds__(128) transr_bwd_kernel(const float* __restrict
 // (row_slot[node] = index of the first claimant, -1 = untouched; the Adam kernel resets the claims), and the
 // 3B x d gradient rows are zeroed -- instead of zeroing and re-reading an n_nodes x d gradient table per step.
 __global__ void transr_claim_rows_kernel(const int64_t* __restrict__ heads, const int64_t* __restrict__ pt, const int64_t* __restrict__ nt,
-                                         int batch, int d, int32_t* __restrict__ row_slot, float4* __restrict__ g_rows) {
+                                         int batch, int d, int32_t* __restrict__ row_slot, float4* __restrict__ g_rows,
+                                         float4* __restrict__ zero_a = nullptr, int n_a = 0, float4* __restrict__ zero_b = nullptr,
+                                         int n_b = 0) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 3 * batch * (d / 4)) g_rows[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n_a) zero_a[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // the step's other gradient buffers, zeroed in the same launch
+    if (i < n_b) zero_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < 3 * batch) {
         const int64_t id = i < batch ? heads[i] : (i < 2 * batch ? pt[i - batch] : nt[i - 2 * batch]);
         atomicCAS(row_slot + id, -1, i);
@@ -367,8 +399,27 @@ int kgat_transr_backward(const float* emb, const float* rel_emb, const float* W,
     if (batch <= 0) return KGAT_ERR_INVALID_ARGUMENT;
     const unsigned blocks = (unsigned)batch;  // one 4-warp CTA per sample
     KGAT_TRANSR_DISPATCH((transr_bwd_kernel<DM, KM><<<blocks, 128, 0, stream>>>(emb, rel_emb, W, heads, rels, pos_tails, neg_tails,
-                                                                               batch, reg, margin, g_loss, g_emb, g_rel_emb, g_W,
-                                                                               row_slot)));
+                                                                               batch, reg, const_cast<float*>(margin), g_loss, g_emb,
+                                                                               g_rel_emb, g_W, row_slot)));
+    return check_launch();
+}
+
+int kgat_transr_step(const float* emb, const float* rel_emb, const float* W, int32_t d, int32_t k, int32_t n_rel, const int64_t* heads,
+                     const int64_t* rels, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, float reg, float* loss,
+                     float* loss_sum, float* margin, int32_t* row_slot, float* g_rows, float* g_rel_emb, float* g_W, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (batch <= 0 || d <= 0 || (d & 3) || (k & 3) || n_rel <= 0 || !row_slot || !g_rows || !g_rel_emb || !g_W || !loss || !margin)
+        return KGAT_ERR_INVALID_ARGUMENT;
+    const int n_rows4 = 3 * batch * (d / 4), n_rel4 = n_rel * k / 4, n_w4 = n_rel * d * (k / 4);
+    const int n = n_rows4 > n_w4 ? (n_rows4 > n_rel4 ? n_rows4 : n_rel4) : (n_w4 > n_rel4 ? n_w4 : n_rel4);
+    transr_claim_rows_kernel<<<(n + 255) / 256, 256, 0, stream>>>(heads, pos_tails, neg_tails, batch, d, row_slot,
+                                                                 reinterpret_cast<float4*>(g_rows), reinterpret_cast<float4*>(g_rel_emb),
+                                                                 n_rel4, reinterpret_cast<float4*>(g_W), n_w4);
+    const unsigned blocks = (unsigned)batch;
+    KGAT_TRANSR_DISPATCH((transr_bwd_kernel<DM, KM, true><<<blocks, 128, 0, stream>>>(emb, rel_emb, W, heads, rels, pos_tails, neg_tails,
+                                                                                     batch, reg, margin, nullptr, g_rows, g_rel_emb, g_W,
+                                                                                     row_slot)));
+    loss_reduce_kernel<<<1, 256, 0, stream>>>(margin, batch, reg, loss, loss_sum);
     return check_launch();
 }
 

@@ -163,13 +163,10 @@ class TrainEngine:
             for ids in (h, tails):
                 ops.adam_sparse_rows(emb, self.kg_grads[0], ad.exp_avg[0], ad.exp_avg_sq[0], self.kg_row_step, ids, ad.step_dev, self.kg_s0, ad.hyper)
         else:
-            ops.transr_forward(emb, rel, w, h, r, pt, nt, reg, self.kg_loss, self.kg_scratch)
-            ops.transr_claim_rows(h, pt, nt, emb.shape[1], self.kg_row_slot, self.kg_grad_rows)
-            for g in self.kg_grads[1:]:
-                ops.fill_(g, 0.0)
-            ops.transr_backward(emb, rel, w, h, r, pt, nt, reg, self.kg_scratch, self.one, self.kg_grad_rows, *self.kg_grads[1:],
-                                row_slot=self.kg_row_slot)
+            ops.transr_step(emb, rel, w, h, r, pt, nt, reg, self.kg_loss, self.kg_loss_sum, self.kg_scratch, self.kg_row_slot,
+                            self.kg_grad_rows, self.kg_grads[1], self.kg_grads[2])
             ad.apply([self.kg_grad_rows] + self.kg_grads[1:], row_slot0=self.kg_row_slot)
+            return
         self.kg_loss_sum.add_(self.kg_loss)
 
     def _kg_phase_begin(self, n_kg: int):

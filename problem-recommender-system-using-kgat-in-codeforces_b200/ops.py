@@ -326,6 +326,19 @@ def transr_claim_rows(heads, pos_t, neg_t, d: int, row_slot, g_rows):
                                      _ptr(g_rows, f32), _stream()), "transr_claim_rows")
 
 
+@_timed("transr_step")
+def transr_step(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, loss, loss_sum, scratch, row_slot, g_rows, g_rel, g_W):
+    """Claim compact gradient rows + zero the gradient buffers, TransR forward and backward in one pass, loss value
+    (added to ``loss_sum`` when given): the KG half-step of the epoch engine in three launches."""
+    lib = _lib.load()
+    if g_rows.numel() < 3 * heads.numel() * emb.shape[1] or scratch.numel() < 2 * heads.numel():
+        raise KgatLibraryError("transr_step: g_rows needs 3 * batch * d floats, scratch 2 * batch")
+    check(lib.kgat_transr_step(_ptr(emb, f32), _ptr(rel_emb, f32), _ptr(W, f32), emb.shape[1], rel_emb.shape[1], rel_emb.shape[0],
+                               _ptr(heads, i64), _ptr(rels, i64), _ptr(pos_t, i64), _ptr(neg_t, i64), heads.numel(), float(reg),
+                               _ptr(loss, f32), _ptr(loss_sum, f32) if loss_sum is not None else None, _ptr(scratch, f32),
+                               _ptr(row_slot, i32), _ptr(g_rows, f32), _ptr(g_rel, f32), _ptr(g_W, f32), _stream()), "transr_step")
+
+
 def transr_backward(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, scratch, g_loss, g_emb, g_rel, g_W, row_slot=None):
     lib = _lib.load()
     check(
