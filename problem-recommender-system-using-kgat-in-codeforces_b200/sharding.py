@@ -639,8 +639,10 @@ def bench_main(args, metric, unit, workload, make_workload, config_dict, ClockSa
             "propagation_edges_per_s": graph.nnz * 3 * 2 * data.n_cf / epoch_s,
             "cf_loss": losses[0], "kg_loss": losses[1], "gpu_launches": _lib.LaunchCounter.count, "clocks": clocks.summary(),
             "e2e": None, "roofline": None, "cpu_baseline": None,
-            "note": "CF phase row-sharded (cyclic) with 7 all-gathers + 1 all-reduce per step over NCCL; KG phase and the refresh are replicated; "
-                    "timed on the device, max over ranks",
+            "exchange": eng.exchange_kind,
+            "note": "CF phase row-sharded (cyclic): 7 row exchanges + 1 gradient all-reduce per step over NVLink peer memory (stores from the "
+                    "bi-interaction forward epilogue / a push kernel + flag handshake; exchange=nccl uses NCCL collectives instead), the whole "
+                    "step captured as one CUDA graph per rank; KG phase and the refresh are replicated; timed on the device, max over ranks",
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     # tear-down: drop the captured graphs (they hold NCCL work) before the communicator, and do not let a

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Short, ncu-friendly slice of the Amazon-book-shaped workload: a few eager (un-captured) CF steps,
-KG steps and one attention refresh through the public model API, so every kernel shows up as its own
-launch.  Used with the ncu recipes of /opt/skills/guides/B200_PROFILING.md; summaries go to profiles/.
+KG steps and one attention refresh through the public model API, then the same number of steps through the epoch
+engine's un-captured step bodies, so every kernel shows up as its own launch.  Used with the ncu recipes of /opt/skills/guides/B200_PROFILING.md; summaries go to profiles/.
 
     python tools/prof_steps.py [--shape amazon-book] [--cf 3] [--kg 6]
 """
@@ -47,5 +47,15 @@ model(*edges, mode=KGATMode.UPDATE_ATTENTION)
 with torch.no_grad():
     model.eval()
     s = model(torch.arange(256), torch.arange(g.item_num, device=dev), mode=KGATMode.PREDICT)
+# the epoch engine's own step bodies, un-captured (compact KG gradient rows, fused TransR step)
+from kgat_b200.engine import TrainEngine  # noqa: E402
+from kgat_b200.trainer import EpochData  # noqa: E402
+
+model.train()
+g_full = synthetic.make_ckg(args.shape, with_dicts=True)
+data = EpochData.sample(g_full, n_cf=args.cf, n_kg=args.kg)
+eng = TrainEngine(model, use_graphs=False)
+eng.bind_resident(data.tensors())
+eng.run_epoch(refresh=False)
 torch.cuda.synchronize()
 print("ok", float(loss), tuple(s.shape))
