@@ -200,12 +200,15 @@ class PeerExchange:
     all-reduce is the same pattern: every rank deposits its partial in slot ``rank`` of every peer and all ranks
     add the slots in rank order (bit-identical results on every rank)."""
 
-    def __init__(self, part: CyclicPartition, dims, device, n_flat: int, fused=("t",)):
+    def __init__(self, part: CyclicPartition, dims, device, n_flat: int, fused=()):
         """``fused``: which producers store into the peers' tables from their own epilogue -- "t" the bi-interaction
-        forward (layer tables), "g" its backward (side gradients), "e" Adam (embedding rows).  Measured at the C3
-        shape: the forward kernel is tensor-pipe bound and hides the NVLink stores (2 GPUs: 126 us fused vs 103 + 47
-        us kernel + push); the backward's 8-byte fragment stores and the HBM-bound Adam sweep do not (4 GPUs: 319 vs
-        127 + 100 us, 69 vs 20 + 40 us), so by default those rows go out with the push kernel."""
+        forward (layer tables), "g" its backward (side gradients), "e" Adam (embedding rows) -- instead of a push
+        kernel after them.  Measured at the C3 shape, the fused stores only pay where they leave the SM as wide,
+        coalesced bursts from a kernel that is not memory-bound: the mma.sync forward (tile staged in shared memory,
+        512-byte warp stores) hid half of them at 2 GPUs (126 us fused vs 103 + 47 us kernel + push); the backward's
+        8-byte fragment stores, the HBM-bound Adam sweep (4 GPUs: 319 vs 127 + 100 us, 69 vs 20 + 40 us) and the
+        thread-per-row 16-byte stores of the tcgen05 forward epilogue (8 GPUs: 502 vs 60 us + push) do not.  Default:
+        nothing fused, every table goes out with the push kernel at NVLink rate."""
         from .peer import PeerArena
 
         self.part, self.fused_kinds = part, tuple(fused)
@@ -395,10 +398,10 @@ class ShardedEngine:
     """Epoch driver for P ranks: sharded CF phase, replicated KG phase and refresh."""
 
     def __init__(self, model, part: CyclicPartition, use_graphs: bool = True, exchange: str | None = None):
-        """``exchange``: "peer" (default; NVLink peer memory: the bi-interaction forward stores its rows into the peers'
-        tables from its own epilogue, the other rows go out with a push kernel), "peer-all" (every producer fused),
-        "peer-push" (no producer fused) or "nccl" (all-gather / all-reduce collectives, the baseline the peer path is
-        measured against).  Environment override: KGAT_EXCHANGE."""
+        """``exchange``: "peer" (default; NVLink peer memory: every produced table is pushed into the peers' copies by a
+        store kernel, flag handshake instead of a collective), "peer-fwd" / "peer-all" (the bi-interaction forward /
+        every producer stores into the peers' tables from its own epilogue) or "nccl" (all-gather / all-reduce
+        collectives, the baseline the peer path is measured against).  Environment override: KGAT_EXCHANGE."""
         import os
 
         from . import ops
@@ -407,7 +410,9 @@ class ShardedEngine:
         self.model, self.part, self.kops, self.ops = model, part, KernelOps(), ops
         self.use_graphs = use_graphs
         self.exchange_kind = exchange or os.environ.get("KGAT_EXCHANGE", "peer")
-        if self.exchange_kind not in ("peer", "peer-all", "peer-push", "nccl"):
+        if self.exchange_kind == "peer-push":
+            self.exchange_kind = "peer"
+        if self.exchange_kind not in ("peer", "peer-fwd", "peer-all", "nccl"):
             raise ValueError(f"unknown exchange {self.exchange_kind!r}")
         self.exchange = None
         self._cf_kernels = 0
@@ -428,7 +433,7 @@ class ShardedEngine:
         dims = [model._cf_embedding_dim, *model._layer_dims]
         if part.world > 1 and self.exchange_kind != "nccl":
             n_flat = sum(t.numel() for grp in self.layers for t in grp)
-            fused = {"peer": ("t",), "peer-all": ("t", "g", "e"), "peer-push": ()}[self.exchange_kind]
+            fused = {"peer": (), "peer-fwd": ("t",), "peer-all": ("t", "g", "e")}[self.exchange_kind]
             self.exchange = PeerExchange(part, dims, self.dev, n_flat, fused=fused)
         self._build_graph(dims)
         n_loc = part.count()
@@ -640,8 +645,8 @@ def bench_main(args, metric, unit, workload, make_workload, config_dict, ClockSa
             "cf_loss": losses[0], "kg_loss": losses[1], "gpu_launches": _lib.LaunchCounter.count, "clocks": clocks.summary(),
             "e2e": None, "roofline": None, "cpu_baseline": None,
             "exchange": eng.exchange_kind,
-            "note": "CF phase row-sharded (cyclic): 7 row exchanges + 1 gradient all-reduce per step over NVLink peer memory (stores from the "
-                    "bi-interaction forward epilogue / a push kernel + flag handshake; exchange=nccl uses NCCL collectives instead), the whole "
+            "note": "CF phase row-sharded (cyclic): 7 row exchanges + 1 gradient all-reduce per step over NVLink peer memory (store kernel "
+                    "into the peers' tables + flag handshake; exchange=nccl uses NCCL collectives instead), the whole "
                     "step captured as one CUDA graph per rank; KG phase and the refresh are replicated; timed on the device, max over ranks",
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())

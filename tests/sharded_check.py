@@ -48,7 +48,7 @@ def main():
     ref_eng.bind_resident(data.tensors())
     ref_losses = ref_eng.run_epoch()
     ref_state = {k: v.detach().clone() for k, v in ref.state_dict().items() if not v.is_sparse}
-    for kind in ("nccl", "peer-push", "peer", "peer-all"):
+    for kind in ("nccl", "peer", "peer-fwd", "peer-all"):
         for use_graphs in (False, True):
             m, holder = fresh()
             eng = sharding.ShardedEngine(m, sharding.CyclicPartition(g.node_num, world, rank), use_graphs=use_graphs, exchange=kind)
