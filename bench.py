@@ -149,6 +149,61 @@ def cpu_reference_sample(g, params, data, n_cf_steps: int = 1, n_kg_steps: int =
     }
 
 
+def aten_gpu_sample(g, params, data, device, n_cf_steps: int = 3, n_kg_steps: int = 10, refresh_relations: int = 2):
+    """The same oracle port (the reference's ATen call sequence) with every tensor on the B200: what stock PyTorch
+    -- cuSPARSE SpMM, cuBLAS, ~100 elementwise kernels per step, torch.optim.Adam, the device -> host -> device round
+    trip around the CPU sparse softmax of model.py:364-366 -- makes of this epoch on the same box (SURVEY.md 8d:
+    "the real kernel to beat").  Part of the baseline leg: bounded sample, extrapolated like the CPU one."""
+    from oracle import kgat_oracle as O
+
+    n = g.node_num
+    att = torch.sparse_coo_tensor(torch.from_numpy(np.vstack([g.att_rows, g.att_cols])).long(), torch.from_numpy(g.att_vals),
+                                  size=(n, n)).to(device)
+    p = {k: v.detach().clone().to(device).requires_grad_(True) for k, v in params.items()}
+    opt = {"cf": torch.optim.Adam(list(p.values()), lr=1e-3), "kg": torch.optim.Adam(list(p.values()), lr=1e-4)}
+
+    def run(kind, batches, loss_fn):
+        ts = []
+        for i, b in enumerate(batches):
+            b = [torch.from_numpy(a).to(device) for a in b]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            loss = loss_fn(p, b)
+            loss.backward()
+            opt[kind].step()
+            opt[kind].zero_grad()
+            float(loss)  # main.py:314 / 343 read the loss every step
+            ts.append(time.perf_counter() - t0)
+        return float(np.mean(ts[1:]))  # first step = warm-up (cuSPARSE / cuBLAS handles, allocator)
+
+    t_cf = run("cf", [[a[i] for a in data.cf] for i in range(n_cf_steps + 1)], lambda q, b: O.cf_loss(q, att, *b))
+    t_kg = run("kg", [[a[i] for a in data.kg] for i in range(n_kg_steps + 1)], lambda q, b: O.kg_loss(q, *b))
+    rels = np.asarray(g.adjacency_relations[:refresh_relations])
+    sel = np.isin(g.relations, rels)
+    heads = torch.from_numpy(g.heads[sel].astype(np.int64)).to(device)
+    tails = torch.from_numpy(g.tails[sel].astype(np.int64)).to(device)
+    rel_of = torch.from_numpy(g.relations[sel].astype(np.int64)).to(device)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        q = {k: v.detach() for k, v in p.items()}
+        rows, cols, vals = [], [], []
+        for r in rels.tolist():  # model.py:342-353
+            idx = torch.where(rel_of == r)[0]
+            rows.append(heads[idx])
+            cols.append(tails[idx])
+            vals.append(O.attention_by_relation(q, heads[idx], tails[idx], r, n))
+        m = torch.sparse_coo_tensor(torch.stack([torch.cat(rows), torch.cat(cols)]), torch.cat(vals), size=(n, n))
+        m = torch.sparse.softmax(m.cpu(), dim=1).to(device)  # model.py:364-366
+    torch.cuda.synchronize()
+    share = float(sel.sum()) / max(g.nnz, 1)
+    t_refresh = (time.perf_counter() - t0) / max(share, 1e-9)
+    return {"value": data.n_cf * t_cf + data.n_kg * t_kg + t_refresh, "unit": UNIT,
+            "kind": "oracle port with all tensors on cuda:0 (stock ATen / cuSPARSE / torch.optim.Adam kernels, loss read every step)",
+            "cf_step_s": t_cf, "kg_step_s": t_kg, "refresh_s": t_refresh,
+            "sample": f"{n_cf_steps} CF + {n_kg_steps} KG steps after one warm-up step each + refresh of {share:.1%} of the edges, extrapolated"}
+
+
 def make_workload(workload: str, seed: int = 2024):
     from kgat_b200 import synthetic
     from kgat_b200.trainer import EpochData
@@ -420,6 +475,10 @@ def main():
         c = cpu_reference_sample(g, init_state, data)
         cpu = {"value": c["epoch_s_extrapolated"], "unit": UNIT, "cores": c["cores"], "kind": "port", "sample": c["sample"],
                "cf_step_s": c["cf_step_s"], "kg_step_s": c["kg_step_s"], "refresh_s": c["refresh_s_extrapolated"]}
+        try:  # the same port on the GPU itself (stock ATen kernels): reported next to the CPU figure
+            cpu["same_port_on_gpu"] = aten_gpu_sample(g, init_state, data, dev)
+        except Exception as e:  # noqa: BLE001 - a baseline must never take the bench line down
+            cpu["same_port_on_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
     n_layers = 3
     edges_per_epoch = graph.nnz * n_layers * 2 * data.n_cf
