@@ -75,8 +75,8 @@ class FusedAdam(torch.optim.Optimizer):
         the 80 us of GPU work of a KG step.  Falls back to the wrapped methods as soon as any hook is registered."""
         from torch.optim import optimizer as _o
 
-        if (self._optimizer_step_pre_hooks or self._optimizer_step_post_hooks or _o._global_optimizer_pre_hooks
-                or _o._global_optimizer_post_hooks):
+        if (getattr(self, "_optimizer_step_pre_hooks", None) or getattr(self, "_optimizer_step_post_hooks", None)
+                or getattr(_o, "_global_optimizer_pre_hooks", None) or getattr(_o, "_global_optimizer_post_hooks", None)):
             self.step()
             self.zero_grad()
             return
