@@ -66,14 +66,19 @@ class TorchOps:
         out.copy_(F.normalize(x, dim=1, eps=1e-12))
         return None, None
 
-    def biagg_backward(self, g_out, out, inv, flags, e, s, layer, p, g_s, g_e):
+    def biagg_backward(self, g_out, out, inv, flags, e, s, layer, p, g_s, g_e, accumulate_into=None):
         leaves = [t.detach().clone().requires_grad_(True) for t in (e, s, *layer)]
         ee, ss, w1, b1, w2, b2 = leaves
         x = F.leaky_relu(F.linear(ee + ss, w1, b1), 0.01) + F.leaky_relu(F.linear(ee * ss, w2, b2), 0.01)
         F.normalize(x, dim=1, eps=1e-12).backward(g_out)
         g_e.copy_(ee.grad)
         g_s.copy_(ss.grad)
-        return [w1.grad, b1.grad, w2.grad, b2.grad]
+        grads = [w1.grad, b1.grad, w2.grad, b2.grad]
+        if accumulate_into is not None:  # later row chunks of a layer add to the first chunk's parameter gradients
+            for acc, g in zip(accumulate_into, grads):
+                acc.add_(g)
+            return accumulate_into
+        return grads
 
     def bpr_forward(self, tables, u, p, n, reg, loss, scratch):
         from oracle import kgat_oracle as O
@@ -90,7 +95,7 @@ class TorchOps:
                 g.add_(leaf.grad)
 
 
-def _worker(rank, world, port, ok):
+def _worker(rank, world, port, ok, n_chunks=1):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -109,14 +114,20 @@ def _worker(rank, world, port, ok):
         trow = torch._convert_indices_from_coo_to_csr(att_t.indices()[0], n).numpy()
         tcol, tval = att_t.indices()[1].numpy(), att_t.values()
 
-        def local(rp, ci, vals):
-            lp, lc, slots = shard_csr(rp, ci, part)
+        def local(rp, ci, vals, rng=None):
+            lp, lc, slots = shard_csr(rp, ci, part, rng)
+            rows = part.count() if rng is None else rng[1] - rng[0]
             csr = torch.sparse_csr_tensor(torch.from_numpy(lp).long(), torch.from_numpy(lc).long(), vals[torch.from_numpy(slots).long()],
-                                          size=(part.count(), part.padded))
+                                          size=(rows, part.padded))
             return {"csr": csr}
 
         dims = [64, 64, 32, 16]
-        prop = ShardedPropagation(part, local(crow, col, val), local(trow, tcol, tval), TorchOps(), dims, "cpu")
+        # the forward SpMM / bi-interaction optionally run over consecutive chunks of the local rows (the pipeline the
+        # peer exchange uses to overlap transfers); the result must not depend on the chunking
+        cuts = [part.count() * c // n_chunks for c in range(n_chunks + 1)]
+        bounds = [(cuts[c], cuts[c + 1]) for c in range(n_chunks)]
+        a_chunks = [local(crow, col, val, b) for b in bounds]
+        prop = ShardedPropagation(part, a_chunks, local(trow, tcol, tval), TorchOps(), dims, "cpu", chunk_bounds=bounds)
         layers = [tuple(params[f"_aggregator_layers.{l}.linear{k}.{w}"] for k in (1, 2) for w in ("weight", "bias")) for l in range(3)]
         e0 = params["_user_entity_embedding.weight"]
         # only the own slice is filled: the forward all-gathers the rest
@@ -143,9 +154,10 @@ def _worker(rank, world, port, ok):
 
 
 @pytest.mark.timeout(300)
-def test_sharded_cf_step_world2_gloo_matches_oracle():
+@pytest.mark.parametrize("n_chunks", [1, 3])
+def test_sharded_cf_step_world2_gloo_matches_oracle(n_chunks):
     world = 2
     ok = mp.get_context("spawn").Array("i", [0] * world)
-    port = 29000 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(world, port, ok), nprocs=world, join=True)
+    port = 29000 + (os.getpid() % 2000) + 7 * n_chunks
+    mp.spawn(_worker, args=(world, port, ok, n_chunks), nprocs=world, join=True)
     assert list(ok) == [1] * world
