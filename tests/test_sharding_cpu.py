@@ -52,6 +52,48 @@ def test_cyclic_partition_index_math():
     assert (seen == 1).all()
 
 
+def test_cyclic_partition_properties_random_shapes():
+    """Property test over random (n, world, chunking): the padded cyclic layout is a bijection onto distinct rows, rank
+    slices tile it, and the row-chunked local CSRs partition the non-zeros of a rank exactly."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from kgat_b200.sharding import CyclicPartition, shard_csr
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.integers(1, 200), world=st.integers(1, 9), n_chunks=st.integers(1, 5), seed=st.integers(0, 10**6))
+    def check(n, world, n_chunks, seed):
+        rng = np.random.default_rng(seed)
+        parts = [CyclicPartition(n, world, r) for r in range(world)]
+        pad = parts[0].to_padded(np.arange(n))
+        assert len(set(pad.tolist())) == n and pad.min() >= 0 and pad.max() < parts[0].padded
+        assert sum(p.count() for p in parts) == n and all(p.count() <= p.max_rows for p in parts)
+        lens = rng.integers(0, 5, n)
+        rp = np.concatenate([[0], np.cumsum(lens)])
+        ci = rng.integers(0, n, rp[-1])
+        seen = np.zeros(rp[-1], int)
+        for p in parts:
+            sl, fs = p.slice(), p.full_slice()
+            assert fs.start == p.rank * p.max_rows and fs.stop - fs.start == p.max_rows and sl.stop - sl.start == p.count()
+            cuts = [p.count() * c // n_chunks for c in range(n_chunks + 1)]
+            whole = shard_csr(rp, ci, p)
+            got_slots, got_cols = [], []
+            for c in range(n_chunks):
+                lp, lc, slots = shard_csr(rp, ci, p, (cuts[c], cuts[c + 1]))
+                assert lp[0] == 0 and len(lp) == cuts[c + 1] - cuts[c] + 1 and lp[-1] == len(lc) == len(slots)
+                np.testing.assert_array_equal(np.diff(lp), lens[p.local_rows()[cuts[c] : cuts[c + 1]]])
+                got_slots.append(slots)
+                got_cols.append(lc)
+                seen[slots] += 1
+            np.testing.assert_array_equal(np.concatenate(got_slots) if got_slots else [], whole[2])
+            np.testing.assert_array_equal(np.concatenate(got_cols) if got_cols else [], whole[1])
+        assert (seen == 1).all()
+        t = torch.from_numpy(rng.standard_normal((n, 2)).astype(np.float32))
+        assert torch.equal(parts[-1].gather_rows(parts[-1].scatter_rows(t)), t)
+
+    check()
+
+
 class TorchOps:
     """LocalOps with plain torch CPU ops (test double for sharding.KernelOps)."""
 
