@@ -32,7 +32,7 @@ extern "C" {
 #define KGAT_ERR_UNSUPPORTED (-3)
 #define KGAT_ERR_WORKSPACE (-4)
 
-#define KGAT_ABI_VERSION 2
+#define KGAT_ABI_VERSION 3
 #define KGAT_MAX_LAYERS 8   /* embedding table + up to 7 propagation layers */
 #define KGAT_MAX_TENSORS 24 /* tensors per multi-tensor Adam launch */
 #define KGAT_MAX_PEERS 31   /* other ranks of a row-sharded propagation */
@@ -97,6 +97,36 @@ int kgat_spmm_csr(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_rows, in
                   const int32_t* col_idx, const float* vals, const float* X, int64_t n_cols, int64_t ldx, float* Y,
                   int64_t ldy, const float* Z, int64_t ldz, int32_t d, float* partials, void* stream);
 
+/* The same product restricted to the rows / edges a TRAIN_CF step actually needs (frontier section below):
+ *   row_mask  (bitmap over output rows, NULL = all): tasks of other rows are skipped, their Y rows left untouched;
+ *   edge_mask (bitmap over columns,     NULL = all): edges whose column is outside are dropped (their X rows hold no
+ *             valid data) and the addend Z[row] is added only for rows inside it.
+ * Bit i of a bitmap is bit (i & 31) of word i >> 5. */
+int kgat_spmm_csr_masked(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_rows, int64_t n_heavy,
+                         const int32_t* col_idx, const float* vals, const float* X, int64_t n_cols, int64_t ldx, float* Y,
+                         int64_t ldy, const float* Z, int64_t ldz, int32_t d, float* partials, const uint32_t* row_mask,
+                         const uint32_t* edge_mask, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Needed-row frontier of a TRAIN_CF step: exact pruning of model.py:188 (the full propagation   */
+/* is re-run per mini-batch although model.py:189-191 gathers only the <= 3B batch rows)         */
+/* ------------------------------------------------------------------------------------------- */
+/* F_L = {batch ids}, F_{l-1} = F_l U cols(A[F_l, :]): layer l is computed for the rows of F_l only; every row outside
+ * has an exactly-zero gradient and is never read, so loss and gradients equal the reference's.  A level is a bitmap
+ * over the nodes plus the ascending list of its rows with a device-side count (everything stream-ordered). */
+/* bitmap |= {ids64[i]}; ids outside [0, n_nodes) are skipped and counted in *bad_count_dev (nullable) */
+int kgat_frontier_mark_ids(const int64_t* ids64, int64_t n_ids, int64_t n_nodes, uint32_t* bitmap, int32_t* bad_count_dev,
+                           void* stream);
+/* bitmap_out |= {r} U cols(A[r, :]) for the *count_dev rows listed in `rows` (max_rows sizes the grid) */
+int kgat_frontier_expand(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* rows, const int32_t* count_dev,
+                         int64_t max_rows, uint32_t* bitmap_out, void* stream);
+/* rows[0 .. *count_dev) = ascending node ids of the set bits; scratch: kgat_frontier_scratch_ints(n_nodes) int32 */
+int64_t kgat_frontier_scratch_ints(int64_t n_nodes);
+int kgat_frontier_list(const uint32_t* bitmap, int64_t n_nodes, int32_t* scratch, int32_t* rows, int32_t* count_dev, void* stream);
+/* T[rows[i], 0:d] = 0 for i < *count_dev (gradient rows of the last table before the BPR scatter) */
+int kgat_frontier_zero_rows(float* T, int64_t ld, int32_t d, const int32_t* rows, const int32_t* count_dev, int64_t max_rows,
+                            void* stream);
+
 /* ------------------------------------------------------------------------------------------- */
 /* K2/K3: bi-interaction aggregator   reference aggregator.py:57-65                              */
 /* ------------------------------------------------------------------------------------------- */
@@ -125,6 +155,20 @@ int kgat_biagg_backward(const float* g_out, int64_t ld_gout, const float* out, i
                         int32_t n_ctas, float* const* peer_gS, int32_t n_peers, void* stream);
 int kgat_biagg_reduce_param_grads(const float* partials, int32_t n_ctas, int32_t d_in, int32_t d_out, float* gW1,
                                   float* gb1, float* gW2, float* gb2, int32_t accumulate, void* stream);
+
+/* Forward / backward over a needed-row list (frontier section): the kernels process the *n_rows_dev rows listed in
+ * row_ids (max_rows = capacity of the list, sizes the grid); every per-row array (E, S, out, inv_norm, flags,
+ * keep_bits, g_out, g_S, g_E, the dropout stream) stays indexed by NODE id, rows outside the list are not touched. */
+int kgat_biagg_forward_rows(const float* E, const float* S, const int32_t* row_ids, const int32_t* n_rows_dev, int64_t max_rows,
+                            int32_t d_in, int32_t d_out, const float* W1, const float* b1, const float* W2, const float* b2,
+                            float dropout_p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits,
+                            float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, void* stream);
+int kgat_biagg_backward_rows_ctas(int64_t max_rows, int32_t d_in, int32_t d_out);
+int kgat_biagg_backward_rows(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm,
+                             const uint8_t* flags, const float* E, const float* S, const int32_t* row_ids,
+                             const int32_t* n_rows_dev, int64_t max_rows, int32_t d_in, int32_t d_out, const float* W1,
+                             const float* W2, float dropout_p, float* g_S, float* g_E, float* partials, int32_t n_ctas,
+                             void* stream);
 
 /* ------------------------------------------------------------------------------------------- */
 /* K4: BPR loss over the layer tables      reference model.py:189-202, 142-163                   */

@@ -433,11 +433,13 @@ namespace kgat {
 // tensor-core (3xTF32 mma.sync) implementation, biagg_mma.cu
 int biagg_mma_forward(const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* b1, const float* W2,
                       const float* b2, float p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits,
-                      float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, float* const* peer_out, int n_peers, cudaStream_t stream);
+                      float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, float* const* peer_out, int n_peers,
+                      const int32_t* row_ids, const int32_t* n_dev, cudaStream_t stream);
 int biagg_mma_backward_ctas(int64_t n, int d_in, int d_out);
 int biagg_mma_backward(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm, const uint8_t* flags,
                        const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* W2, float p, float* g_S,
-                       float* g_E, float* partials, int n_ctas, float* const* peer_gS, int n_peers, cudaStream_t stream);
+                       float* g_E, float* partials, int n_ctas, float* const* peer_gS, int n_peers, const int32_t* row_ids,
+                       const int32_t* n_dev, cudaStream_t stream);
 // peer.cu: copy n_floats to the same offset behind every peer pointer
 int peer_push_launch(const float* src, float* const* peer_dst, int n_peers, int64_t n_floats, cudaStream_t stream, int max_ctas = 0);
 
@@ -445,7 +447,8 @@ int peer_push_launch(const float* src, float* const* peer_dst, int n_peers, int6
 bool biagg_tc5_supported(int d_in, int d_out);
 int biagg_tc5_forward(const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* b1, const float* W2,
                       const float* b2, float p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits,
-                      float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, float* const* peer_out, int n_peers, cudaStream_t stream);
+                      float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, float* const* peer_out, int n_peers,
+                      const int32_t* row_ids, const int32_t* n_dev, cudaStream_t stream);
 
 // KGAT_BIAGG_IMPL selects the implementation (A/B comparison): "ffma" = the CUDA-core kernels of this file,
 // "mma" = warp-level mma.sync (biagg_mma.cu), "tc5" = tcgen05 forward + mma.sync backward.
@@ -480,19 +483,22 @@ using namespace kgat;
 
 extern "C" {
 
-int kgat_biagg_forward(const float* E, const float* S, int64_t n, int32_t d_in, int32_t d_out, const float* W1, const float* b1,
-                       const float* W2, const float* b2, float dropout_p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev,
-                       const uint32_t* keep_bits, float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, float* const* peer_out,
-                       int32_t n_peers, void* stream) {
+// row_ids / n_dev: optional needed-row list (frontier.cu).  The kernels then run over the *n_dev listed rows (n = the
+// list's capacity, used for the grid); every per-row array stays indexed by node id.
+static int biagg_forward_impl(const float* E, const float* S, int64_t n, int32_t d_in, int32_t d_out, const float* W1, const float* b1,
+                              const float* W2, const float* b2, float dropout_p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev,
+                              const uint32_t* keep_bits, float* out, int64_t ld_out, float* inv_norm, uint8_t* flags,
+                              float* const* peer_out, int32_t n_peers, const int32_t* row_ids, const int32_t* n_dev, void* stream) {
     if (n < 0 || dropout_p < 0.f || dropout_p >= 1.f || (ld_out & 3) || n_peers < 0 || n_peers > KGAT_MAX_PEERS || (n_peers && !peer_out))
         return KGAT_ERR_INVALID_ARGUMENT;
+    if ((row_ids == nullptr) != (n_dev == nullptr)) return KGAT_ERR_INVALID_ARGUMENT;
     if (n == 0) return KGAT_OK;
     if (biagg_impl() == 2 && biagg_tc5_supported(d_in, d_out))
         return biagg_tc5_forward(E, S, n, d_in, d_out, W1, b1, W2, b2, dropout_p, seed, offset, seed_dev, keep_bits, out, ld_out, inv_norm,
-                                 flags, peer_out, n_peers, (cudaStream_t)stream);
-    if (use_mma())
+                                 flags, peer_out, n_peers, row_ids, n_dev, (cudaStream_t)stream);
+    if (use_mma() || row_ids != nullptr)
         return biagg_mma_forward(E, S, n, d_in, d_out, W1, b1, W2, b2, dropout_p, seed, offset, seed_dev, keep_bits, out, ld_out, inv_norm,
-                                 flags, peer_out, n_peers, (cudaStream_t)stream);
+                                 flags, peer_out, n_peers, row_ids, n_dev, (cudaStream_t)stream);
     if (n_peers > 0 && ld_out != d_out) return KGAT_ERR_UNSUPPORTED;
     const int rc = [&]() -> int {
         KGAT_DISPATCH_DIMS(d_in, d_out, return (launch_fwd<DI, DO>(E, S, n, W1, b1, W2, b2, dropout_p, seed, offset, seed_dev, keep_bits, out,
@@ -502,27 +508,67 @@ int kgat_biagg_forward(const float* E, const float* S, int64_t n, int32_t d_in, 
     return peer_push_launch(out, peer_out, n_peers, n * d_out, (cudaStream_t)stream);  // CUDA-core path: unfused push
 }
 
+int kgat_biagg_forward(const float* E, const float* S, int64_t n, int32_t d_in, int32_t d_out, const float* W1, const float* b1,
+                       const float* W2, const float* b2, float dropout_p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev,
+                       const uint32_t* keep_bits, float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, float* const* peer_out,
+                       int32_t n_peers, void* stream) {
+    return biagg_forward_impl(E, S, n, d_in, d_out, W1, b1, W2, b2, dropout_p, seed, offset, seed_dev, keep_bits, out, ld_out, inv_norm,
+                              flags, peer_out, n_peers, nullptr, nullptr, stream);
+}
+
+int kgat_biagg_forward_rows(const float* E, const float* S, const int32_t* row_ids, const int32_t* n_rows_dev, int64_t max_rows, int32_t d_in,
+                            int32_t d_out, const float* W1, const float* b1, const float* W2, const float* b2, float dropout_p,
+                            uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits, float* out, int64_t ld_out,
+                            float* inv_norm, uint8_t* flags, void* stream) {
+    if (!row_ids || !n_rows_dev) return KGAT_ERR_INVALID_ARGUMENT;
+    return biagg_forward_impl(E, S, max_rows, d_in, d_out, W1, b1, W2, b2, dropout_p, seed, offset, seed_dev, keep_bits, out, ld_out,
+                              inv_norm, flags, nullptr, 0, row_ids, n_rows_dev, stream);
+}
+
+int kgat_biagg_backward_rows_ctas(int64_t max_rows, int32_t d_in, int32_t d_out) {
+    if (max_rows <= 0) return 1;
+    return biagg_mma_backward_ctas(max_rows, d_in, d_out);  // the row-list backward always runs the tensor-core kernel
+}
+
 int kgat_biagg_backward_ctas(int64_t n, int32_t d_in, int32_t d_out) {
     if (n <= 0) return 1;
     if (use_mma()) return biagg_mma_backward_ctas(n, d_in, d_out);
     KGAT_DISPATCH_DIMS(d_in, d_out, return (bwd_ctas<DI, DO>(n)));
 }
 
-int kgat_biagg_backward(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm,
-                        const uint8_t* flags, const float* E, const float* S, int64_t n, int32_t d_in, int32_t d_out, const float* W1,
-                        const float* W2, float dropout_p, float* g_S, float* g_E, float* partials, int32_t n_ctas, float* const* peer_gS,
-                        int32_t n_peers, void* stream) {
+static int biagg_backward_impl(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm,
+                               const uint8_t* flags, const float* E, const float* S, int64_t n, int32_t d_in, int32_t d_out, const float* W1,
+                               const float* W2, float dropout_p, float* g_S, float* g_E, float* partials, int32_t n_ctas,
+                               float* const* peer_gS, int32_t n_peers, const int32_t* row_ids, const int32_t* n_dev, void* stream) {
     if (n <= 0 || n_ctas <= 0 || (ld_gout & 3) || (ld_out & 3) || n_peers < 0 || n_peers > KGAT_MAX_PEERS || (n_peers && !peer_gS))
         return KGAT_ERR_INVALID_ARGUMENT;
-    if (use_mma())
+    if ((row_ids == nullptr) != (n_dev == nullptr)) return KGAT_ERR_INVALID_ARGUMENT;
+    if (use_mma() || row_ids != nullptr)
         return biagg_mma_backward(g_out, ld_gout, out, ld_out, inv_norm, flags, E, S, n, d_in, d_out, W1, W2, dropout_p, g_S, g_E, partials,
-                                  n_ctas, peer_gS, n_peers, (cudaStream_t)stream);
+                                  n_ctas, peer_gS, n_peers, row_ids, n_dev, (cudaStream_t)stream);
     const int rc = [&]() -> int {
         KGAT_DISPATCH_DIMS(d_in, d_out, return (launch_bwd<DI, DO>(g_out, ld_gout, out, ld_out, inv_norm, flags, E, S, n, W1, W2, dropout_p,
                                                                    g_S, g_E, partials, n_ctas, (cudaStream_t)stream)));
     }();
     if (rc != KGAT_OK || n_peers == 0) return rc;
     return peer_push_launch(g_S, peer_gS, n_peers, n * d_in, (cudaStream_t)stream);
+}
+
+int kgat_biagg_backward(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm,
+                        const uint8_t* flags, const float* E, const float* S, int64_t n, int32_t d_in, int32_t d_out, const float* W1,
+                        const float* W2, float dropout_p, float* g_S, float* g_E, float* partials, int32_t n_ctas, float* const* peer_gS,
+                        int32_t n_peers, void* stream) {
+    return biagg_backward_impl(g_out, ld_gout, out, ld_out, inv_norm, flags, E, S, n, d_in, d_out, W1, W2, dropout_p, g_S, g_E, partials,
+                               n_ctas, peer_gS, n_peers, nullptr, nullptr, stream);
+}
+
+int kgat_biagg_backward_rows(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm,
+                             const uint8_t* flags, const float* E, const float* S, const int32_t* row_ids, const int32_t* n_rows_dev,
+                             int64_t max_rows, int32_t d_in, int32_t d_out, const float* W1, const float* W2, float dropout_p, float* g_S,
+                             float* g_E, float* partials, int32_t n_ctas, void* stream) {
+    if (!row_ids || !n_rows_dev) return KGAT_ERR_INVALID_ARGUMENT;
+    return biagg_backward_impl(g_out, ld_gout, out, ld_out, inv_norm, flags, E, S, max_rows, d_in, d_out, W1, W2, dropout_p, g_S, g_E,
+                               partials, n_ctas, nullptr, 0, row_ids, n_rows_dev, stream);
 }
 
 int kgat_biagg_reduce_param_grads(const float* partials, int32_t n_ctas, int32_t d_in, int32_t d_out, float* gW1, float* gb1,

@@ -71,8 +71,9 @@ __global__ void __launch_bounds__(256) biagg_fwd_mma_kernel(
     const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2, float dropout_p,
     uint64_t seed, uint64_t offset, const uint64_t* __restrict__ seed_dev, const uint32_t* __restrict__ keep_bits,
     float* __restrict__ out, int64_t ld_out, float* __restrict__ inv_norm, uint8_t* __restrict__ flags,
-    float* const* __restrict__ peer_out, int n_peers) {
+    float* const* __restrict__ peer_out, int n_peers, const int32_t* __restrict__ row_ids, const int32_t* __restrict__ n_dev) {
     using C = FwdCfg<DIN, DOUT>;
+    if (n_dev != nullptr) n = n_dev[0];  // needed-row pruning: run over the listed rows, arrays stay node-indexed
     static_assert(DOUT <= DIN, "the output tile is staged in the E+S tile for the peer stores");
     extern __shared__ __align__(16) float smem[];
     if (seed_dev != nullptr) seed += seed_dev[0] * 0x9E3779B97F4A7C15ull;
@@ -115,8 +116,9 @@ __global__ void __launch_bounds__(256) biagg_fwd_mma_kernel(
             const int r = i / (DIN / 4), q = i % (DIN / 4);
             float4 e = make_float4(0.f, 0.f, 0.f, 0.f), s = e;
             if (row0 + r < n) {
-                e = ld_stream4(E + (row0 + r) * DIN + q * 4);
-                s = ld_stream4(S + (row0 + r) * DIN + q * 4);
+                const int64_t node = row_ids != nullptr ? (int64_t)__ldg(row_ids + row0 + r) : row0 + r;
+                e = ld_stream4(E + node * DIN + q * 4);
+                s = ld_stream4(S + node * DIN + q * 4);
             }
             *reinterpret_cast<float4*>(Us + r * C::SE + q * 4) = make_float4(e.x + s.x, e.y + s.y, e.z + s.z, e.w + s.w);
             *reinterpret_cast<float4*>(Vs + r * C::SE + q * 4) = make_float4(e.x * s.x, e.y * s.y, e.z * s.z, e.w * s.w);
@@ -182,8 +184,9 @@ __global__ void __launch_bounds__(256) biagg_fwd_mma_kernel(
         float ss[2] = {0.f, 0.f};
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int64_t row = row0 + mt * 16 + g + 8 * h;
-            const bool valid = row < n;
+            const int64_t idx = row0 + mt * 16 + g + 8 * h;
+            const bool valid = idx < n;
+            const int64_t row = (valid && row_ids != nullptr) ? (int64_t)__ldg(row_ids + idx) : idx;
             uint32_t rnd[(C::NTW * 2 + 7) / 8 * 4];
             if (dropout_p > 0.f && keep_bits == nullptr && valid) {
 #pragma unroll
@@ -232,8 +235,9 @@ __global__ void __launch_bounds__(256) biagg_fwd_mma_kernel(
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int64_t row = row0 + mt * 16 + g + 8 * h;
-            if (row >= n) continue;
+            const int64_t idx = row0 + mt * 16 + g + 8 * h;
+            if (idx >= n) continue;
+            const int64_t row = row_ids != nullptr ? (int64_t)__ldg(row_ids + idx) : idx;
             const float nrm = sqrtf(ss[h]);
             const float denom = fmaxf(nrm, KGAT_NORM_EPS);
             const float rinv = 1.f / denom;  // one IEEE division per row; x * rinv is within 1 ulp of x / denom
@@ -255,8 +259,9 @@ __global__ void __launch_bounds__(256) biagg_fwd_mma_kernel(
             for (int i = tid; i < C::TM * (DOUT / 4); i += C::NT) {
                 const int r = i / (DOUT / 4), q4 = i % (DOUT / 4);
                 if (row0 + r < n) {
+                    const int64_t node = row_ids != nullptr ? (int64_t)__ldg(row_ids + row0 + r) : row0 + r;
                     const float4 v = *reinterpret_cast<const float4*>(Us + r * C::SE + q4 * 4);
-                    for (int q = 0; q < n_peers; ++q) *reinterpret_cast<float4*>(peer_out[q] + (row0 + r) * ld_out + q4 * 4) = v;
+                    for (int q = 0; q < n_peers; ++q) *reinterpret_cast<float4*>(peer_out[q] + node * ld_out + q4 * 4) = v;
                 }
             }
         }
@@ -297,8 +302,10 @@ __global__ void __launch_bounds__(BwdCfg<DIN, DOUT>::NT) biagg_bwd_mma_kernel(
     const float* __restrict__ g_out, int64_t ld_gout, const float* __restrict__ out, int64_t ld_out,
     const float* __restrict__ inv_norm, const uint8_t* __restrict__ flags, const float* __restrict__ E,
     const float* __restrict__ S, int64_t n, const float* __restrict__ W1, const float* __restrict__ W2, float dropout_p,
-    float* __restrict__ g_S, float* __restrict__ g_E, float* __restrict__ partials, float* const* __restrict__ peer_gS, int n_peers) {
+    float* __restrict__ g_S, float* __restrict__ g_E, float* __restrict__ partials, float* const* __restrict__ peer_gS, int n_peers,
+    const int32_t* __restrict__ row_ids, const int32_t* __restrict__ n_dev) {
     using C = BwdCfg<DIN, DOUT>;
+    if (n_dev != nullptr) n = n_dev[0];  // needed-row pruning: run over the listed rows, arrays stay node-indexed
     extern __shared__ __align__(16) float smem[];
     float* W1s = smem;                    // [DOUT][SW]
     float* W2s = W1s + DOUT * C::SW;
@@ -331,8 +338,9 @@ __global__ void __launch_bounds__(BwdCfg<DIN, DOUT>::NT) biagg_bwd_mma_kernel(
             const int r = i / (DIN / 4), q = i % (DIN / 4);
             float4 e = make_float4(0.f, 0.f, 0.f, 0.f), s = e;
             if (row0 + r < n) {
-                e = ld_stream4(E + (row0 + r) * DIN + q * 4);
-                s = ld_stream4(S + (row0 + r) * DIN + q * 4);
+                const int64_t node = row_ids != nullptr ? (int64_t)__ldg(row_ids + row0 + r) : row0 + r;
+                e = ld_stream4(E + node * DIN + q * 4);
+                s = ld_stream4(S + node * DIN + q * 4);
             }
             *reinterpret_cast<float4*>(Es + r * C::SE + q * 4) = e;
             *reinterpret_cast<float4*>(Ss + r * C::SE + q * 4) = s;
@@ -342,12 +350,12 @@ __global__ void __launch_bounds__(BwdCfg<DIN, DOUT>::NT) biagg_bwd_mma_kernel(
 #pragma unroll
         for (int i = 0; i < C::RM; ++i) {
             const int r = rg * C::RM + i;
-            const int64_t row = row0 + r;
             const bool in_tile = r < C::TM;
             float4 gg = make_float4(0.f, 0.f, 0.f, 0.f), y = gg;
             uchar4 f = make_uchar4(0, 0, 0, 0);
             float inv = 0.f;
-            if (in_tile && row < n) {
+            if (in_tile && row0 + r < n) {
+                const int64_t row = row_ids != nullptr ? (int64_t)__ldg(row_ids + row0 + r) : row0 + r;
                 gg = ld_stream4(g_out + row * ld_gout + cg * 4);
                 y = ld_stream4(out + row * ld_out + cg * 4);
                 f = *reinterpret_cast<const uchar4*>(flags + row * DOUT + cg * 4);
@@ -428,8 +436,8 @@ __global__ void __launch_bounds__(BwdCfg<DIN, DOUT>::NT) biagg_bwd_mma_kernel(
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int r = mt * 16 + g + 8 * h;
-                    const int64_t row = row0 + r;
-                    if (row < n) {
+                    if (row0 + r < n) {
+                        const int64_t row = row_ids != nullptr ? (int64_t)__ldg(row_ids + row0 + r) : row0 + r;
                         const int k = nt * 8 + 2 * t;
                         const float2 e = *reinterpret_cast<const float2*>(Es + r * C::SE + k);
                         const float2 s2 = *reinterpret_cast<const float2*>(Ss + r * C::SE + k);
@@ -526,7 +534,8 @@ inline int grid_for(int64_t n, int tm, size_t smem_bytes) {
 template <int DIN, int DOUT>
 int launch_fwd(const float* E, const float* S, int64_t n, const float* W1, const float* b1, const float* W2, const float* b2,
                float p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits, float* out, int64_t ld_out,
-               float* inv_norm, uint8_t* flags, float* const* peer_out, int n_peers, cudaStream_t stream) {
+               float* inv_norm, uint8_t* flags, float* const* peer_out, int n_peers, const int32_t* row_ids, const int32_t* n_dev,
+               cudaStream_t stream) {
     using C = FwdCfg<DIN, DOUT>;
     static bool configured = false;
     if (!configured) {
@@ -535,14 +544,15 @@ int launch_fwd(const float* E, const float* S, int64_t n, const float* W1, const
     }
     biagg_fwd_mma_kernel<DIN, DOUT><<<grid_for(n, C::TM, C::smem), C::NT, C::smem, stream>>>(E, S, n, W1, b1, W2, b2, p, seed, offset, seed_dev,
                                                                                          keep_bits, out, ld_out, inv_norm, flags, peer_out,
-                                                                                         n_peers);
+                                                                                         n_peers, row_ids, n_dev);
     return check_launch();
 }
 
 template <int DIN, int DOUT>
 int launch_bwd(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm, const uint8_t* flags,
                const float* E, const float* S, int64_t n, const float* W1, const float* W2, float p, float* g_S, float* g_E,
-               float* partials, int n_ctas, float* const* peer_gS, int n_peers, cudaStream_t stream) {
+               float* partials, int n_ctas, float* const* peer_gS, int n_peers, const int32_t* row_ids, const int32_t* n_dev,
+               cudaStream_t stream) {
     using C = BwdCfg<DIN, DOUT>;
     static bool configured = false;
     if (!configured) {
@@ -550,7 +560,7 @@ int launch_bwd(const float* g_out, int64_t ld_gout, const float* out, int64_t ld
         configured = true;
     }
     biagg_bwd_mma_kernel<DIN, DOUT><<<n_ctas, C::NT, C::smem, stream>>>(g_out, ld_gout, out, ld_out, inv_norm, flags, E, S, n, W1, W2, p, g_S,
-                                                                    g_E, partials, peer_gS, n_peers);
+                                                                    g_E, partials, peer_gS, n_peers, row_ids, n_dev);
     return check_launch();
 }
 
@@ -574,9 +584,10 @@ int launch_bwd(const float* g_out, int64_t ld_gout, const float* out, int64_t ld
 
 int biagg_mma_forward(const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* b1, const float* W2,
                       const float* b2, float p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits,
-                      float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, float* const* peer_out, int n_peers, cudaStream_t stream) {
+                      float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, float* const* peer_out, int n_peers,
+                      const int32_t* row_ids, const int32_t* n_dev, cudaStream_t stream) {
     KGAT_MMA_DISPATCH(d_in, d_out, return (mma::launch_fwd<DI, DO>(E, S, n, W1, b1, W2, b2, p, seed, offset, seed_dev, keep_bits, out, ld_out,
-                                                                   inv_norm, flags, peer_out, n_peers, stream)));
+                                                                   inv_norm, flags, peer_out, n_peers, row_ids, n_dev, stream)));
 }
 
 int biagg_mma_backward_ctas(int64_t n, int d_in, int d_out) {
@@ -585,9 +596,10 @@ int biagg_mma_backward_ctas(int64_t n, int d_in, int d_out) {
 
 int biagg_mma_backward(const float* g_out, int64_t ld_gout, const float* out, int64_t ld_out, const float* inv_norm, const uint8_t* flags,
                        const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* W2, float p, float* g_S,
-                       float* g_E, float* partials, int n_ctas, float* const* peer_gS, int n_peers, cudaStream_t stream) {
+                       float* g_E, float* partials, int n_ctas, float* const* peer_gS, int n_peers, const int32_t* row_ids,
+                       const int32_t* n_dev, cudaStream_t stream) {
     KGAT_MMA_DISPATCH(d_in, d_out, return (mma::launch_bwd<DI, DO>(g_out, ld_gout, out, ld_out, inv_norm, flags, E, S, n, W1, W2, p, g_S, g_E,
-                                                                   partials, n_ctas, peer_gS, n_peers, stream)));
+                                                                   partials, n_ctas, peer_gS, n_peers, row_ids, n_dev, stream)));
 }
 
 }  // namespace kgat

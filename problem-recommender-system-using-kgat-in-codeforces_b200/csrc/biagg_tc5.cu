@@ -105,8 +105,12 @@ __global__ void __launch_bounds__(Cfg<DIN, DOUT>::NT, 1) biagg_fwd_tc5_kernel(
     const float* __restrict__ E, const float* __restrict__ S, int64_t n, const float* __restrict__ W1, const float* __restrict__ b1,
     const float* __restrict__ W2, const float* __restrict__ b2, float dropout_p, uint64_t seed, uint64_t offset,
     const uint64_t* __restrict__ seed_dev, const uint32_t* __restrict__ keep_bits, float* __restrict__ out, int64_t ld_out,
-    float* __restrict__ inv_norm, uint8_t* __restrict__ flags, float* const* __restrict__ peer_out, int n_peers) {
+    float* __restrict__ inv_norm, uint8_t* __restrict__ flags, float* const* __restrict__ peer_out, int n_peers,
+    const int32_t* __restrict__ row_ids, const int32_t* __restrict__ n_dev) {
+    // row_ids / n_dev (needed-row pruning, frontier.cu): the kernel runs over the *n_dev listed rows; every per-row
+    // array (E, S, out, inv_norm, flags, keep_bits, the dropout stream) is still indexed by the node id row_ids[i]
     using C = Cfg<DIN, DOUT>;
+    if (n_dev != nullptr) n = n_dev[0];
     extern __shared__ __align__(128) float smem[];
     float* At = smem;                          // [4][A_TILE]: U hi, U lo, V hi, V lo
     float* Wt = At + 4 * C::A_TILE;            // [4][W_TILE]: W1 hi, W1 lo, W2 hi, W2 lo
@@ -170,8 +174,9 @@ __global__ void __launch_bounds__(Cfg<DIN, DOUT>::NT, 1) biagg_fwd_tc5_kernel(
             const int r = (i / (8 * C::KC)) * 8 + (i & 7), q = (i >> 3) % C::KC;
             pe[it] = ps[it] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (tile < n_tiles && row0 + r < n) {
-                pe[it] = ld_stream4(E + (row0 + r) * DIN + q * 4);
-                ps[it] = ld_stream4(S + (row0 + r) * DIN + q * 4);
+                const int64_t node = row_ids != nullptr ? (int64_t)__ldg(row_ids + row0 + r) : row0 + r;
+                pe[it] = ld_stream4(E + node * DIN + q * 4);
+                ps[it] = ld_stream4(S + node * DIN + q * 4);
             }
         }
     };
@@ -252,8 +257,8 @@ __global__ void __launch_bounds__(Cfg<DIN, DOUT>::NT, 1) biagg_fwd_tc5_kernel(
         }
 
         // ---- epilogue: this thread's row, columns [half * CH, half * CH + CH)
-        const int64_t row = row0 + r_tile;
-        const bool valid = row < n;
+        const bool valid = row0 + r_tile < n;
+        const int64_t row = (valid && row_ids != nullptr) ? (int64_t)__ldg(row_ids + row0 + r_tile) : row0 + r_tile;
         uint32_t z1[C::CH], z2[C::CH];
         const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + buf * 2 * DOUT + half * C::CH;
 #pragma unroll
@@ -323,7 +328,8 @@ __global__ void __launch_bounds__(Cfg<DIN, DOUT>::NT, 1) biagg_fwd_tc5_kernel(
 template <int DIN, int DOUT>
 int launch_fwd(const float* E, const float* S, int64_t n, const float* W1, const float* b1, const float* W2, const float* b2, float p,
                uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits, float* out, int64_t ld_out,
-               float* inv_norm, uint8_t* flags, float* const* peer_out, int n_peers, cudaStream_t stream) {
+               float* inv_norm, uint8_t* flags, float* const* peer_out, int n_peers, const int32_t* row_ids, const int32_t* n_dev,
+               cudaStream_t stream) {
     using C = Cfg<DIN, DOUT>;
     static bool configured = false;
     if (!configured) {
@@ -333,7 +339,7 @@ int launch_fwd(const float* E, const float* S, int64_t n, const float* W1, const
     const int64_t tiles = (n + C::TM - 1) / C::TM;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
     biagg_fwd_tc5_kernel<DIN, DOUT><<<grid, C::NT, C::smem, stream>>>(E, S, n, W1, b1, W2, b2, p, seed, offset, seed_dev, keep_bits, out,
-                                                                   ld_out, inv_norm, flags, peer_out, n_peers);
+                                                                   ld_out, inv_norm, flags, peer_out, n_peers, row_ids, n_dev);
     return check_launch();
 }
 
@@ -346,11 +352,12 @@ bool biagg_tc5_supported(int d_in, int d_out) {
 
 int biagg_tc5_forward(const float* E, const float* S, int64_t n, int d_in, int d_out, const float* W1, const float* b1, const float* W2,
                       const float* b2, float p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const uint32_t* keep_bits,
-                      float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, float* const* peer_out, int n_peers, cudaStream_t stream) {
+                      float* out, int64_t ld_out, float* inv_norm, uint8_t* flags, float* const* peer_out, int n_peers,
+                      const int32_t* row_ids, const int32_t* n_dev, cudaStream_t stream) {
 #define KGAT_TC5_CASE(DI, DO)                                                                                                          \
     if (d_in == DI && d_out == DO)                                                                                                     \
         return tc5::launch_fwd<DI, DO>(E, S, n, W1, b1, W2, b2, p, seed, offset, seed_dev, keep_bits, out, ld_out, inv_norm, flags,     \
-                                       peer_out, n_peers, stream);
+                                       peer_out, n_peers, row_ids, n_dev, stream);
     KGAT_TC5_CASE(64, 64)
     KGAT_TC5_CASE(64, 32)
     KGAT_TC5_CASE(64, 16)

@@ -1,0 +1,176 @@
+// Needed-row frontier of a TRAIN_CF step (exact pruning of the propagation, reference model.py:165-202).
+//
+// The BPR loss gathers only the <= 3B batch rows of the propagated tables (model.py:189-191), so a row of layer l
+// matters only if it is a batch row or a graph neighbour (through layers l+1 .. L) of one:
+//     F_L = {batch ids},   F_{l-1} = F_l  U  cols(A[F_l, :])          (aggregator.py:54 reads E_{l-1}[c] for A[r, c] != 0)
+// Everything outside F_l has an exactly-zero gradient and is never read, so layer l is computed (forward and
+// backward) for the rows of F_l only -- same loss, same gradients as the reference's full propagation.
+// A frontier level is a bitmap over the nodes (one bit per node, tested by the masked SpMM, spmm.cu) plus the
+// ascending list of its rows (enumerated by the bi-interaction kernels).  All of it is stream-ordered device
+// work with device-side counts, so a whole step still replays as one CUDA graph.
+#include "common.cuh"
+
+namespace kgat {
+namespace {
+
+constexpr int kListBlock = 256;  // bitmap words per CTA of the listing kernels (one word per thread)
+
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// bitmap |= {ids}; ids outside [0, n_nodes) are counted in *bad and skipped (the reference raises an IndexError)
+__global__ void frontier_mark_kernel(const int64_t* __restrict__ ids, int64_t n_ids, int64_t n_nodes, uint32_t* __restrict__ bitmap,
+                                     int32_t* __restrict__ bad) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_ids) return;
+    const int64_t id = ids[i];
+    if (id < 0 || id >= n_nodes) {
+        if (bad != nullptr) atomicAdd(bad, 1);
+        return;
+    }
+    atomicOr(bitmap + (id >> 5), 1u << (id & 31));
+}
+
+// out |= {r} U cols(A[r, :]) for every listed row r (one warp per row, persistent grid, device-side count)
+__global__ void __launch_bounds__(128) frontier_expand_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                                                              const int32_t* __restrict__ rows, const int32_t* __restrict__ cnt_dev,
+                                                              uint32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int cnt = cnt_dev[0];
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < cnt; i += n_warps) {
+        const int r = rows[i];
+        if (lane == 0) {
+            const uint32_t bit = 1u << (r & 31);
+            if (!(out[r >> 5] & bit)) atomicOr(out + (r >> 5), bit);
+        }
+        const int b = row_ptr[r], e = row_ptr[r + 1];
+        for (int k = b + lane; k < e; k += 32) {
+            const int c = __ldg(col_idx + k);
+            const uint32_t bit = 1u << (c & 31);
+            // test before set: hub columns are hit thousands of times, one atomic is enough
+            if (!(__ldcg(out + (c >> 5)) & bit)) atomicOr(out + (c >> 5), bit);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kListBlock) frontier_count_kernel(const uint32_t* __restrict__ bitmap, int64_t n_words,
+                                                                   int32_t* __restrict__ block_total) {
+    __shared__ int sh[kListBlock / 32];
+    const int64_t w = blockIdx.x * (int64_t)kListBlock + threadIdx.x;
+    int c = w < n_words ? __popc(bitmap[w]) : 0;
+    c = warp_sum_i(c);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < kListBlock / 32; ++i) t += sh[i];
+        block_total[blockIdx.x] = t;
+    }
+}
+
+// rows[...] = ascending node ids of the set bits; *cnt = their number
+__global__ void __launch_bounds__(kListBlock) frontier_write_kernel(const uint32_t* __restrict__ bitmap, int64_t n_words,
+                                                                   const int32_t* __restrict__ block_total, int32_t* __restrict__ rows,
+                                                                   int32_t* __restrict__ cnt) {
+    __shared__ int sh[kListBlock / 32];
+    __shared__ int sh_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // rows of all earlier blocks
+    int part = 0;
+    for (int j = tid; j < (int)blockIdx.x; j += kListBlock) part += block_total[j];
+    part = warp_sum_i(part);
+    if (lane == 0) sh[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int i = 0; i < kListBlock / 32; ++i) t += sh[i];
+        sh_base = t;
+    }
+    __syncthreads();
+    const int base = sh_base;
+    __syncthreads();
+    const int64_t w = blockIdx.x * (int64_t)kListBlock + tid;
+    uint32_t bits = w < n_words ? bitmap[w] : 0u;
+    const int c = __popc(bits);
+    int incl = c;  // inclusive scan inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) sh[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int i = 0; i < warp; ++i) woff += sh[i];
+    int pos = base + woff + incl - c;
+    while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        rows[pos++] = (int)(w * 32 + b);
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == kListBlock - 1) cnt[0] = pos;  // the last thread ends at the grand total
+}
+
+// T[rows[i], :] = 0 for i < *cnt  (the gradient rows of the last table, before the BPR scatter)
+__global__ void frontier_zero_rows_kernel(float* __restrict__ T, int64_t ld, int d4, const int32_t* __restrict__ rows,
+                                          const int32_t* __restrict__ cnt_dev) {
+    const int cnt = cnt_dev[0];
+    const int64_t total = (int64_t)cnt * d4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = rows[i / d4];
+        reinterpret_cast<float4*>(T + (int64_t)r * ld)[i % d4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+}  // namespace
+}  // namespace kgat
+
+using namespace kgat;
+
+extern "C" {
+
+int64_t kgat_frontier_scratch_ints(int64_t n_nodes) {
+    const int64_t n_words = (n_nodes + 31) / 32;
+    return (n_words + kListBlock - 1) / kListBlock + 1;
+}
+
+int kgat_frontier_mark_ids(const int64_t* ids64, int64_t n_ids, int64_t n_nodes, uint32_t* bitmap, int32_t* bad_count_dev, void* stream) {
+    if (n_ids < 0 || n_nodes <= 0 || !bitmap) return KGAT_ERR_INVALID_ARGUMENT;
+    if (n_ids == 0) return KGAT_OK;
+    frontier_mark_kernel<<<(unsigned)((n_ids + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ids64, n_ids, n_nodes, bitmap, bad_count_dev);
+    return check_launch();
+}
+
+int kgat_frontier_expand(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* rows, const int32_t* count_dev, int64_t max_rows,
+                         uint32_t* bitmap_out, void* stream) {
+    if (!row_ptr || !col_idx || !rows || !count_dev || !bitmap_out || max_rows <= 0) return KGAT_ERR_INVALID_ARGUMENT;
+    int64_t ctas = (max_rows + 3) / 4;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (ctas > cap) ctas = cap;
+    frontier_expand_kernel<<<(unsigned)ctas, 128, 0, (cudaStream_t)stream>>>(row_ptr, col_idx, rows, count_dev, bitmap_out);
+    return check_launch();
+}
+
+int kgat_frontier_list(const uint32_t* bitmap, int64_t n_nodes, int32_t* scratch, int32_t* rows, int32_t* count_dev, void* stream) {
+    if (!bitmap || !scratch || !rows || !count_dev || n_nodes <= 0 || n_nodes >= ((int64_t)1 << 31)) return KGAT_ERR_INVALID_ARGUMENT;
+    const int64_t n_words = (n_nodes + 31) / 32;
+    const unsigned blocks = (unsigned)((n_words + kListBlock - 1) / kListBlock);
+    frontier_count_kernel<<<blocks, kListBlock, 0, (cudaStream_t)stream>>>(bitmap, n_words, scratch);
+    frontier_write_kernel<<<blocks, kListBlock, 0, (cudaStream_t)stream>>>(bitmap, n_words, scratch, rows, count_dev);
+    return check_launch();
+}
+
+int kgat_frontier_zero_rows(float* T, int64_t ld, int32_t d, const int32_t* rows, const int32_t* count_dev, int64_t max_rows, void* stream) {
+    if (!T || !rows || !count_dev || d <= 0 || (d & 3) || (ld & 3) || max_rows <= 0) return KGAT_ERR_INVALID_ARGUMENT;
+    int64_t ctas = (max_rows * (d / 4) + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 4;
+    if (ctas > cap) ctas = cap;
+    frontier_zero_rows_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(T, ld, d / 4, rows, count_dev);
+    return check_launch();
+}
+
+}  // extern "C"

@@ -62,12 +62,17 @@ __device__ __forceinline__ void finish_heavy_row(int slot, float* __restrict__ p
 // per edge group is: LDS.64 (broadcast), LDG.128 (gather of the neighbour row), 4 FFMA -- no
 // shuffles, no predicates (tail lanes carry weight 0 and a valid, already-cached address).
 // WIDE = false: the table is < 4 GiB so a 32-bit byte offset addresses it.
-template <int D, int U, bool WIDE>
+// MASKED (needed-row pruning of a CF step, frontier.cu): `row_mask` (bitmap over output rows, NULL = all) skips the
+// tasks of rows nobody reads; `edge_mask` (bitmap over columns, NULL = all) drops the edges whose source row holds
+// no valid data (the surviving edges are compacted in the staging slab, so the hot loop is unchanged) and gates the
+// addend Z the same way (Z[row] counts only when row is in `edge_mask`).
+template <int D, int U, bool WIDE, bool MASKED>
 __global__ void __launch_bounds__(128) spmm_task_kernel(const int4* __restrict__ tasks, int64_t n_tasks,
                                                         const int32_t* __restrict__ col_idx, const float* __restrict__ vals,
                                                         const float* __restrict__ X, int64_t ldx, float* __restrict__ Y,
                                                         int64_t ldy, const float* __restrict__ Z, int64_t ldz,
-                                                        float* __restrict__ partials, int4* __restrict__ heavy, int n_heavy) {
+                                                        float* __restrict__ partials, int4* __restrict__ heavy, int n_heavy,
+                                                        const uint32_t* __restrict__ row_mask, const uint32_t* __restrict__ edge_mask) {
     constexpr int LPE = D / 4;        // lanes per edge
     constexpr int EPW = 32 / LPE;     // edges per warp step
     constexpr int EPI = EPW * U;      // edges per unrolled iteration (divides 32)
@@ -78,6 +83,8 @@ __global__ void __launch_bounds__(128) spmm_task_kernel(const int4* __restrict__
     const int64_t task_id = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (task_id >= n_tasks) return;
     const int4 t = __ldg(tasks + task_id);  // {row, begin, end, partial_slot}
+    if (MASKED && row_mask != nullptr && !((__ldg(row_mask + (t.x >> 5)) >> (t.x & 31)) & 1u)) return;
+    if (MASKED && Z != nullptr && edge_mask != nullptr && !((__ldg(edge_mask + (t.x >> 5)) >> (t.x & 31)) & 1u)) Z = nullptr;
     const int sub = lane % LPE;
     const int slot = lane / LPE;
     const char* xb = reinterpret_cast<const char*>(X) + sub * 16;
@@ -95,9 +102,25 @@ __global__ void __launch_bounds__(128) spmm_task_kernel(const int4* __restrict__
         v = k < t.z ? ld_stream_f32(vals + k) : 0.f;
     }
     while (base < t.z) {
-        eb[lane] = make_int2(WIDE ? c : (int)((uint32_t)c * row_bytes32), __float_as_int(v));
+        int cnt;
+        if (MASKED && edge_mask != nullptr) {
+            // keep the edges whose source row is live, packed to the front of the slab; pad to a whole unrolled step
+            // (padding entries carry weight 0 and the address of a LIVE row: dead rows may hold NaN garbage)
+            const bool live = (base + lane < t.z) && ((__ldg(edge_mask + (c >> 5)) >> (c & 31)) & 1u);
+            const unsigned m = __ballot_sync(kFull, live);
+            cnt = __popc(m);
+            const int off = WIDE ? c : (int)((uint32_t)c * row_bytes32);
+            if (live) eb[__popc(m & ((1u << lane) - 1u))] = make_int2(off, __float_as_int(v));
+            if (cnt > 0) {
+                const int live_off = __shfl_sync(kFull, off, __ffs(m) - 1);
+                const int pad = (EPI - (cnt % EPI)) % EPI;
+                if (lane < pad) eb[cnt + lane] = make_int2(live_off, 0);
+            }
+        } else {
+            eb[lane] = make_int2(WIDE ? c : (int)((uint32_t)c * row_bytes32), __float_as_int(v));
+            cnt = min(32, t.z - base);
+        }
         __syncwarp();
-        const int cnt = min(32, t.z - base);
         base += 32;
         if (base < t.z) {  // prefetch the next 32 (col, val) pairs while this batch is gathered
             const int k = base + lane;
@@ -215,9 +238,9 @@ __global__ void __launch_bounds__(128) spmm_heavy_reduce_kernel(const int4* __re
 
 using namespace kgat;
 
-extern "C" int kgat_spmm_csr(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_rows, int64_t n_heavy,
-                             const int32_t* col_idx, const float* vals, const float* X, int64_t n_cols, int64_t ldx, float* Y, int64_t ldy,
-                             const float* Z, int64_t ldz, int32_t d, float* partials, void* stream_) {
+static int spmm_launch(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_rows, int64_t n_heavy, const int32_t* col_idx,
+                       const float* vals, const float* X, int64_t n_cols, int64_t ldx, float* Y, int64_t ldy, const float* Z, int64_t ldz,
+                       int32_t d, float* partials, const uint32_t* row_mask, const uint32_t* edge_mask, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_tasks < 0 || n_heavy < 0 || d <= 0 || (d & 3) || d > 256) return KGAT_ERR_INVALID_ARGUMENT;
     if ((ldx & 3) || (ldy & 3) || (Z && (ldz & 3))) return KGAT_ERR_INVALID_ARGUMENT;
@@ -225,16 +248,23 @@ extern "C" int kgat_spmm_csr(const int32_t* tasks, int64_t n_tasks, int32_t* hea
     if (n_tasks == 0) return KGAT_OK;
     if (n_cols <= 0) return KGAT_ERR_INVALID_ARGUMENT;
     const bool use_wide = n_cols * ldx * 4 >= ((int64_t)1 << 32);  // 32-bit byte offsets cover tables < 4 GiB
+    const bool masked = row_mask != nullptr || edge_mask != nullptr;
     const int threads = 128;
     const unsigned blocks = (unsigned)((n_tasks * 32 + threads - 1) / threads);
     const int4* t4 = reinterpret_cast<const int4*>(tasks);
     int4* h4 = reinterpret_cast<int4*>(heavy_rows);
     bool fused_reduce = false;  // the templated kernels reduce heavy rows themselves (last chunk to arrive)
-#define KGAT_SPMM_LAUNCH(DD, UU)                                                                                              \
-    do {                                                                                                                      \
-        if (use_wide) spmm_task_kernel<DD, UU, true><<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, h4, (int)n_heavy); \
-        else spmm_task_kernel<DD, UU, false><<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, h4, (int)n_heavy);        \
-        fused_reduce = true;                                                                                                  \
+#define KGAT_SPMM_ARGS t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, h4, (int)n_heavy, row_mask, edge_mask
+#define KGAT_SPMM_LAUNCH(DD, UU)                                                                                       \
+    do {                                                                                                               \
+        if (masked) {                                                                                                  \
+            if (use_wide) spmm_task_kernel<DD, UU, true, true><<<blocks, threads, 0, stream>>>(KGAT_SPMM_ARGS);        \
+            else spmm_task_kernel<DD, UU, false, true><<<blocks, threads, 0, stream>>>(KGAT_SPMM_ARGS);                \
+        } else {                                                                                                       \
+            if (use_wide) spmm_task_kernel<DD, UU, true, false><<<blocks, threads, 0, stream>>>(KGAT_SPMM_ARGS);       \
+            else spmm_task_kernel<DD, UU, false, false><<<blocks, threads, 0, stream>>>(KGAT_SPMM_ARGS);               \
+        }                                                                                                              \
+        fused_reduce = true;                                                                                           \
     } while (0)
     switch (d) {
         case 16: KGAT_SPMM_LAUNCH(16, 2); break;
@@ -242,13 +272,30 @@ extern "C" int kgat_spmm_csr(const int32_t* tasks, int64_t n_tasks, int32_t* hea
         case 64: KGAT_SPMM_LAUNCH(64, 4); break;
         case 128: KGAT_SPMM_LAUNCH(128, 4); break;
         default:
+            if (masked) return KGAT_ERR_UNSUPPORTED;
             spmm_task_kernel_generic<<<blocks, threads, 0, stream>>>(t4, n_tasks, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, d);
     }
 #undef KGAT_SPMM_LAUNCH
+#undef KGAT_SPMM_ARGS
     if (n_heavy > 0 && !fused_reduce) {
         const unsigned hb = (unsigned)((n_heavy * 32 + threads - 1) / threads);
         spmm_heavy_reduce_kernel<<<hb, threads, 0, stream>>>(reinterpret_cast<const int4*>(heavy_rows), n_heavy, partials, Y, ldy, Z,
                                                              ldz, d);
     }
     return check_launch();
+}
+
+extern "C" int kgat_spmm_csr(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_rows, int64_t n_heavy,
+                             const int32_t* col_idx, const float* vals, const float* X, int64_t n_cols, int64_t ldx, float* Y, int64_t ldy,
+                             const float* Z, int64_t ldz, int32_t d, float* partials, void* stream_) {
+    return spmm_launch(tasks, n_tasks, heavy_rows, n_heavy, col_idx, vals, X, n_cols, ldx, Y, ldy, Z, ldz, d, partials, nullptr, nullptr,
+                       stream_);
+}
+
+extern "C" int kgat_spmm_csr_masked(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_rows, int64_t n_heavy,
+                                    const int32_t* col_idx, const float* vals, const float* X, int64_t n_cols, int64_t ldx, float* Y,
+                                    int64_t ldy, const float* Z, int64_t ldz, int32_t d, float* partials, const uint32_t* row_mask,
+                                    const uint32_t* edge_mask, void* stream_) {
+    return spmm_launch(tasks, n_tasks, heavy_rows, n_heavy, col_idx, vals, X, n_cols, ldx, Y, ldy, Z, ldz, d, partials, row_mask, edge_mask,
+                       stream_);
 }

@@ -16,7 +16,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib, ops
-from .functions import DropoutSpec, propagate_backward, propagate_forward
+from .functions import DropoutSpec, last_table_grad, propagate_backward, propagate_forward
 from .model import KGAT, KGATMode
 from .optim import FusedAdam
 from .trainer import CF_BATCH, KG_BATCH, EpochData
@@ -123,7 +123,11 @@ class TrainEngine:
         drop = m._drop_spec()
         if m.training and drop.keep_bits is None and any(q > 0 for q in drop.ps):
             drop = DropoutSpec(ps=drop.ps, seed=drop.seed, seed_dev=self.cf_adam.step_dev)
-        st = propagate_forward(graph, m._user_entity_embedding.weight.detach(), layers, drop, save=True)
+        frontier = m._frontier(graph, 3 * self.cf_batch)
+        self.frontier = frontier
+        if frontier is not None:
+            frontier.build([self.cf_ids.view(-1)])
+        st = propagate_forward(graph, m._user_entity_embedding.weight.detach(), layers, drop, save=True, frontier=frontier)
         reg = float(m._regularization_params[0])
         ops.bpr_forward(st.tables, u, p, n, reg, self.cf_loss, self.cf_scratch)
         n_tab = len(st.tables)
@@ -133,9 +137,9 @@ class TrainEngine:
             grads[l] = buf
             ops.bpr_backward(st.tables, grads, u, p, n, reg, self.cf_scratch, self.one)
 
-        g_last = torch.zeros_like(st.tables[-1])
+        g_last = last_table_grad(st, frontier)
         inject(n_tab - 1, g_last)
-        g_e0, pgrads = propagate_backward(graph, st, layers, g_last, inject)
+        g_e0, pgrads = propagate_backward(graph, st, layers, g_last, inject, frontier=frontier)
         self.cf_adam.apply([g_e0] + [t for grp in pgrads for t in grp])
         self.cf_loss_sum.add_(self.cf_loss)
 
@@ -197,7 +201,8 @@ class TrainEngine:
     # ------------------------------------------------------------------------------------------
     def _token(self):
         g = self.model._graph()
-        return (id(g), g.vals.data_ptr(), g.t_vals.data_ptr(), self.model.training, id(self._resident), id(self.device_sampler))
+        return (id(g), g.vals.data_ptr(), g.t_vals.data_ptr(), self.model.training, id(self._resident), id(self.device_sampler),
+                self.model.cf_pruning)
 
     def _get(self, kind: str, select: bool):
         """Returns a callable running one step (a captured graph replay when graphs are enabled)."""

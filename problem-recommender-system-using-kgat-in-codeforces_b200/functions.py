@@ -41,22 +41,42 @@ class PropState:
     ps: list = field(default_factory=list)
 
 
-def propagate_forward(graph: AttentiveGraph, e0: torch.Tensor, layers, drop: DropoutSpec, save: bool = True) -> PropState:
-    """E_{l} = Agg_l(E_{l-1}, A) for all layers (model.py:124-140, aggregator.py:37-65)."""
+# Test hook: fill every freshly allocated propagation buffer with NaN (0xFF for flag bytes), so that a pruned step that
+# read a row outside its frontier would poison the loss / gradients (tests/test_gpu_pruning.py).
+POISON_STALE_ROWS = False
+
+
+def _buf(*shape, dtype=f32, device=None) -> torch.Tensor:
+    if not POISON_STALE_ROWS:
+        return torch.empty(*shape, dtype=dtype, device=device)
+    return torch.full(shape, 255 if dtype == torch.uint8 else float("nan"), dtype=dtype, device=device)
+
+
+def _row_args(frontier, level: int) -> dict:
+    if frontier is None:
+        return {}
+    return {"rows": frontier.rows(level), "n_rows_dev": frontier.count(level), "max_rows": frontier.cap(level)}
+
+
+def propagate_forward(graph: AttentiveGraph, e0: torch.Tensor, layers, drop: DropoutSpec, save: bool = True, frontier=None) -> PropState:
+    """E_{l} = Agg_l(E_{l-1}, A) for all layers (model.py:124-140, aggregator.py:37-65).
+
+    With a ``frontier`` (frontier.Frontier, already built for this batch) layer ``l`` is computed for the rows of level
+    ``l`` only; the other rows of the returned tables hold stale bytes that nothing downstream reads."""
     n = e0.shape[0]
     dev = e0.device
     st = PropState(tables=[e0])
     for l, (w1, b1, w2, b2) in enumerate(layers):
         x = st.tables[-1]
         d_out = w1.shape[0]
-        side = graph.matmul(x)
-        out = torch.empty(n, d_out, dtype=f32, device=dev)
-        inv = torch.empty(n, dtype=f32, device=dev) if save else None
-        flags = torch.empty(n, d_out, dtype=torch.uint8, device=dev) if save else None
+        side = graph.matmul(x, out=_buf(n, x.shape[1], device=dev), row_mask=None if frontier is None else frontier.mask(l + 1))
+        out = _buf(n, d_out, device=dev)
+        inv = _buf(n, device=dev) if save else None
+        flags = _buf(n, d_out, dtype=torch.uint8, device=dev) if save else None
         p = float(drop.ps[l])
         ops.biagg_forward(
             x, side, w1, b1, w2, b2, out, inv, flags, dropout_p=p, seed=drop.seed, offset=(l + 1) << 40,
-            keep_bits=None if drop.keep_bits is None else drop.keep_bits[l], seed_dev=drop.seed_dev,
+            keep_bits=None if drop.keep_bits is None else drop.keep_bits[l], seed_dev=drop.seed_dev, **_row_args(frontier, l + 1),
         )
         st.tables.append(out)
         if save:
@@ -67,11 +87,25 @@ def propagate_forward(graph: AttentiveGraph, e0: torch.Tensor, layers, drop: Dro
     return st
 
 
-def propagate_backward(graph: AttentiveGraph, st: PropState, layers, g_last: torch.Tensor, inject):
+def last_table_grad(st: PropState, frontier=None) -> torch.Tensor:
+    """Zeroed gradient buffer of the last table (only the frontier's batch rows are zeroed / valid under pruning)."""
+    if frontier is None:
+        return torch.zeros_like(st.tables[-1])
+    g = _buf(*st.tables[-1].shape, device=st.tables[-1].device)
+    top = frontier.n_layers
+    ops.frontier_zero_rows(g, frontier.rows(top), frontier.count(top), frontier.cap(top))
+    return g
+
+
+def propagate_backward(graph: AttentiveGraph, st: PropState, layers, g_last: torch.Tensor, inject, frontier=None):
     """Backward through all layers.  ``g_last`` is the dense gradient w.r.t. the last table;
     ``inject(l, G)`` adds the loss's direct gradient for table ``l`` into the dense buffer ``G``
     (called for l = L-1 .. 0, after the propagated part of G has been written).
-    Returns (g_E0, [(gW1, gb1, gW2, gb2) per layer])."""
+    Returns (g_E0, [(gW1, gb1, gW2, gb2) per layer]).
+
+    With a ``frontier`` the backward of layer ``l`` runs over level ``l``'s rows: ``A^T g_S`` gathers only the edges whose
+    source row is in level ``l`` and produces the rows of level ``l-1`` (all rows for the embedding table, whose
+    gradient the dense Adam sweep reads in full)."""
     n = st.tables[0].shape[0]
     dev = g_last.device
     g = g_last
@@ -80,19 +114,28 @@ def propagate_backward(graph: AttentiveGraph, st: PropState, layers, g_last: tor
         w1, b1, w2, b2 = layers[l - 1]
         x = st.tables[l - 1]
         d_in, d_out = x.shape[1], w1.shape[0]
-        n_ctas = ops.biagg_backward_ctas(n, d_in, d_out)
+        n_ctas = ops.biagg_backward_ctas(n if frontier is None else frontier.cap(l), d_in, d_out, rows=frontier is not None)
         partials = torch.empty(n_ctas * (2 * d_in * d_out + 2 * d_out), dtype=f32, device=dev)
-        g_s = torch.empty(n, d_in, dtype=f32, device=dev)
-        g_e = torch.empty(n, d_in, dtype=f32, device=dev)
+        g_s = _buf(n, d_in, device=dev)
+        g_e = _buf(n, d_in, device=dev)
         ops.biagg_backward(g, st.tables[l], st.inv_norm[l - 1], st.flags[l - 1], x, st.side[l - 1], w1, w2, st.ps[l - 1],
-                           g_s, g_e, partials, n_ctas)
+                           g_s, g_e, partials, n_ctas, **_row_args(frontier, l))
         gw1, gb1, gw2, gb2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2)
         ops.biagg_reduce_param_grads(partials, n_ctas, d_in, d_out, gw1, gb1, gw2, gb2)
         param_grads[l - 1] = (gw1, gb1, gw2, gb2)
-        g_prev = graph.matmul_t(g_s, addend=g_e)  # dL/dE_{l-1} = g_E(direct) + A^T g_S
+        if frontier is None:
+            g_prev = graph.matmul_t(g_s, addend=g_e)  # dL/dE_{l-1} = g_E(direct) + A^T g_S
+        else:
+            g_prev = graph.matmul_t(g_s, out=_buf(n, d_in, device=dev), addend=g_e, row_mask=frontier.mask(l - 1) if l > 1 else None,
+                                    edge_mask=frontier.mask(l))
         inject(l - 1, g_prev)
         g = g_prev
     return g, param_grads
+
+
+def _bump(frontier) -> int:
+    frontier.serial = getattr(frontier, "serial", 0) + 1
+    return frontier.serial
 
 
 def _flat_layers(flat):
@@ -101,10 +144,12 @@ def _flat_layers(flat):
 
 class CFLossFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, graph, users, pos, neg, reg, drop, e0, *flat):
+    def forward(ctx, graph, users, pos, neg, reg, drop, frontier, e0, *flat):
         layers = _flat_layers([t.detach() for t in flat])
         e0d = e0.detach()
-        st = propagate_forward(graph, e0d, layers, drop, save=True)
+        if frontier is not None:
+            frontier.build([users, pos, neg])
+        st = propagate_forward(graph, e0d, layers, drop, save=True, frontier=frontier)
         b = users.numel()
         loss = torch.empty(1, dtype=f32, device=e0.device)
         scratch = torch.empty(2 * b, dtype=f32, device=e0.device)
@@ -112,12 +157,18 @@ class CFLossFunction(torch.autograd.Function):
         ctx.graph, ctx.st, ctx.layers = graph, st, layers
         ctx.ids = (users, pos, neg)
         ctx.reg, ctx.scratch = reg, scratch
+        ctx.frontier = frontier
+        ctx.frontier_serial = None if frontier is None else _bump(frontier)
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, g_loss):
         st, layers, graph = ctx.st, ctx.layers, ctx.graph
         users, pos, neg = ctx.ids
+        frontier = ctx.frontier
+        if frontier is not None and frontier.serial != ctx.frontier_serial:
+            frontier.build([users, pos, neg])  # another forward re-used the frontier buffers in between: rebuild for this batch
+            ctx.frontier_serial = _bump(frontier)
         g_loss = g_loss.reshape(1).to(f32).contiguous()
         n_tab = len(st.tables)
 
@@ -126,11 +177,11 @@ class CFLossFunction(torch.autograd.Function):
             grads[l] = buf
             ops.bpr_backward(st.tables, grads, users, pos, neg, ctx.reg, ctx.scratch, g_loss)
 
-        g_last = torch.zeros_like(st.tables[-1])
+        g_last = last_table_grad(st, frontier)
         inject(n_tab - 1, g_last)
-        g_e0, pgrads = propagate_backward(graph, st, layers, g_last, inject)
+        g_e0, pgrads = propagate_backward(graph, st, layers, g_last, inject, frontier=frontier)
         flat = [t for grp in pgrads for t in grp]
-        return (None, None, None, None, None, None, g_e0, *flat)
+        return (None, None, None, None, None, None, None, g_e0, *flat)
 
 
 class PropagateFunction(torch.autograd.Function):

@@ -141,17 +141,17 @@ class AttentiveGraph:
         return self._partials
 
     # -- ops ----------------------------------------------------------------------------------
-    def matmul(self, x: torch.Tensor, out: torch.Tensor | None = None, addend: torch.Tensor | None = None):
-        """out = A @ x (+ addend)   -- reference aggregator.py:54"""
+    def matmul(self, x: torch.Tensor, out: torch.Tensor | None = None, addend: torch.Tensor | None = None, row_mask=None, edge_mask=None):
+        """out = A @ x (+ addend)   -- reference aggregator.py:54.  ``row_mask`` / ``edge_mask``: frontier bitmaps (ops.spmm)."""
         if out is None:
             out = torch.empty(self.n, x.shape[1], dtype=torch.float32, device=x.device)
-        return ops.spmm(self.plan, self.col_idx, self.vals, x, out, addend, self.partials(x.shape[1]))
+        return ops.spmm(self.plan, self.col_idx, self.vals, x, out, addend, self.partials(x.shape[1]), row_mask=row_mask, edge_mask=edge_mask)
 
-    def matmul_t(self, x: torch.Tensor, out: torch.Tensor | None = None, addend: torch.Tensor | None = None):
+    def matmul_t(self, x: torch.Tensor, out: torch.Tensor | None = None, addend: torch.Tensor | None = None, row_mask=None, edge_mask=None):
         """out = A^T @ x (+ addend)   -- autograd backward of aggregator.py:54"""
         if out is None:
             out = torch.empty(self.n, x.shape[1], dtype=torch.float32, device=x.device)
-        return ops.spmm(self.t_plan, self.t_idx, self.t_vals, x, out, addend, self.partials(x.shape[1]))
+        return ops.spmm(self.t_plan, self.t_idx, self.t_vals, x, out, addend, self.partials(x.shape[1]), row_mask=row_mask, edge_mask=edge_mask)
 
     # -- the reference-facing view --------------------------------------------------------------
     def indices64(self) -> torch.Tensor:

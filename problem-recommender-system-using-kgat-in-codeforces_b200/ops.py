@@ -186,25 +186,74 @@ def fill_(t: torch.Tensor, value: float = 0.0):
 # ----------------------------------------------------------------------------------------------
 
 
-@_timed(lambda plan, col_idx, vals, x, out, addend=None, *a, **k: f"spmm{'T' if addend is not None else ''}_d{x.shape[1]}")
-def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.Tensor | None = None, partials=None):
-    """out = A @ x (+ addend); ``plan`` is a graph.SpmmPlan."""
+def _spmm_name(plan, col_idx, vals, x, out, addend=None, partials=None, row_mask=None, edge_mask=None):
+    return f"spmm{'T' if addend is not None else ''}_d{x.shape[1]}{'_pruned' if (row_mask is not None or edge_mask is not None) else ''}"
+
+
+@_timed(_spmm_name)
+def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.Tensor | None = None, partials=None,
+         row_mask: torch.Tensor | None = None, edge_mask: torch.Tensor | None = None):
+    """out = A @ x (+ addend); ``plan`` is a graph.SpmmPlan.  ``row_mask`` / ``edge_mask``: node bitmaps of a
+    ``frontier.Frontier`` level (only the rows in ``row_mask`` are computed; edges / addend rows outside ``edge_mask`` are dropped)."""
     lib = _lib.load()
     d = x.shape[1]
     if plan.n_heavy > 0:
         need = plan.n_partials * d
         if partials is None or partials.numel() < need:
             raise KgatLibraryError("spmm: partials scratch too small")
-    check(
-        lib.kgat_spmm_csr(
-            _ptr(plan.tasks, i32), plan.n_tasks, _ptr(plan.heavy, i32) if plan.n_heavy else None, plan.n_heavy,
-            _ptr(col_idx, i32), _ptr(vals, f32), _ptr(x, f32, "x", True), x.shape[0], x.stride(0), _ptr(out, f32, "out", True), out.stride(0),
-            _ptr(addend, f32, "addend", True) if addend is not None else None, addend.stride(0) if addend is not None else 0, d,
-            _ptr(partials, f32) if partials is not None else None, _stream(),
-        ),
-        "spmm_csr",
+    args = (
+        _ptr(plan.tasks, i32), plan.n_tasks, _ptr(plan.heavy, i32) if plan.n_heavy else None, plan.n_heavy,
+        _ptr(col_idx, i32), _ptr(vals, f32), _ptr(x, f32, "x", True), x.shape[0], x.stride(0), _ptr(out, f32, "out", True), out.stride(0),
+        _ptr(addend, f32, "addend", True) if addend is not None else None, addend.stride(0) if addend is not None else 0, d,
+        _ptr(partials, f32) if partials is not None else None,
     )
+    if row_mask is None and edge_mask is None:
+        check(lib.kgat_spmm_csr(*args, _stream()), "spmm_csr")
+    else:
+        words = (max(x.shape[0], out.shape[0]) + 31) // 32
+        for m in (row_mask, edge_mask):
+            if m is not None and m.numel() < words:
+                raise KgatLibraryError("spmm: node bitmap too small")
+        check(lib.kgat_spmm_csr_masked(*args, _ptr(row_mask, i32) if row_mask is not None else None,
+                                       _ptr(edge_mask, i32) if edge_mask is not None else None, _stream()), "spmm_csr_masked")
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# needed-row frontier of a TRAIN_CF step (csrc/frontier.cu)
+# ----------------------------------------------------------------------------------------------
+
+
+def frontier_scratch_ints(n_nodes: int) -> int:
+    return int(_lib.load().kgat_frontier_scratch_ints(int(n_nodes)))
+
+
+def frontier_mark_ids(ids: torch.Tensor, n_nodes: int, bitmap: torch.Tensor, bad_count: torch.Tensor | None = None):
+    lib = _lib.load()
+    if bitmap.numel() * 32 < n_nodes:
+        raise KgatLibraryError("frontier_mark_ids: bitmap too small")
+    check(lib.kgat_frontier_mark_ids(_ptr(ids, i64, "ids"), ids.numel(), int(n_nodes), _ptr(bitmap, i32),
+                                     _ptr(bad_count, i32) if bad_count is not None else None, _stream()), "frontier_mark_ids")
+
+
+def frontier_expand(row_ptr, col_idx, rows, count_dev, max_rows: int, bitmap_out):
+    lib = _lib.load()
+    check(lib.kgat_frontier_expand(_ptr(row_ptr, i32), _ptr(col_idx, i32), _ptr(rows, i32), _ptr(count_dev, i32), int(max_rows),
+                                   _ptr(bitmap_out, i32), _stream()), "frontier_expand")
+
+
+def frontier_list(bitmap, n_nodes: int, scratch, rows, count_dev):
+    lib = _lib.load()
+    if scratch.numel() < frontier_scratch_ints(n_nodes) or bitmap.numel() * 32 < n_nodes:
+        raise KgatLibraryError("frontier_list: scratch / bitmap too small")
+    check(lib.kgat_frontier_list(_ptr(bitmap, i32), int(n_nodes), _ptr(scratch, i32), _ptr(rows, i32), _ptr(count_dev, i32), _stream()),
+          "frontier_list")
+
+
+def frontier_zero_rows(table: torch.Tensor, rows, count_dev, max_rows: int):
+    lib = _lib.load()
+    check(lib.kgat_frontier_zero_rows(_ptr(table, f32, "table", True), table.stride(0), table.shape[1], _ptr(rows, i32), _ptr(count_dev, i32),
+                                      int(max_rows), _stream()), "frontier_zero_rows")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -212,13 +261,28 @@ def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.
 # ----------------------------------------------------------------------------------------------
 
 
-@_timed(lambda E, S, W1, *a, **k: f"biagg_fwd_{E.shape[1]}x{W1.shape[0]}")
+@_timed(lambda E, S, W1, *a, **k: f"biagg_fwd_{E.shape[1]}x{W1.shape[0]}{'_pruned' if k.get('rows') is not None else ''}")
 def biagg_forward(E, S, W1, b1, W2, b2, out, inv_norm, flags, dropout_p=0.0, seed=0, offset=0, keep_bits=None, seed_dev=None,
-                  peer_out=None):
-    """``peer_out``: int64 device tensor of pointers to this rank's rows in every peer's copy of ``out`` (peer.PeerArena)."""
+                  peer_out=None, rows=None, n_rows_dev=None, max_rows=None):
+    """``peer_out``: int64 device tensor of pointers to this rank's rows in every peer's copy of ``out`` (peer.PeerArena).
+    ``rows`` / ``n_rows_dev`` / ``max_rows``: needed-row list of a ``frontier.Frontier`` level (arrays stay node-indexed)."""
     lib = _lib.load()
     n, d_in = E.shape
     d_out = W1.shape[0]
+    if rows is not None:
+        if peer_out is not None:
+            raise KgatLibraryError("biagg_forward: a row list and peer stores are mutually exclusive")
+        check(
+            lib.kgat_biagg_forward_rows(
+                _ptr(E, f32, "E"), _ptr(S, f32, "S"), _ptr(rows, i32, "rows"), _ptr(n_rows_dev, i32), int(max_rows), d_in, d_out,
+                _ptr(W1, f32), _ptr(b1, f32), _ptr(W2, f32), _ptr(b2, f32), float(dropout_p), int(seed), int(offset),
+                _ptr(seed_dev, i64) if seed_dev is not None else None, _ptr(keep_bits, i32) if keep_bits is not None else None,
+                _ptr(out, f32, "out"), out.stride(0), _ptr(inv_norm, f32) if inv_norm is not None else None,
+                _ptr(flags, u8) if flags is not None else None, _stream(),
+            ),
+            f"biagg_forward_rows({d_in}->{d_out})",
+        )
+        return out
     check(
         lib.kgat_biagg_forward(
             _ptr(E, f32, "E"), _ptr(S, f32, "S"), n, d_in, d_out, _ptr(W1, f32), _ptr(b1, f32), _ptr(W2, f32), _ptr(b2, f32),
@@ -233,17 +297,31 @@ def biagg_forward(E, S, W1, b1, W2, b2, out, inv_norm, flags, dropout_p=0.0, see
     return out
 
 
-def biagg_backward_ctas(n: int, d_in: int, d_out: int) -> int:
-    return _lib.load().kgat_biagg_backward_ctas(n, d_in, d_out)
+def biagg_backward_ctas(n: int, d_in: int, d_out: int, rows: bool = False) -> int:
+    lib = _lib.load()
+    return lib.kgat_biagg_backward_rows_ctas(n, d_in, d_out) if rows else lib.kgat_biagg_backward_ctas(n, d_in, d_out)
 
 
-@_timed(lambda g_out, out, inv_norm, flags, E, S, W1, *a, **k: f"biagg_bwd_{E.shape[1]}x{W1.shape[0]}")
-def biagg_backward(g_out, out, inv_norm, flags, E, S, W1, W2, dropout_p, g_S, g_E, partials, n_ctas, peer_out=None):
+@_timed(lambda g_out, out, inv_norm, flags, E, S, W1, *a, **k: f"biagg_bwd_{E.shape[1]}x{W1.shape[0]}{'_pruned' if k.get('rows') is not None else ''}")
+def biagg_backward(g_out, out, inv_norm, flags, E, S, W1, W2, dropout_p, g_S, g_E, partials, n_ctas, peer_out=None, rows=None,
+                   n_rows_dev=None, max_rows=None):
     lib = _lib.load()
     n, d_in = E.shape
     d_out = W1.shape[0]
     if partials.numel() < n_ctas * (2 * d_in * d_out + 2 * d_out):
         raise KgatLibraryError("biagg_backward: partials scratch too small")
+    if rows is not None:
+        if peer_out is not None:
+            raise KgatLibraryError("biagg_backward: a row list and peer stores are mutually exclusive")
+        check(
+            lib.kgat_biagg_backward_rows(
+                _ptr(g_out, f32, "g_out"), g_out.stride(0), _ptr(out, f32), out.stride(0), _ptr(inv_norm, f32), _ptr(flags, u8),
+                _ptr(E, f32), _ptr(S, f32), _ptr(rows, i32, "rows"), _ptr(n_rows_dev, i32), int(max_rows), d_in, d_out, _ptr(W1, f32),
+                _ptr(W2, f32), float(dropout_p), _ptr(g_S, f32), _ptr(g_E, f32), _ptr(partials, f32), n_ctas, _stream(),
+            ),
+            f"biagg_backward_rows({d_in}->{d_out})",
+        )
+        return
     check(
         lib.kgat_biagg_backward(
             _ptr(g_out, f32, "g_out"), g_out.stride(0), _ptr(out, f32), out.stride(0), _ptr(inv_norm, f32), _ptr(flags, u8),
