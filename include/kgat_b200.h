@@ -170,6 +170,10 @@ int kgat_biagg_backward_rows(const float* g_out, int64_t ld_gout, const float* o
                              const float* W2, float dropout_p, float* g_S, float* g_E, float* partials, int32_t n_ctas,
                              void* stream);
 
+/* T[ids64[i], 0:d] = 0 (ids outside [0, n_rows) ignored): re-zero the rows a batch's gradient scatter touched instead of
+ * clearing a whole n_rows x d gradient table per step (model.py:211-261 touches <= 3B of the N embedding rows) */
+int kgat_zero_rows_i64(float* T, int64_t n_rows, int64_t ld, int32_t d, const int64_t* ids64, int64_t n_ids, void* stream);
+
 /* ------------------------------------------------------------------------------------------- */
 /* K4: BPR loss over the layer tables      reference model.py:189-202, 142-163                   */
 /* ------------------------------------------------------------------------------------------- */
@@ -243,6 +247,13 @@ typedef struct {
     float ln_eps;
     int32_t n_heads;
 } kgat_mha_t;
+
+/* MultiHeadAttention.forward (multi_head_attention.py:35-58) on caller-provided projected tail embeddings (n x d):
+ * out = LayerNorm(Wo drop(Wv x + bv) + bo), n x d.  The query / key inputs cancel (softmax over a length-1 axis,
+ * SURVEY.md Q1) and are not taken.  Per-head dropout as in kgat_att_edge_scores_dropout (head_bits: one byte per row,
+ * bit h keeps head h; else Philox (seed, offset + row)); dropout_p = 0 in eval mode. */
+int kgat_mha_forward(const float* tail_embedding, int64_t n, int32_t d, const kgat_mha_t* mha, float dropout_p,
+                     const uint8_t* head_bits, uint64_t seed, uint64_t offset, float* out, void* stream);
 
 /* Per unique (tail, relation) pair: x = e_t W_r, v = Wv x + bv.  If v_out != NULL stores v (n_pairs x d).
  * If score_out != NULL also o = Wo v + bo, LayerNorm, score = sum tanh  (the eval-mode edge score
@@ -377,6 +388,20 @@ int kgat_peer_signal_wait(int32_t* const* peer_flags, const int32_t* my_flags, i
 
 /* utility: fill used by the host glue so no torch kernel sits on the hot path */
 int kgat_fill_f32(float* p, int64_t n, float value, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* host-latency helpers of the API fast path (the reference driver's per-step loop,               */
+/* main.py:297-345: model(...), loss.backward(), update_*_weights(), loss.item())                */
+/* ------------------------------------------------------------------------------------------- */
+/* ring_host_mapped[s % n_slots] = (s << 32) | bits(*loss) with s = ++(*serial_dev): one aligned 8-byte store into
+ * mapped pinned HOST memory (device-visible pointer), so the host can read a step's loss by polling without
+ * synchronising the stream behind it. */
+int kgat_publish_loss(const float* loss, uint64_t* serial_dev, uint64_t* ring_host_mapped, int32_t n_slots, void* stream);
+/* cudaGraphLaunch(graph_exec, stream); graph_exec is a cudaGraphExec_t (host handle) */
+int kgat_graph_launch(void* graph_exec, void* stream);
+/* cudaMemcpyAsync(dst_dev, src, n_bytes, default kind, stream) followed by cudaGraphLaunch(graph_exec, stream):
+ * the ids of one training step and the step itself in one call.  src: pinned host or device memory. */
+int kgat_step_submit(void* dst_dev, const void* src, int64_t n_bytes, void* graph_exec, void* stream);
 
 #ifdef __cplusplus
 }

@@ -170,6 +170,65 @@ __global__ void __launch_bounds__(128) edge_scores_dropout_kernel(const float* _
     }
 }
 
+// MultiHeadAttention.forward on caller-provided (already projected) tail embeddings (multi_head_attention.py:35-58):
+// y = LayerNorm(Wo drop(Wv x + bv) + bo).  The query / key inputs do not influence the output (softmax over a
+// length-1 axis), so only x = tail_embedding is read.  One warp per row.
+template <int DM>
+__global__ void __launch_bounds__(128) mha_forward_kernel(const float* __restrict__ x_in, int64_t n, Mha P, float dropout_p,
+                                                          const uint8_t* __restrict__ head_bits, uint64_t seed, uint64_t offset,
+                                                          float* __restrict__ y_out) {
+    constexpr int D = DM * 32;
+    extern __shared__ __align__(16) float smem[];
+    float* WvT = smem;
+    float* WoT = smem + D * D;
+    stage_transposed<DM>(P.Wv, WvT, threadIdx.x, blockDim.x);
+    stage_transposed<DM>(P.Wo, WoT, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int depth = D / P.n_heads;
+    const float scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+    const float q = 1.f - dropout_p;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp0; i < n; i += nwarps) {
+        float x[DM], v[DM], o[DM];
+#pragma unroll
+        for (int m = 0; m < DM; ++m) x[m] = __ldg(x_in + i * D + lane + 32 * m);
+        matvec_smem<DM>(WvT, P.bv, x, lane, v);
+        if (dropout_p > 0.f) {
+            uint32_t keep;
+            if (head_bits != nullptr) {
+                keep = head_bits[i];
+            } else {
+                const uint4 rnd = philox4x32(seed, offset + (uint64_t)i);
+                const uint32_t w[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+                keep = 0;
+                for (int hd = 0; hd < P.n_heads && hd < 8; ++hd) {
+                    const uint32_t bits16 = (w[hd >> 1] >> ((hd & 1) * 16)) & 0xffffu;
+                    if ((float)bits16 * (1.f / 65536.f) < q) keep |= 1u << hd;
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < DM; ++m) v[m] = ((keep >> ((lane + 32 * m) / depth)) & 1u) ? v[m] * scale : 0.f;
+        }
+        matvec_smem<DM>(WoT, P.bo, v, lane, o);
+        float s = 0.f;
+#pragma unroll
+        for (int m = 0; m < DM; ++m) s += o[m];
+        const float mean = warp_sum(s) / (float)D;
+        float qq = 0.f;
+#pragma unroll
+        for (int m = 0; m < DM; ++m) {
+            const float c = o[m] - mean;
+            qq = fmaf(c, c, qq);
+        }
+        const float rstd = rsqrtf(warp_sum(qq) / (float)D + P.eps);
+#pragma unroll
+        for (int m = 0; m < DM; ++m)
+            y_out[i * D + lane + 32 * m] = (o[m] - mean) * rstd * P.gamma[lane + 32 * m] + P.beta[lane + 32 * m];
+    }
+}
+
 __global__ void __launch_bounds__(128) row_softmax_kernel(const int32_t* __restrict__ row_ptr, int64_t n_rows,
                                                           const int32_t* __restrict__ slot_ptr, const float* __restrict__ pair_score,
                                                           const int32_t* __restrict__ pair_of_edge,
@@ -253,12 +312,44 @@ int launch_edges(const float* pair_v, const int32_t* poe, int64_t n_edges, const
     return check_launch();
 }
 
+template <int DM>
+int launch_mha(const float* x, int64_t n, const Mha& P, float p, const uint8_t* head_bits, uint64_t seed, uint64_t offset, float* y,
+               cudaStream_t stream) {
+    constexpr int D = DM * 32;
+    const size_t smem = sizeof(float) * 2 * D * D;
+    static bool configured = false;
+    if (!configured) {
+        KGAT_CUDA_TRY(cudaFuncSetAttribute(mha_forward_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int64_t blocks = (n + 3) / 4;
+    const int64_t cap = (int64_t)sm_count() * (DM <= 2 ? 4 : 1);
+    if (blocks > cap) blocks = cap;
+    mha_forward_kernel<DM><<<(unsigned)blocks, 128, smem, stream>>>(x, n, P, p, head_bits, seed, offset, y);
+    return check_launch();
+}
+
 }  // namespace
 }  // namespace kgat
 
 using namespace kgat;
 
 extern "C" {
+
+int kgat_mha_forward(const float* tail_embedding, int64_t n, int32_t d, const kgat_mha_t* mha, float dropout_p, const uint8_t* head_bits,
+                     uint64_t seed, uint64_t offset, float* out, void* stream) {
+    Mha P;
+    int rc = pack_mha(mha, &P);
+    if (rc != KGAT_OK) return rc;
+    if (n < 0 || dropout_p < 0.f || dropout_p >= 1.f || P.n_heads > 8 || d % P.n_heads) return KGAT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return KGAT_OK;
+    switch (d) {
+        case 32: return launch_mha<1>(tail_embedding, n, P, dropout_p, head_bits, seed, offset, out, (cudaStream_t)stream);
+        case 64: return launch_mha<2>(tail_embedding, n, P, dropout_p, head_bits, seed, offset, out, (cudaStream_t)stream);
+        case 128: return launch_mha<4>(tail_embedding, n, P, dropout_p, head_bits, seed, offset, out, (cudaStream_t)stream);
+        default: return KGAT_ERR_UNSUPPORTED;
+    }
+}
 
 int kgat_att_pair_scores(const float* emb, const float* W, int32_t d, const int32_t* pair_tail, const int32_t* pair_rel, int64_t n_pairs,
                          const kgat_mha_t* mha, float* v_out, float* score_out, void* stream) {

@@ -337,12 +337,30 @@ __global__ void transr_claim_rows_kernel(const int64_t* __restrict__ heads, cons
     }
 }
 
+// T[ids[i], :] = 0: re-zero the few rows a sparse scatter touched instead of memsetting the whole table
+__global__ void zero_rows_i64_kernel(float* __restrict__ T, int64_t ld, int d4, const int64_t* __restrict__ ids, int64_t n_ids,
+                                     int64_t n_rows) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_ids * d4) return;
+    const int64_t r = ids[i / d4];
+    if (r < 0 || r >= n_rows) return;
+    reinterpret_cast<float4*>(T + r * ld)[i % d4] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 }  // namespace
 }  // namespace kgat
 
 using namespace kgat;
 
 extern "C" {
+
+int kgat_zero_rows_i64(float* T, int64_t n_rows, int64_t ld, int32_t d, const int64_t* ids64, int64_t n_ids, void* stream) {
+    if (!T || !ids64 || n_rows <= 0 || d <= 0 || (d & 3) || (ld & 3) || n_ids < 0) return KGAT_ERR_INVALID_ARGUMENT;
+    if (n_ids == 0) return KGAT_OK;
+    const int64_t total = n_ids * (d / 4);
+    zero_rows_i64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, ld, d / 4, ids64, n_ids, n_rows);
+    return check_launch();
+}
 
 int kgat_bpr_forward(const kgat_tables_t* tables, const int64_t* users, const int64_t* pos, const int64_t* neg, int32_t batch,
                      float reg, float* loss, float* margin, void* stream_) {

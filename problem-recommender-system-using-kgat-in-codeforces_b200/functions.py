@@ -231,63 +231,231 @@ class KGLossFunction(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------
-# CUDA-graph fast path behind the reference-facing API (model(...), loss.backward())
+# CUDA-graph fast path behind the reference-facing API (model(...), loss.backward(), update_*_weights(), loss.item())
 # ----------------------------------------------------------------------------------------------
 class GraphedStep:
-    """Forward and backward of one training mode captured as two CUDA graphs over static buffers.
+    """One training mode's forward AND backward captured as ONE CUDA graph over static buffers.
 
-    The reference driver always runs ``loss = model(...); loss.backward(); model.update_*_weights()``
-    (main.py:306-314, 334-343); an epoch is ~15 k such steps whose Python / launch overhead exceeds
-    their GPU time.  ``replay_forward`` copies the step's ids into static buffers and replays the
-    forward graph; ``GraphedLoss`` hands autograd a node whose backward replays the backward graph and
-    returns *views* of the static gradient buffers (autograd adopts them as ``.grad`` without a copy).
+    The reference driver always runs ``loss = model(...); loss.backward(); model.update_*_weights(); loss.item()``
+    (main.py:306-314, 334-343); an epoch is ~15 k such steps and a KG step is ~60 us of GPU work, so the API path is
+    bound by host time per call.  Here ``model(...)`` is one C call (``kgat_step_submit``: copy of the step's ids into
+    the static buffer + launch of the graph) whose graph computes the loss, publishes it to a pinned host ring
+    (``kgat_publish_loss``) and goes straight on to the gradients w.r.t. a unit upstream gradient; the returned
+    ``LazyLoss`` makes ``loss.backward()`` a hand-over of the static gradient buffers (no autograd engine run) and
+    ``loss.item()`` a host-side poll of the ring (no stream synchronisation: the backward / Adam kernels queued behind
+    the loss keep running).  Anything else done with the loss falls back to a real autograd node (``GraphedLoss``).
     """
 
+    RING = 1024  # published losses kept readable on the host
+
     def __init__(self, params, batch: int, n_ids: int, body_fwd, body_bwd):
+        from . import _lib
+
         dev = params[0].device
-        self.params = params
+        self.params = list(params)
+        self.device = dev
         self.ids = torch.zeros(n_ids, batch, dtype=torch.int64, device=dev)
         self.loss = torch.zeros(1, dtype=f32, device=dev)
-        self.g_loss = torch.ones(1, dtype=f32, device=dev)
+        self.loss_scalar = self.loss.reshape(())
+        self.g_loss = torch.ones(1, dtype=f32, device=dev)  # the unit upstream gradient the captured backward uses
         self.scratch = torch.empty(2 * batch, dtype=f32, device=dev)
         self.counter = torch.zeros(1, dtype=torch.int64, device=dev)  # forward calls so far (dropout stream)
-        self.serial = 0
+        self.pub_serial = torch.zeros(1, dtype=torch.int64, device=dev)  # losses published so far (device side)
+        self.ring = torch.zeros(self.RING, dtype=torch.int64).pin_memory()  # (serial << 32) | float bits, written by the GPU
+        self._ring_words = self.ring.numpy()
+        self._ring_f32 = self._ring_words.view("<f4")
+        self.serial = 0  # forward launches so far (host side; equals pub_serial once the launches have run)
+        self.adopted = 0  # serial whose gradients were handed to the parameters
+        self.updated = 0  # serial whose gradients went through the fused optimiser step
         self.grads = None
+        self._adam = {}
+        self._lib = _lib.load()
+        # the captured graph bakes in the addresses of every buffer the bodies' closures own (needed-row frontier, static
+        # gradient tables, previous-batch ids ...): keep the closures -- and with them those buffers -- alive as long as the graph
+        self._bodies = (body_fwd, body_bwd)
+
+        def whole(st):
+            body_fwd(st)
+            ops.publish_loss(st.loss, st.pub_serial, st.ring)
+            return body_bwd(st)
+
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # eager warm-up (no parameter is modified by forward / backward)
-            body_fwd(self)
-            body_bwd(self)
+            whole(self)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph_f = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_f):
-            body_fwd(self)
-        self.graph_b = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_b, pool=self.graph_f.pool()):
-            self.grads = body_bwd(self)
+        self.pub_serial.zero_()
+        self.ring.zero_()
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.grads = whole(self)
+        self._exec = self.graph.raw_cuda_graph_exec()
+        self._ids_ptr = self.ids.data_ptr()
+        self._ids_bytes = self.ids.numel() * 8
+        self._grad_key = tuple(g.data_ptr() for g in self.grads)
+        self._param_ids = tuple(id(p) for p in self.params)
 
-    def replay_forward(self, ids):
+    # -- forward ---------------------------------------------------------------------------------
+    def submit(self, ids) -> "LazyLoss":
+        """Copy the ids into the static buffer and launch forward + backward.  ``ids``: int64 tensors on the device or in
+        pinned host memory; consecutive rows of one [n_ids, B] block travel in the same call as the launch."""
+        for p, g in zip(self.params, self.grads):
+            pg = p.grad
+            if pg is not None and (pg is g or pg.data_ptr() == g.data_ptr()):
+                p.grad = pg.clone()  # an un-applied gradient still aliases our buffer (accumulation): keep its value
         b = self.ids.shape[1]
         first = ids[0]
-        st0 = first.untyped_storage()
-        if (first.numel() == b and all(t.data_ptr() == first.data_ptr() + i * b * 8 and t.untyped_storage().data_ptr() == st0.data_ptr()
-                                       for i, t in enumerate(ids))
-                and st0.nbytes() >= (first.storage_offset() + len(ids) * b) * 8):
-            # the id tensors are consecutive rows of one [n_ids, B] block (one H2D copy upstream): one copy here too
-            self.ids.copy_(first.as_strided((len(ids), b), (b, 1)), non_blocking=True)
+        stream = torch.cuda.current_stream().cuda_stream
+        one_block = first.numel() == b and first.dtype == torch.int64 and first.is_contiguous()
+        if one_block:
+            base = first.data_ptr()
+            for i, t in enumerate(ids):
+                if t.data_ptr() != base + i * b * 8 or t.dtype != torch.int64 or not t.is_contiguous() or t.numel() != b:
+                    one_block = False
+                    break
+            one_block = one_block and (first.is_cuda or first.is_pinned())
+        if one_block:
+            rc = self._lib.kgat_step_submit(self._ids_ptr, base, self._ids_bytes, self._exec, stream)
         else:
             for dst, src in zip(self.ids, ids):
                 dst.copy_(src, non_blocking=True)
-        self.graph_f.replay()
+            rc = self._lib.kgat_graph_launch(self._exec, stream)
+        if rc != 0:
+            from ._lib import check
+
+            check(rc, "api step launch")
         self.serial += 1
+        return LazyLoss.make(self)
+
+    # -- backward --------------------------------------------------------------------------------
+    def adopt_grads(self, serial: int) -> None:
+        """``loss.backward()``: hand the static gradient buffers (computed at forward time) to the parameters."""
+        if serial != self.serial:
+            raise RuntimeError(
+                "kgat_b200: backward() of a loss whose forward buffers were reused by a later model(...) call. "
+                "The API fast path assumes forward -> backward -> update per step (as the reference driver does); "
+                "set model.api_graphs = False for free-form autograd use."
+            )
+        if self.adopted == serial:
+            raise RuntimeError("Trying to backward through the graph a second time (kgat_b200 API fast path keeps no graph to retain)")
+        self.adopted = serial
+        for p, g in zip(self.params, self.grads):
+            if p.grad is None:
+                p.grad = g
+            else:
+                p.grad = p.grad + g  # accumulation: never in place into a buffer we may not own
+
+    # -- optimiser -------------------------------------------------------------------------------
+    def try_fused_update(self, opt) -> bool:
+        """``update_*_weights()`` right after ``backward()``: replay the captured Adam step over (params, static grads) and
+        drop the gradients.  Returns False (nothing done) whenever the situation is anything but exactly that."""
+        if self.adopted != self.serial or self.updated == self.serial:
+            return False
+        for p, g in zip(self.params, self.grads):
+            if p.grad is not g:
+                return False
+        plan = opt.fast_plan(self.params, self.grads, self._grad_key)
+        if plan is None:
+            return False
+        opt.fast_replay(plan, self.params)
+        self.updated = self.serial
+        return True
+
+    # -- loss value ------------------------------------------------------------------------------
+    def read_loss(self, serial: int) -> float:
+        """Host value of the loss published by forward number ``serial`` (polls the pinned ring; no stream sync)."""
+        import time
+
+        if self.serial - serial >= self.RING:
+            raise RuntimeError("kgat_b200: this loss value is no longer available (more than 1024 later steps were issued)")
+        slot = serial % self.RING
+        words = self._ring_words
+        want = serial & 0xFFFFFFFF
+        spins = 0
+        deadline = None
+        while True:
+            w = int(words[slot])
+            if ((w >> 32) & 0xFFFFFFFF) == want:
+                return float(self._ring_f32[2 * slot])
+            spins += 1
+            if spins & 1023 == 0:
+                now = time.perf_counter()
+                if deadline is None:
+                    deadline = now + 20.0
+                elif now > deadline:
+                    torch.cuda.synchronize()  # surfaces a CUDA error if the step faulted
+                    if ((int(words[slot]) >> 32) & 0xFFFFFFFF) == want:
+                        return float(self._ring_f32[2 * slot])
+                    raise RuntimeError("kgat_b200: the loss of this step was never published")
+
+    def loss_tensor(self, serial: int) -> torch.Tensor:
+        """A plain 0-dim device tensor holding the loss of forward ``serial`` (no autograd)."""
+        if serial == self.serial:
+            return self.loss_scalar.clone()
+        return torch.tensor(self.read_loss(serial), dtype=f32, device=self.device)
+
+
+class LazyLoss(torch.Tensor):
+    """The 0-dim loss returned by the API fast path.  ``backward()`` / ``item()`` / ``float()`` / ``detach()`` are served
+    directly by the step's static buffers; any other use materialises a real autograd-tracked tensor first."""
+
+    @staticmethod
+    def make(step: GraphedStep) -> "LazyLoss":
+        t = torch.Tensor._make_subclass(LazyLoss, step.loss_scalar)
+        t._step, t._serial, t._real = step, step.serial, None
+        return t
+
+    def _materialize(self) -> torch.Tensor:
+        if self._real is None:
+            step = self._step
+            if self._serial == step.serial:
+                self._real = GraphedLoss.apply(step, self._serial, *step.params)
+            else:
+                self._real = step.loss_tensor(self._serial)
+        return self._real
+
+    def backward(self, gradient=None, retain_graph=None, create_graph=False, inputs=None):
+        if gradient is not None or create_graph or inputs is not None or self._real is not None:
+            return self._materialize().backward(gradient, retain_graph, create_graph, inputs)
+        self._step.adopt_grads(self._serial)
+
+    def item(self) -> float:
+        return self._step.read_loss(self._serial)
+
+    def __float__(self) -> float:
+        return self._step.read_loss(self._serial)
+
+    def tolist(self) -> float:
+        return self._step.read_loss(self._serial)
+
+    def detach(self) -> torch.Tensor:
+        return self._step.loss_tensor(self._serial)
+
+    def __repr__(self) -> str:
+        return f"tensor({self.item():.4f}, device='{self._step.device}', grad_fn=<KgatGraphedStep>)"
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        def real(a):
+            if isinstance(a, LazyLoss):
+                return a._materialize()
+            if isinstance(a, (list, tuple)):
+                return type(a)(real(x) for x in a)
+            return a
+
+        with torch._C.DisableTorchFunctionSubclass():
+            return func(*[real(a) for a in args], **{k: real(v) for k, v in (kwargs or {}).items()})
 
 
 class GraphedLoss(torch.autograd.Function):
+    """Slow-path autograd node of a graphed step (composition with other tensors, non-unit upstream gradient, ...)."""
+
     @staticmethod
-    def forward(ctx, step: GraphedStep, *params):
-        ctx.step, ctx.serial = step, step.serial
-        return step.loss.reshape(()).clone()
+    def forward(ctx, step: GraphedStep, serial: int, *params):
+        ctx.step, ctx.serial = step, serial
+        return step.loss_scalar.clone()
 
     @staticmethod
     def backward(ctx, g_loss):
@@ -298,7 +466,5 @@ class GraphedLoss(torch.autograd.Function):
                 "The API fast path assumes forward -> backward -> update per step (as the reference driver does); "
                 "set model.api_graphs = False for free-form autograd use."
             )
-        step.g_loss.copy_(g_loss.reshape(1))
-        step.graph_b.replay()
-        adopt = all(p.grad is None for p in step.params)  # accumulation into an existing .grad must not alias our buffers
-        return (None, *[g.view_as(g) if adopt else g.clone() for g in step.grads])
+        # the step's graph already produced the gradients for a unit upstream gradient; they are linear in it
+        return (None, None, *[g * g_loss for g in step.grads])

@@ -32,7 +32,7 @@ from . import ops
 from ._lib import KgatLibraryError
 from .aggregator import Aggregator, AggregatorArgs
 from .frontier import Frontier
-from .functions import (CFLossFunction, DropoutSpec, GraphedLoss, GraphedStep, KGLossFunction, PropagateFunction, last_table_grad,
+from .functions import (CFLossFunction, DropoutSpec, GraphedStep, KGLossFunction, PropagateFunction, last_table_grad,
                         propagate_backward, propagate_forward)
 from .graph import AttentiveGraph, EdgeIndex
 from .multi_head_attention import MultiHeadAttention
@@ -119,6 +119,7 @@ class KGAT(nn.Module):
         # CUDA-graph fast path behind model(...) / loss.backward() for the two training modes (functions.GraphedStep)
         self.api_graphs = True
         self._api_steps: dict = {}
+        self._last_step: dict = {}
         # TRAIN_CF computes every layer only for the rows the batch can reach (frontier.py): exact, ~2x less work at the
         # Amazon-book shape.  False = the reference's literal full-graph propagation per batch.
         self.cf_pruning = True
@@ -162,6 +163,7 @@ class KGAT(nn.Module):
         self._graph_cache = self._graph_key = None
         self._table_cache = self._table_key = None
         self._api_steps = {}
+        self._last_step = {}
         self._frontiers = {}
 
     def _frontier(self, graph: AttentiveGraph, n_ids: int, fresh: bool = False) -> Frontier | None:
@@ -244,14 +246,26 @@ class KGAT(nn.Module):
                 self._api_steps.clear()
             body_fwd, body_bwd = make_bodies()
             step = self._api_steps[key] = GraphedStep(params, batch, n_ids, body_fwd, body_bwd)
+        self._last_step[kind] = step
         return step
+
+    def _ids_fast(self, tensors):
+        """Index tensors for the graphed API path: int64 tensors already on the device, or views of pinned host memory
+        (copied by the step's own launch call), pass through untouched; anything else goes through ``_ids``."""
+        out = []
+        for t in tensors:
+            if isinstance(t, torch.Tensor) and t.dtype == torch.int64 and t.is_contiguous() and (t.is_cuda or t.is_pinned()):
+                out.append(t)
+            else:
+                out.append(self._ids(t))
+        return out
 
     def _calc_cf_loss(self, user_ids, positive_item_ids, negative_item_ids) -> torch.Tensor:
         graph = self._graph()
         flat = [t for grp in self._layers() for t in grp]
         params = [self._user_entity_embedding.weight, *flat]
         if self._use_api_graphs(params):
-            ids = [self._ids(user_ids), self._ids(positive_item_ids), self._ids(negative_item_ids)]
+            ids = self._ids_fast((user_ids, positive_item_ids, negative_item_ids))
 
             def make_bodies():
                 reg = float(self._regularization_params[0])
@@ -262,6 +276,7 @@ class KGAT(nn.Module):
 
                 def body_fwd(st):
                     st.counter.add_(1)
+                    st.frontier = frontier  # (introspection: tests / tools read the step's frontier levels)
                     drop = DropoutSpec(ps=ps, seed=seed, seed_dev=st.counter)
                     if frontier is not None:
                         frontier.build([st.ids.view(-1)])
@@ -284,8 +299,7 @@ class KGAT(nn.Module):
 
             step = self._api_step("cf", ids[0].numel(), params,
                                   (id(graph), graph.vals.data_ptr(), graph.t_vals.data_ptr(), self.cf_pruning), 3, make_bodies)
-            step.replay_forward(ids)
-            return GraphedLoss.apply(step, *params)
+            return step.submit(ids)
         u, p, n = self._ids(user_ids), self._ids(positive_item_ids), self._ids(negative_item_ids)
         return CFLossFunction.apply(
             graph, u, p, n, float(self._regularization_params[0]), self._drop_spec(),
@@ -296,27 +310,30 @@ class KGAT(nn.Module):
         self._device()
         params = [self._user_entity_embedding.weight, self._relation_embedding.weight, self._trans_matrix]
         if self._use_api_graphs(params):
-            ids = [self._ids(heads), self._ids(relations), self._ids(positive_tails), self._ids(negative_tails)]
+            ids = self._ids_fast((heads, relations, positive_tails, negative_tails))
 
             def make_bodies():
                 reg = float(self._regularization_params[1])
                 emb, rel, w = (p.detach() for p in params)
+                # static dense gradients (what autograd would hand out, model.py:204-261).  The N x d embedding gradient is
+                # all-zero outside the <= 3B rows of the previous batch, which are re-zeroed instead of clearing 41 MB a step.
+                kg_grads = [torch.zeros_like(p) for p in (emb, rel, w)]
+                prev_ids = torch.zeros(4, ids[0].numel(), dtype=torch.int64, device=emb.device)
 
                 def body_fwd(st):
                     ops.transr_forward(emb, rel, w, st.ids[0], st.ids[1], st.ids[2], st.ids[3], reg, st.loss, st.scratch)
 
                 def body_bwd(st):
-                    if st.grads is None:
-                        st.kg_grads = [torch.zeros_like(p) for p in (emb, rel, w)]
-                    for g in st.kg_grads:
-                        ops.fill_(g, 0.0)
-                    ops.transr_backward(emb, rel, w, st.ids[0], st.ids[1], st.ids[2], st.ids[3], reg, st.scratch, st.g_loss, *st.kg_grads)
-                    return st.kg_grads
+                    ops.zero_rows_(kg_grads[0], prev_ids.view(-1))
+                    ops.fill_(kg_grads[1], 0.0)
+                    ops.fill_(kg_grads[2], 0.0)
+                    ops.transr_backward(emb, rel, w, st.ids[0], st.ids[1], st.ids[2], st.ids[3], reg, st.scratch, st.g_loss, *kg_grads)
+                    prev_ids.copy_(st.ids)
+                    return kg_grads
                 return body_fwd, body_bwd
 
             step = self._api_step("kg", ids[0].numel(), params, None, 4, make_bodies)
-            step.replay_forward(ids)
-            return GraphedLoss.apply(step, *params)
+            return step.submit(ids)
         return KGLossFunction.apply(
             self._ids(heads), self._ids(relations), self._ids(positive_tails), self._ids(negative_tails),
             float(self._regularization_params[1]), self._user_entity_embedding.weight, self._relation_embedding.weight,
@@ -403,10 +420,14 @@ class KGAT(nn.Module):
         self._kg_optimizer = FusedAdam(params=self.parameters(), lr=kg_lr)
 
     def update_cf_weights(self) -> None:
-        self._cf_optimizer.step_and_zero()
+        step = self._last_step.get("cf")
+        if step is None or not step.try_fused_update(self._cf_optimizer):
+            self._cf_optimizer.step_and_zero()
 
     def update_kg_weights(self) -> None:
-        self._kg_optimizer.step_and_zero()
+        step = self._last_step.get("kg")
+        if step is None or not step.try_fused_update(self._kg_optimizer):
+            self._kg_optimizer.step_and_zero()
 
     # ------------------------------------------------------------------------------------------
     # A2: dispatch

@@ -59,7 +59,19 @@ class MultiHeadAttention(nn.Module):
         return float(self._layer_norm.eps)
 
     def forward(self, head_embedding: torch.Tensor, relation_embedding: torch.Tensor, tail_embedding: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError(
-            "kgat_b200 fuses this module into the attention-refresh kernels (KGATMode.UPDATE_ATTENTION); "
-            "it has no stand-alone forward and no PyTorch fallback."
-        )
+        """Stand-alone call with the reference's signature and output shape ``(batch, 1, kg_embedding_dim)``
+        (multi_head_attention.py:35-58).  ``head_embedding`` / ``relation_embedding`` are accepted and shape-checked but
+        cannot influence the result: the reference's softmax runs over a length-1 key axis.  Per-head
+        dropout is live in ``train()`` mode, as in the reference.  No autograd graph is recorded: in the reference these
+        weights never receive a gradient either (the refreshed matrix is assigned through ``.data``, model.py:366)."""
+        from . import ops
+
+        batch = head_embedding.size(0)
+        if tail_embedding.size(0) != batch or tail_embedding.size(-1) != self._cf_embedding_dim or relation_embedding.size(-1) != self._cf_embedding_dim:
+            raise ValueError("MultiHeadAttention.forward: (batch, cf_dim) heads / tails and a (cf_dim,) relation embedding are expected")
+        x = tail_embedding.detach().reshape(batch, self._cf_embedding_dim).to(torch.float32).contiguous()
+        p = self.dropout_p if self.training else 0.0
+        seed = int(torch.randint(0, 2**62, (1,)).item()) if p > 0 else 0
+        head_bits = getattr(self, "_injected_head_bits", None)  # test hook: uint8 [batch], bit h keeps head h
+        y = ops.mha_forward(x, self.kernel_params(), dropout_p=p, head_bits=head_bits, seed=seed, n_heads=self._head_num, eps=self.ln_eps)
+        return y.view(batch, 1, self._kg_embedding_dim)

@@ -350,6 +350,14 @@ def biagg_reduce_param_grads(partials, n_ctas, d_in, d_out, gW1, gb1, gW2, gb2, 
 # ----------------------------------------------------------------------------------------------
 
 
+def zero_rows_(table: torch.Tensor, ids: torch.Tensor):
+    """table[ids] = 0 (int64 ids; out-of-range ones ignored)."""
+    lib = _lib.load()
+    check(lib.kgat_zero_rows_i64(_ptr(table, f32, "table", True), table.shape[0], table.stride(0), table.shape[1], _ptr(ids, i64, "ids"),
+                                 ids.numel(), _stream()), "zero_rows")
+    return table
+
+
 @_timed("bpr_fwd")
 def bpr_forward(tables, users, pos, neg, reg, loss, scratch):
     lib = _lib.load()
@@ -443,6 +451,18 @@ def _mha(mha_params: dict, n_heads: int, eps: float):
     m.ln_eps = eps
     m.n_heads = n_heads
     return m, keep
+
+
+def mha_forward(x_tail, mha_params, dropout_p=0.0, head_bits=None, seed=0, offset=0, n_heads=8, eps=1e-5):
+    """MultiHeadAttention.forward's value path: LayerNorm(Wo drop(Wv x + bv) + bo) for every row of ``x_tail`` (n x d)."""
+    lib = _lib.load()
+    n, d = x_tail.shape
+    m, _keep = _mha(mha_params, n_heads, eps)
+    out = torch.empty(n, d, dtype=f32, device=x_tail.device)
+    check(lib.kgat_mha_forward(_ptr(x_tail, f32, "tail_embedding"), n, d, C.byref(m), float(dropout_p),
+                               _ptr(head_bits, u8) if head_bits is not None else None, int(seed), int(offset), _ptr(out, f32), _stream()),
+          f"mha_forward(d={d})")
+    return out
 
 
 def att_pair_scores(emb, W, pair_tail, pair_rel, mha_params, n_heads=8, eps=1e-5, want_v=False, want_score=True):
@@ -614,6 +634,15 @@ def adam_lazy_flush(param, exp_avg, exp_avg_sq, row_step, cur_step_dev, s0, tabl
     check(lib.kgat_adam_lazy_flush(_ptr(param, f32), _ptr(exp_avg, f32), _ptr(exp_avg_sq, f32), _ptr(row_step, i32), param.shape[0],
                                    param.shape[1], _ptr(cur_step_dev, i64), _ptr(s0, i64), _ptr(table, f32), _ptr(hyper, f32), _stream()),
           "adam_lazy_flush")
+
+
+def publish_loss(loss: torch.Tensor, serial_dev: torch.Tensor, ring_pinned: torch.Tensor):
+    """ring[s % len] = (s << 32) | bits(loss) with s = ++serial_dev, written by the GPU into pinned host memory (the pointer
+    of a pinned allocation is device-visible under unified addressing)."""
+    lib = _lib.load()
+    if ring_pinned.is_cuda or not ring_pinned.is_pinned() or ring_pinned.dtype != i64:
+        raise KgatLibraryError("publish_loss: the ring must be a pinned int64 host tensor")
+    check(lib.kgat_publish_loss(_ptr(loss, f32), _ptr(serial_dev, i64), ring_pinned.data_ptr(), ring_pinned.numel(), _stream()), "publish_loss")
 
 
 def sample_cf_batch(user_ptr, user_items, active_users, item_num: int, seed: int, step_dev, out):

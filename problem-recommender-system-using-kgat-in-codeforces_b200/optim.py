@@ -24,6 +24,7 @@ class FusedAdam(torch.optim.Optimizer):
         self.use_graphs = use_graphs
         self._plans: dict = {}
         self._seen: set = set()
+        self._fast: dict = {}
 
     def _graphed_step(self, group, ps) -> bool:
         if not self.use_graphs or not ps or torch.cuda.is_current_stream_capturing():
@@ -62,6 +63,67 @@ class FusedAdam(torch.optim.Optimizer):
             self.state[p]["step"] += 1
             torch.autograd.graph.increment_version(p)
         return True
+
+    # -- the API fast path (functions.GraphedStep.try_fused_update) ---------------------------------
+    def fast_plan(self, ps, grads, grads_key=None):
+        """Captured ``adam_advance + adam_apply`` over exactly ``(ps, grads)`` (static gradient buffers of a graphed step),
+        or None when it cannot be used yet: first sighting (the generic path creates the state and warms the kernels up),
+        parameters with different step counts, graphs disabled, or some other parameter of the group holds a gradient."""
+        if not self.use_graphs or torch.cuda.is_current_stream_capturing():
+            return None
+        group = self.param_groups[0]
+        n_with = 0
+        for p in group["params"]:
+            if p.grad is not None:
+                n_with += 1
+        if n_with != len(ps) or len(self.param_groups) != 1:
+            return None
+        beta1, beta2 = group["betas"]
+        if grads_key is None:
+            grads_key = tuple(g.data_ptr() for g in grads)
+        key = (id(ps[0]), len(ps), grads_key, group["lr"], beta1, beta2, group["eps"])
+        plan = self._fast.get(key)
+        if plan is None:
+            steps = {int(self.state[p]["step"]) if self.state[p] else 0 for p in ps}
+            if len(steps) != 1 or 0 in steps:
+                return None
+            if len(self._fast) > 8:
+                self._fast.clear()
+            dev = ps[0].device
+            cur = steps.pop()
+            plan = {"step_dev": torch.full((1,), cur, dtype=torch.int64, device=dev), "hyper": torch.empty(8, dtype=torch.float32, device=dev),
+                    "count": cur, "graph": torch.cuda.CUDAGraph(), "states": [self.state[p] for p in ps], "grads": list(grads),
+                    "state_ptrs": [self.state[p]["exp_avg"].data_ptr() for p in ps]}
+            params = [p.data for p in ps]
+            ms, vs = [self.state[p]["exp_avg"] for p in ps], [self.state[p]["exp_avg_sq"] for p in ps]
+            torch.cuda.synchronize()
+            with torch.cuda.graph(plan["graph"]):
+                ops.adam_advance(plan["step_dev"], group["lr"], beta1, beta2, group["eps"], plan["hyper"])
+                ops.adam_apply(params, list(grads), ms, vs, plan["hyper"])
+            plan["exec"] = plan["graph"].raw_cuda_graph_exec()
+            self._fast[key] = plan
+        states = plan["states"]
+        cur = states[0]["step"]
+        for st, ptr in zip(states, plan["state_ptrs"]):
+            if st["step"] != cur or st["exp_avg"].data_ptr() != ptr:  # load_state_dict / external steps changed the state under us
+                self._fast.clear()
+                return None
+        if plan["count"] != cur:  # someone else advanced these parameters: resynchronise the device counter
+            plan["step_dev"].fill_(cur)
+            plan["count"] = cur
+        return plan
+
+    def fast_replay(self, plan, ps) -> None:
+        from . import _lib
+        from ._lib import check
+
+        check(_lib.load().kgat_graph_launch(plan["exec"], torch.cuda.current_stream().cuda_stream), "adam graph launch")
+        plan["count"] += 1
+        for st in plan["states"]:
+            st["step"] += 1
+        torch.autograd.graph.increment_version(ps)  # the kernel wrote through raw pointers: tell autograd the data changed
+        for p in ps:
+            p.grad = None
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -4,8 +4,11 @@ there are fewer than ``B``), one uniformly drawn positive item per user and one 
 the user has not interacted with; a KG batch is ``B`` distinct heads, one uniformly drawn
 ``(relation, tail)`` of the head and one uniformly drawn node that is not a tail of ``(head,
 relation)``.  The reference draws them with per-sample Python loops on an unseeded module-level
-Generator, so parity is distributional; the RNG-stream-exact replay lives in the
-oracle (``oracle/kgat_oracle.py: sample_cf_batch / sample_kg_batch``) and is tested there.
+Generator, so for ``BatchSampler`` / ``DeviceSampler`` parity is distributional.
+``ReferenceStreamSampler`` is the bit-exact one: given the same ``numpy.random.Generator`` it returns
+the reference's batches id for id (it consumes the generator through the same call sequence; only
+the O(degree) ``in list`` membership scans are replaced by hash lookups), tested against batches
+recorded from the unmodified ``Preprocess`` under an injected seeded generator.
 
 Used by the benchmark / epoch driver to pre-sample an epoch's batches (the samplers are outside
 the measured hot path, which starts at ``model(...)``).
@@ -80,6 +83,88 @@ class BatchSampler:
                 break
             neg[bad] = rng.integers(0, n, size=int(bad.sum()))
         return heads, rels, pos, neg
+
+
+def kg_dict_reference_order(g: CKG):
+    """``(heads_in_key_order, ptr, relations, tails)`` of the reference's ``kg_dict`` (preprocess.py:248-266), vectorised.
+
+    The reference walks the Laplacians in ``adjacency_relations`` order and, inside one, scipy's COO of
+    ``(D^-1/2 A)^T D^-1/2`` -- a column-major walk of the transposed product, i.e. the merged adjacency entries in
+    (adjacency row, adjacency col) order with head = adjacency col.  Dict keys keep first-seen order; a head's list keeps
+    walk order.  Both orders feed the samplers (``rng.choice(list(keys))`` and ``positive_triplets[i]``), hence matter
+    for stream parity; verified against the recorded reference dict (tests/test_host_logic.py)."""
+    n = g.node_num
+    rel_pos = {int(r): i for i, r in enumerate(g.adjacency_relations)}
+    lap = np.asarray([rel_pos[int(r)] for r in range(max(rel_pos) + 1)], dtype=np.int64)[g.relations]
+    # edge (head, rel, tail) of Laplacian k came from adjacency entry (row = tail, col = head): walk order = (k, tail, head)
+    order = np.lexsort((g.heads, g.tails, lap))
+    heads, rels, tails = g.heads[order].astype(np.int64), g.relations[order].astype(np.int64), g.tails[order].astype(np.int64)
+    _, first = np.unique(heads, return_index=True)
+    key_heads = heads[np.sort(first)]
+    rank = np.empty(n, dtype=np.int64)
+    rank[key_heads] = np.arange(key_heads.size)
+    by_head = np.argsort(rank[heads], kind="stable")
+    counts = np.bincount(rank[heads], minlength=key_heads.size)
+    ptr = np.concatenate([[0], np.cumsum(counts)])
+    return key_heads, ptr, rels[by_head], tails[by_head]
+
+
+class ReferenceStreamSampler:
+    """Bit-exact replay of ``Preprocess.generate_cf_batch`` / ``generate_kg_batch`` (preprocess.py:328-530) for an injected
+    ``numpy.random.Generator`` (the reference's own module-level generator is unseeded).
+
+    ``interaction_dict``: ``{user: [items...]}`` in the reference's key and list order; ``kg``: either the reference-ordered
+    ``{head: [(relation, tail), ...]}`` dict or a ``CKG`` (then the order is derived, ``kg_dict_reference_order``)."""
+
+    def __init__(self, interaction_dict: dict, kg, item_num: int, node_num: int, rng: np.random.Generator, cf_batch_size: int = 256,
+                 kg_batch_size: int = 512):
+        self.rng = rng
+        self.item_num, self.node_num = int(item_num), int(node_num)
+        self.cf_batch_size, self.kg_batch_size = int(cf_batch_size), int(kg_batch_size)
+        self._users = list(interaction_dict.keys())
+        self._items = {u: list(v) for u, v in interaction_dict.items()}
+        self._item_sets = {u: set(v) for u, v in self._items.items()}
+        if isinstance(kg, CKG):
+            key_heads, ptr, rels, tails = kg_dict_reference_order(kg)
+            rt = np.stack([rels, tails], axis=1).tolist()
+            kg = {int(h): [tuple(x) for x in rt[ptr[i] : ptr[i + 1]]] for i, h in enumerate(key_heads)}
+        self._heads = list(kg.keys())
+        self._triples = {h: list(v) for h, v in kg.items()}
+        self._triple_sets = {h: set(v) for h, v in self._triples.items()}
+
+    def generate_cf_batch(self):
+        """-> (users, positive items, negative items), int64 arrays of length ``cf_batch_size`` (preprocess.py:380-415)."""
+        rng, b = self.rng, self.cf_batch_size
+        users = rng.choice(self._users, size=b, replace=b > len(self._users))
+        pos, neg = [], []
+        for u in users.tolist():
+            items = self._items[u]
+            pos.append(items[rng.integers(low=0, high=len(items), size=1)[0]])  # one draw: the set of size 1 fills at once
+            seen = self._item_sets[u]
+            while True:
+                cand = int(rng.integers(low=0, high=self.item_num, size=1)[0])
+                if cand not in seen:
+                    neg.append(cand)
+                    break
+        return users.astype(np.int64), np.asarray(pos, np.int64), np.asarray(neg, np.int64)
+
+    def generate_kg_batch(self):
+        """-> (heads, relations, positive tails, negative tails) (preprocess.py:484-530)."""
+        rng, b = self.rng, self.kg_batch_size
+        heads = rng.choice(a=self._heads, size=b, replace=b > len(self._heads)).tolist()
+        rels, pos, neg = [], [], []
+        for h in heads:
+            trip = self._triples[h]
+            r, t = trip[rng.integers(low=0, high=len(trip))]
+            rels.append(r)
+            pos.append(t)
+            seen = self._triple_sets[h]
+            while True:
+                cand = int(rng.integers(low=0, high=self.node_num, size=1)[0])
+                if (r, cand) not in seen:
+                    neg.append(cand)
+                    break
+        return np.asarray(heads, np.int64), np.asarray(rels, np.int64), np.asarray(pos, np.int64), np.asarray(neg, np.int64)
 
 
 class DeviceSampler:

@@ -99,14 +99,16 @@ def run_epoch(model: KGAT, data: EpochData, read_loss_every_step: bool = False, 
     cf_host = 0.0
     cf_block, kg_block = getattr(data, "cf_block", None), getattr(data, "kg_block", None)
     for i in range(n_cf):
-        if cf_block is not None and not cf_block.is_cuda:  # one pinned [3, B] block per step -> one H2D copy
-            u, p, n = cf_block[i].to(dev, non_blocking=True).unbind(0)
+        if cf_block is not None and not cf_block.is_cuda:
+            # one pinned [3, B] block per step, handed to the model as host views: model(...) copies it host->device itself
+            # (one cudaMemcpyAsync inside the step's launch call; the API accepts index tensors that live on the CPU)
+            u, p, n = cf_block[i].unbind(0)
             h2d += 3 * u.numel() * 8
         else:
             u, p, n = (t[i] for t in data.cf)
-        if not u.is_cuda:
-            u, p, n = u.to(dev, non_blocking=True), p.to(dev, non_blocking=True), n.to(dev, non_blocking=True)
-            h2d += 3 * u.numel() * 8
+            if not u.is_cuda:
+                u, p, n = u.to(dev, non_blocking=True), p.to(dev, non_blocking=True), n.to(dev, non_blocking=True)
+                h2d += 3 * u.numel() * 8
         loss = model(u, p, n, mode=KGATMode.TRAIN_CF)
         loss.backward()
         model.update_cf_weights()
@@ -119,13 +121,13 @@ def run_epoch(model: KGAT, data: EpochData, read_loss_every_step: bool = False, 
     kg_host = 0.0
     for i in range(n_kg):
         if kg_block is not None and not kg_block.is_cuda:
-            h, r, pt, nt = kg_block[i].to(dev, non_blocking=True).unbind(0)
+            h, r, pt, nt = kg_block[i].unbind(0)
             h2d += 4 * h.numel() * 8
         else:
             h, r, pt, nt = (t[i] for t in data.kg)
-        if not h.is_cuda:
-            h, r, pt, nt = (x.to(dev, non_blocking=True) for x in (h, r, pt, nt))
-            h2d += 4 * h.numel() * 8
+            if not h.is_cuda:
+                h, r, pt, nt = (x.to(dev, non_blocking=True) for x in (h, r, pt, nt))
+                h2d += 4 * h.numel() * 8
         loss = model(h, r, pt, nt, mode=KGATMode.TRAIN_KG)
         loss.backward()
         model.update_kg_weights()

@@ -91,3 +91,31 @@ def rel_err(a, b) -> float:
     b = torch.as_tensor(b, dtype=torch.float64).flatten().cpu()
     denom = max(float(b.abs().max()), 1e-30)
     return float((a - b).abs().max()) / denom
+
+
+# ---------------------------------------------------------------------------------------------
+# KGAT_POISON=1: every CUDA buffer handed out by torch.empty / torch.empty_like is filled with NaN (0xFF for bytes)
+# -- inside captured graphs on every replay -- so a kernel that reads memory nobody wrote (a row outside the
+# needed-row frontier, a partial a CTA skipped, ...) poisons the result instead of silently reusing stale bytes.
+# (compute-sanitizer's initcheck is closed on the GPU pool; this is the stand-in.)
+# ---------------------------------------------------------------------------------------------
+import os  # noqa: E402
+
+if os.environ.get("KGAT_POISON") == "1":
+    _empty, _empty_like = torch.empty, torch.empty_like
+
+    def _poison(t):
+        if t.is_cuda and t.numel():
+            if t.dtype == torch.float32:
+                t.fill_(float("nan"))
+            elif t.dtype == torch.uint8:
+                t.fill_(255)
+        return t
+
+    def _p_empty(*a, **k):
+        return _poison(_empty(*a, **k))
+
+    def _p_empty_like(*a, **k):
+        return _poison(_empty_like(*a, **k))
+
+    torch.empty, torch.empty_like = _p_empty, _p_empty_like

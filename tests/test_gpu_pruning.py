@@ -2,8 +2,9 @@
 row-list bi-interaction kernels).  The pruned step must equal the reference's full-graph propagation
 (model.py:165-202) on everything the loss reads and on every gradient.
 
-Tolerances: frontier bitmaps / row lists / counts bit-exact vs a numpy breadth-first restatement; the masked SpMM
-bit-exact vs the unmasked kernel on the surviving rows; pruned vs full step: loss 1e-6, gradients 2e-6 normwise
+Tolerances: frontier bitmaps / row lists / counts bit-exact vs a numpy breadth-first restatement; the row-masked SpMM
+bit-exact vs the unmasked kernel on the surviving rows (2e-6 when edges are masked too: the survivors are packed, which
+changes the fp32 summation order); pruned vs full step: loss 1e-6, gradients 2e-6 normwise
 (identical per-row arithmetic; only the summation order of the weight-gradient partials differs)."""
 
 from __future__ import annotations
@@ -112,7 +113,8 @@ def test_masked_spmm_equals_dense_on_live_rows_and_never_reads_dead_ones(kb, d, 
             out = torch.full((n, d), 7.0, device="cuda")
             mm(x, out=out, addend=z, row_mask=_bits(rmask, words), edge_mask=_bits(cmask, words))
             rm = torch.from_numpy(rmask).cuda()
-            assert torch.equal(out[rm], ref[rm])  # same kernel, same per-row order: bit-exact
+            # surviving edges are packed before the gather, so they meet the lane groups in another order: fp32 rounding only
+            assert rel_err(out[rm], ref[rm]) < 2e-6 and bool(torch.isfinite(out[rm]).all())
             assert bool((out[~rm] == 7.0).all())  # rows outside the row mask are not written
         # row mask only (the forward use): no edge filtering, no addend gating
         ref = g.matmul(xz)

@@ -137,7 +137,7 @@ def test_no_silent_cpu_path(golden_tiny):
     for args, mode in (((ids, ids, ids), KGATMode.TRAIN_CF), ((ids, ids, ids, ids), KGATMode.TRAIN_KG), ((ids, ids), KGATMode.PREDICT)):
         with pytest.raises(kgat_b200.KgatLibraryError):
             m(*args, mode=mode)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(kgat_b200.KgatLibraryError):  # the stand-alone MultiHeadAttention.forward is a kernel too: no CPU substitute
         m._multi_head_attention(torch.zeros(1, 64), torch.zeros(64), torch.zeros(1, 64))
 
 
@@ -146,3 +146,43 @@ def test_product_code_never_imports_the_oracle():
     for f in pkg.rglob("*.py"):
         src = f.read_text()
         assert "oracle" not in src.replace("kgat_oracle", "oracle") or "import oracle" not in src and "from oracle" not in src, f
+
+
+# ---------------------------------------------------------------------------------------------
+# P5: the product sampler that replays the reference's numpy stream (preprocess.py:328-530)
+# ---------------------------------------------------------------------------------------------
+def _fixture_kg_dict(g):
+    heads, ptr, rt = g["kg_dict_heads"], g["kg_dict_ptr"], g["kg_dict_rt"]
+    return {int(h): [tuple(x) for x in rt[ptr[i] : ptr[i + 1]].tolist()] for i, h in enumerate(heads)}
+
+
+def test_kg_dict_reference_order_matches_the_recorded_reference_dict(golden_pre):
+    """Key order and per-head list order of ``Preprocess._get_kg_dict`` derived from the CKG arrays (both feed the samplers)."""
+    from kgat_b200 import ckg
+    from kgat_b200.sampler import kg_dict_reference_order
+
+    g = golden_pre
+    c = ckg.build_ckg(int(g["user_num"]), int(g["entity_num"]), int(g["item_num"]), int(g["kg_relation_num"]), g["interactions"], g["triples"])
+    heads, ptr, rels, tails = kg_dict_reference_order(c)
+    np.testing.assert_array_equal(heads, g["kg_dict_heads"])
+    np.testing.assert_array_equal(ptr, g["kg_dict_ptr"])
+    np.testing.assert_array_equal(np.stack([rels, tails], axis=1), g["kg_dict_rt"])
+
+
+@pytest.mark.parametrize("kg_source", ["recorded-dict", "derived-from-ckg"])
+def test_reference_stream_sampler_is_bit_exact(golden_pre, kg_source):
+    """Same Generator, same batches as the unmodified ``Preprocess.generate_{cf,kg}_batch`` (recorded by make_golden.py)."""
+    from kgat_b200 import ckg
+    from kgat_b200.sampler import ReferenceStreamSampler
+
+    g = golden_pre
+    n_nodes = int(g["user_num"]) + int(g["entity_num"])
+    kg = _fixture_kg_dict(g)
+    if kg_source == "derived-from-ckg":
+        kg = ckg.build_ckg(int(g["user_num"]), int(g["entity_num"]), int(g["item_num"]), int(g["kg_relation_num"]), g["interactions"], g["triples"])
+    s = ReferenceStreamSampler(g.ragged("train_dict"), kg, int(g["item_num"]), n_nodes, np.random.default_rng(2024), cf_batch_size=8, kg_batch_size=16)
+    for i in range(3):
+        np.testing.assert_array_equal(np.stack(s.generate_cf_batch()), g[f"cf_batch{i}"])
+    s.rng = np.random.default_rng(2025)
+    for i in range(3):
+        np.testing.assert_array_equal(np.stack(s.generate_kg_batch()), g[f"kg_batch{i}"])
