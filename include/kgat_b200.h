@@ -107,6 +107,17 @@ int kgat_spmm_csr_masked(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_r
                          int64_t ldy, const float* Z, int64_t ldz, int32_t d, float* partials, const uint32_t* row_mask,
                          const uint32_t* edge_mask, void* stream);
 
+/* Persistent variant over a needed-row LIST (one warp strides over work items; no CTA is launched for a dead row):
+ * work = the plan's first n_heavy_tasks tasks (the chunks of the heavy rows; filtered by row_mask, required then) followed
+ * by rows[0 .. *n_rows_dev) where a light row owns the single task n_heavy_tasks + light_rank[row] (light_rank[row] < 0
+ * marks a heavy row); rows == NULL runs every task (dense output, e.g. the embedding gradient) and only masks edges.
+ * edge_mask as above (staged in shared memory when n_mask_bits / 8 <= 32 KB).  d in {16, 32, 64, 128}. */
+int kgat_spmm_csr_rows(const int32_t* tasks, int64_t n_tasks, int64_t n_heavy_tasks, const int32_t* light_rank,
+                       int32_t* heavy_rows, int64_t n_heavy, const int32_t* col_idx, const float* vals, const float* X,
+                       int64_t n_cols, int64_t ldx, float* Y, int64_t ldy, const float* Z, int64_t ldz, int32_t d,
+                       float* partials, const int32_t* rows, const int32_t* n_rows_dev, const uint32_t* row_mask,
+                       const uint32_t* edge_mask, int64_t n_mask_bits, void* stream);
+
 /* ------------------------------------------------------------------------------------------- */
 /* Needed-row frontier of a TRAIN_CF step: exact pruning of model.py:188 (the full propagation   */
 /* is re-run per mini-batch although model.py:189-191 gathers only the <= 3B batch rows)         */

@@ -62,35 +62,27 @@ __device__ __forceinline__ void finish_heavy_row(int slot, float* __restrict__ p
 // per edge group is: LDS.64 (broadcast), LDG.128 (gather of the neighbour row), 4 FFMA -- no
 // shuffles, no predicates (tail lanes carry weight 0 and a valid, already-cached address).
 // WIDE = false: the table is < 4 GiB so a 32-bit byte offset addresses it.
-// MASKED (needed-row pruning of a CF step, frontier.cu): `row_mask` (bitmap over output rows, NULL = all) skips the
-// tasks of rows nobody reads; `edge_mask` (bitmap over columns, NULL = all) drops the edges whose source row holds
-// no valid data (the surviving edges are compacted in the staging slab, so the hot loop is unchanged) and gates the
-// addend Z the same way (Z[row] counts only when row is in `edge_mask`).
+// MASKED (needed-row pruning of a CF step, frontier.cu): `edge_mask` (bitmap over columns, NULL = all; may point to a
+// shared-memory copy) drops the edges whose source row holds no valid data -- the surviving edges are compacted in the
+// staging slab, so the hot loop is unchanged -- and gates the addend Z the same way (Z[row] counts only when row is in
+// `edge_mask`).  Row masking (skipping the tasks of rows nobody reads) is done by the callers.
 template <int D, int U, bool WIDE, bool MASKED>
-__global__ void __launch_bounds__(128) spmm_task_kernel(const int4* __restrict__ tasks, int64_t n_tasks,
-                                                        const int32_t* __restrict__ col_idx, const float* __restrict__ vals,
-                                                        const float* __restrict__ X, int64_t ldx, float* __restrict__ Y,
-                                                        int64_t ldy, const float* __restrict__ Z, int64_t ldz,
-                                                        float* __restrict__ partials, int4* __restrict__ heavy, int n_heavy,
-                                                        const uint32_t* __restrict__ row_mask, const uint32_t* __restrict__ edge_mask) {
+__device__ __forceinline__ void spmm_do_task(const int4 t, int2* __restrict__ eb, const int32_t* __restrict__ col_idx,
+                                             const float* __restrict__ vals, const float* __restrict__ X, int64_t ldx,
+                                             float* __restrict__ Y, int64_t ldy, const float* __restrict__ Z, int64_t ldz,
+                                             float* __restrict__ partials, int4* __restrict__ heavy, int n_heavy,
+                                             const uint32_t* __restrict__ edge_mask, const uint32_t* __restrict__ edge_mask_global) {
     constexpr int LPE = D / 4;        // lanes per edge
     constexpr int EPW = 32 / LPE;     // edges per warp step
     constexpr int EPI = EPW * U;      // edges per unrolled iteration (divides 32)
     static_assert(32 % EPI == 0, "unroll must divide the 32-edge batch");
-    __shared__ int2 ebuf[4][32];
     const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int64_t task_id = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (task_id >= n_tasks) return;
-    const int4 t = __ldg(tasks + task_id);  // {row, begin, end, partial_slot}
-    if (MASKED && row_mask != nullptr && !((__ldg(row_mask + (t.x >> 5)) >> (t.x & 31)) & 1u)) return;
-    if (MASKED && Z != nullptr && edge_mask != nullptr && !((__ldg(edge_mask + (t.x >> 5)) >> (t.x & 31)) & 1u)) Z = nullptr;
+    if (MASKED && Z != nullptr && edge_mask_global != nullptr && !((__ldg(edge_mask_global + (t.x >> 5)) >> (t.x & 31)) & 1u)) Z = nullptr;
     const int sub = lane % LPE;
     const int slot = lane / LPE;
     const char* xb = reinterpret_cast<const char*>(X) + sub * 16;
     const uint32_t row_bytes32 = (uint32_t)(ldx * 4);
     const int64_t row_bytes64 = ldx * 4;
-    int2* eb = ebuf[wib];
 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int base = t.y;
@@ -106,7 +98,7 @@ __global__ void __launch_bounds__(128) spmm_task_kernel(const int4* __restrict__
         if (MASKED && edge_mask != nullptr) {
             // keep the edges whose source row is live, packed to the front of the slab; pad to a whole unrolled step
             // (padding entries carry weight 0 and the address of a LIVE row: dead rows may hold NaN garbage)
-            const bool live = (base + lane < t.z) && ((__ldg(edge_mask + (c >> 5)) >> (c & 31)) & 1u);
+            const bool live = (base + lane < t.z) && ((edge_mask[c >> 5] >> (c & 31)) & 1u);
             const unsigned m = __ballot_sync(kFull, live);
             cnt = __popc(m);
             const int off = WIDE ? c : (int)((uint32_t)c * row_bytes32);
@@ -161,6 +153,71 @@ __global__ void __launch_bounds__(128) spmm_task_kernel(const int4* __restrict__
         }
     }
     if (t.w >= 0) finish_heavy_row<D>(t.w, partials, heavy, n_heavy, Y, ldy, Z, ldz, lane);
+}
+
+// grid-per-task launch: one warp per task of the plan (`row_mask`: bitmap over output rows, NULL = all; the warps of
+// other rows exit at once and their Y rows stay untouched)
+template <int D, int U, bool WIDE, bool MASKED>
+__global__ void __launch_bounds__(128) spmm_task_kernel(const int4* __restrict__ tasks, int64_t n_tasks,
+                                                        const int32_t* __restrict__ col_idx, const float* __restrict__ vals,
+                                                        const float* __restrict__ X, int64_t ldx, float* __restrict__ Y,
+                                                        int64_t ldy, const float* __restrict__ Z, int64_t ldz,
+                                                        float* __restrict__ partials, int4* __restrict__ heavy, int n_heavy,
+                                                        const uint32_t* __restrict__ row_mask, const uint32_t* __restrict__ edge_mask) {
+    __shared__ int2 ebuf[4][32];
+    const int64_t task_id = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (task_id >= n_tasks) return;
+    const int4 t = __ldg(tasks + task_id);  // {row, begin, end, partial_slot}
+    if (MASKED && row_mask != nullptr && !((__ldg(row_mask + (t.x >> 5)) >> (t.x & 31)) & 1u)) return;
+    spmm_do_task<D, U, WIDE, MASKED>(t, ebuf[threadIdx.x >> 5], col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, heavy, n_heavy, edge_mask,
+                                     edge_mask);
+}
+
+// Persistent launch over a needed-row list (frontier.cu): the warps of a fixed grid stride over
+//   [0, n_heavy_tasks)            the chunk tasks of the heavy rows (first in the plan), filtered by `row_mask`, then
+//   rows[0 .. *n_rows_dev)        the listed rows: a light row owns exactly one task, n_heavy_tasks + light_rank[row]
+// (rows == NULL: every task of the plan -- the dense-output backward, which only masks edges).  No warp is launched for
+// a row outside the frontier -- the grid-per-task kernel spends ~30 us on 40 k empty CTAs when 3 % of the rows are live --
+// and the edge bitmap is staged in shared memory once per CTA when it fits, so the per-edge test is an LDS.
+constexpr int kRowsThreads = 256;
+template <int D, int U, bool WIDE>
+__global__ void __launch_bounds__(kRowsThreads, 5) spmm_rows_kernel(const int4* __restrict__ tasks, int n_tasks, int n_heavy_tasks,
+                                                                const int32_t* __restrict__ light_rank, const int32_t* __restrict__ rows,
+                                                                const int32_t* __restrict__ n_rows_dev, const int32_t* __restrict__ col_idx,
+                                                                const float* __restrict__ vals, const float* __restrict__ X, int64_t ldx,
+                                                                float* __restrict__ Y, int64_t ldy, const float* __restrict__ Z, int64_t ldz,
+                                                                float* __restrict__ partials, int4* __restrict__ heavy, int n_heavy,
+                                                                const uint32_t* __restrict__ row_mask, const uint32_t* __restrict__ edge_mask,
+                                                                int mask_words_smem) {
+    extern __shared__ __align__(16) uint32_t smem_mask[];
+    __shared__ int2 ebuf[kRowsThreads / 32][32];
+    const uint32_t* emask = edge_mask;
+    if (edge_mask != nullptr && mask_words_smem > 0) {
+        for (int i = threadIdx.x; i < mask_words_smem; i += kRowsThreads) smem_mask[i] = __ldg(edge_mask + i);
+        __syncthreads();
+        emask = smem_mask;
+    }
+    const int n_warps = (gridDim.x * kRowsThreads) >> 5;
+    const int total = rows != nullptr ? n_heavy_tasks + n_rows_dev[0] : n_tasks;
+    for (int i = (blockIdx.x * kRowsThreads + threadIdx.x) >> 5; i < total; i += n_warps) {
+        int4 t;
+        if (rows == nullptr) {
+            t = __ldg(tasks + i);
+        } else if (i < n_heavy_tasks) {
+            t = __ldg(tasks + i);
+            if (row_mask != nullptr && !((__ldg(row_mask + (t.x >> 5)) >> (t.x & 31)) & 1u)) continue;
+        } else {
+            const int lr = __ldg(light_rank + __ldg(rows + (i - n_heavy_tasks)));
+            if (lr < 0) continue;  // a heavy row: its chunks were taken above
+            t = __ldg(tasks + n_heavy_tasks + lr);
+        }
+        if (edge_mask != nullptr)
+            spmm_do_task<D, U, WIDE, true>(t, ebuf[threadIdx.x >> 5], col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, heavy, n_heavy, emask,
+                                           edge_mask);
+        else
+            spmm_do_task<D, U, WIDE, false>(t, ebuf[threadIdx.x >> 5], col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, heavy, n_heavy, nullptr,
+                                            nullptr);
+    }
 }
 
 // any d % 4 == 0, d <= 256: a whole warp per edge, up to two float4 per lane
@@ -298,4 +355,47 @@ extern "C" int kgat_spmm_csr_masked(const int32_t* tasks, int64_t n_tasks, int32
                                     const uint32_t* edge_mask, void* stream_) {
     return spmm_launch(tasks, n_tasks, heavy_rows, n_heavy, col_idx, vals, X, n_cols, ldx, Y, ldy, Z, ldz, d, partials, row_mask, edge_mask,
                        stream_);
+}
+
+extern "C" int kgat_spmm_csr_rows(const int32_t* tasks, int64_t n_tasks, int64_t n_heavy_tasks, const int32_t* light_rank,
+                                  int32_t* heavy_rows, int64_t n_heavy, const int32_t* col_idx, const float* vals, const float* X,
+                                  int64_t n_cols, int64_t ldx, float* Y, int64_t ldy, const float* Z, int64_t ldz, int32_t d, float* partials,
+                                  const int32_t* rows, const int32_t* n_rows_dev, const uint32_t* row_mask, const uint32_t* edge_mask,
+                                  int64_t n_mask_bits, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_tasks < 0 || n_heavy < 0 || n_heavy_tasks < 0 || n_heavy_tasks > n_tasks || n_tasks >= ((int64_t)1 << 31)) return KGAT_ERR_INVALID_ARGUMENT;
+    if ((ldx & 3) || (ldy & 3) || (Z && (ldz & 3))) return KGAT_ERR_INVALID_ARGUMENT;
+    if (n_heavy > 0 && partials == nullptr) return KGAT_ERR_INVALID_ARGUMENT;
+    if ((rows == nullptr) != (n_rows_dev == nullptr) || (rows != nullptr && light_rank == nullptr)) return KGAT_ERR_INVALID_ARGUMENT;
+    if (rows != nullptr && n_heavy_tasks > 0 && row_mask == nullptr) return KGAT_ERR_INVALID_ARGUMENT;
+    if (n_tasks == 0) return KGAT_OK;
+    if (n_cols <= 0) return KGAT_ERR_INVALID_ARGUMENT;
+    if (d != 16 && d != 32 && d != 64 && d != 128) return KGAT_ERR_UNSUPPORTED;
+    const bool use_wide = n_cols * ldx * 4 >= ((int64_t)1 << 32);
+    int mask_words = 0;
+    if (edge_mask != nullptr) {
+        const int64_t words = (n_mask_bits + 31) / 32;
+        if (words > 0 && words * 4 <= 32 * 1024) mask_words = (int)words;  // 1 M nodes: a 32 KB bitmap per CTA still leaves 6 CTAs / SM
+    }
+    const size_t smem = (size_t)mask_words * 4;
+    const int ctas_per_sm = 5;  // 44-46 registers x 256 threads; 5 x (32 KB bitmap + 2 KB slabs) of shared memory fit as well
+    const unsigned blocks = (unsigned)(sm_count() * ctas_per_sm);
+    const int4* t4 = reinterpret_cast<const int4*>(tasks);
+    int4* h4 = reinterpret_cast<int4*>(heavy_rows);
+#define KGAT_ROWS_ARGS t4, (int)n_tasks, (int)n_heavy_tasks, light_rank, rows, n_rows_dev, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, h4, \
+                       (int)n_heavy, row_mask, edge_mask, mask_words
+#define KGAT_ROWS_LAUNCH(DD, UU)                                                                                  \
+    do {                                                                                                          \
+        if (use_wide) spmm_rows_kernel<DD, UU, true><<<blocks, kRowsThreads, smem, stream>>>(KGAT_ROWS_ARGS);      \
+        else spmm_rows_kernel<DD, UU, false><<<blocks, kRowsThreads, smem, stream>>>(KGAT_ROWS_ARGS);              \
+    } while (0)
+    switch (d) {
+        case 16: KGAT_ROWS_LAUNCH(16, 2); break;
+        case 32: KGAT_ROWS_LAUNCH(32, 4); break;
+        case 64: KGAT_ROWS_LAUNCH(64, 4); break;
+        default: KGAT_ROWS_LAUNCH(128, 4); break;
+    }
+#undef KGAT_ROWS_LAUNCH
+#undef KGAT_ROWS_ARGS
+    return check_launch();
 }

@@ -69,7 +69,11 @@ def propagate_forward(graph: AttentiveGraph, e0: torch.Tensor, layers, drop: Dro
     for l, (w1, b1, w2, b2) in enumerate(layers):
         x = st.tables[-1]
         d_out = w1.shape[0]
-        side = graph.matmul(x, out=_buf(n, x.shape[1], device=dev), row_mask=None if frontier is None else frontier.mask(l + 1))
+        if frontier is None:
+            side = graph.matmul(x, out=_buf(n, x.shape[1], device=dev))
+        else:
+            side = graph.matmul(x, out=_buf(n, x.shape[1], device=dev), row_mask=frontier.mask(l + 1), rows=frontier.rows(l + 1),
+                                n_rows_dev=frontier.count(l + 1))
         out = _buf(n, d_out, device=dev)
         inv = _buf(n, device=dev) if save else None
         flags = _buf(n, d_out, dtype=torch.uint8, device=dev) if save else None
@@ -126,8 +130,8 @@ def propagate_backward(graph: AttentiveGraph, st: PropState, layers, g_last: tor
         if frontier is None:
             g_prev = graph.matmul_t(g_s, addend=g_e)  # dL/dE_{l-1} = g_E(direct) + A^T g_S
         else:
-            g_prev = graph.matmul_t(g_s, out=_buf(n, d_in, device=dev), addend=g_e, row_mask=frontier.mask(l - 1) if l > 1 else None,
-                                    edge_mask=frontier.mask(l))
+            below = {"row_mask": frontier.mask(l - 1), "rows": frontier.rows(l - 1), "n_rows_dev": frontier.count(l - 1)} if l > 1 else {}
+            g_prev = graph.matmul_t(g_s, out=_buf(n, d_in, device=dev), addend=g_e, edge_mask=frontier.mask(l), **below)
         inject(l - 1, g_prev)
         g = g_prev
     return g, param_grads

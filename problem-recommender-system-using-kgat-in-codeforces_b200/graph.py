@@ -33,7 +33,8 @@ class SpmmPlan:
     heavy: torch.Tensor  # int32 [n_heavy, 4] = row, first_slot, n_chunks, 0
     n_tasks: int
     n_heavy: int
-    n_partials: int
+    n_partials: int  # = number of heavy-chunk tasks; they come first in `tasks`
+    light_rank: torch.Tensor | None = None  # int32 [n_rows]: a light row's task is n_partials + light_rank[row]; -1 = heavy row
 
 
 def spmm_plan_host(row_ptr: np.ndarray, chunk: int = DEFAULT_CHUNK):
@@ -66,14 +67,18 @@ def spmm_plan_host(row_ptr: np.ndarray, chunk: int = DEFAULT_CHUNK):
 
 
 def make_plan(row_ptr: torch.Tensor, chunk: int = DEFAULT_CHUNK) -> SpmmPlan:
-    tasks, heavy, n_partials = spmm_plan_host(row_ptr.cpu().numpy(), chunk)
+    rp = row_ptr.cpu().numpy()
+    tasks, heavy, n_partials = spmm_plan_host(rp, chunk)
     dev = row_ptr.device
+    light = np.diff(rp.astype(np.int64)) <= chunk  # light rows follow the heavy chunks in row order (spmm_plan_host)
+    light_rank = np.where(light, np.cumsum(light) - 1, -1).astype(np.int32)
     return SpmmPlan(
         tasks=torch.from_numpy(tasks).to(dev).contiguous(),
         heavy=torch.from_numpy(heavy).to(dev).contiguous(),
         n_tasks=int(tasks.shape[0]),
         n_heavy=int(heavy.shape[0]),
         n_partials=n_partials,
+        light_rank=torch.from_numpy(light_rank).to(dev).contiguous(),
     )
 
 
@@ -141,17 +146,22 @@ class AttentiveGraph:
         return self._partials
 
     # -- ops ----------------------------------------------------------------------------------
-    def matmul(self, x: torch.Tensor, out: torch.Tensor | None = None, addend: torch.Tensor | None = None, row_mask=None, edge_mask=None):
-        """out = A @ x (+ addend)   -- reference aggregator.py:54.  ``row_mask`` / ``edge_mask``: frontier bitmaps (ops.spmm)."""
+    def matmul(self, x: torch.Tensor, out: torch.Tensor | None = None, addend: torch.Tensor | None = None, row_mask=None, edge_mask=None,
+               rows=None, n_rows_dev=None):
+        """out = A @ x (+ addend)   -- reference aggregator.py:54.  ``row_mask`` / ``edge_mask`` / ``rows``: a frontier level's
+        bitmap(s) and row list (ops.spmm)."""
         if out is None:
             out = torch.empty(self.n, x.shape[1], dtype=torch.float32, device=x.device)
-        return ops.spmm(self.plan, self.col_idx, self.vals, x, out, addend, self.partials(x.shape[1]), row_mask=row_mask, edge_mask=edge_mask)
+        return ops.spmm(self.plan, self.col_idx, self.vals, x, out, addend, self.partials(x.shape[1]), row_mask=row_mask, edge_mask=edge_mask,
+                        rows=rows, n_rows_dev=n_rows_dev)
 
-    def matmul_t(self, x: torch.Tensor, out: torch.Tensor | None = None, addend: torch.Tensor | None = None, row_mask=None, edge_mask=None):
+    def matmul_t(self, x: torch.Tensor, out: torch.Tensor | None = None, addend: torch.Tensor | None = None, row_mask=None, edge_mask=None,
+                 rows=None, n_rows_dev=None):
         """out = A^T @ x (+ addend)   -- autograd backward of aggregator.py:54"""
         if out is None:
             out = torch.empty(self.n, x.shape[1], dtype=torch.float32, device=x.device)
-        return ops.spmm(self.t_plan, self.t_idx, self.t_vals, x, out, addend, self.partials(x.shape[1]), row_mask=row_mask, edge_mask=edge_mask)
+        return ops.spmm(self.t_plan, self.t_idx, self.t_vals, x, out, addend, self.partials(x.shape[1]), row_mask=row_mask, edge_mask=edge_mask,
+                        rows=rows, n_rows_dev=n_rows_dev)
 
     # -- the reference-facing view --------------------------------------------------------------
     def indices64(self) -> torch.Tensor:

@@ -186,15 +186,19 @@ def fill_(t: torch.Tensor, value: float = 0.0):
 # ----------------------------------------------------------------------------------------------
 
 
-def _spmm_name(plan, col_idx, vals, x, out, addend=None, partials=None, row_mask=None, edge_mask=None):
-    return f"spmm{'T' if addend is not None else ''}_d{x.shape[1]}{'_pruned' if (row_mask is not None or edge_mask is not None) else ''}"
+def _spmm_name(plan, col_idx, vals, x, out, addend=None, partials=None, row_mask=None, edge_mask=None, rows=None, n_rows_dev=None):
+    kind = "_rows" if rows is not None else ("_edges" if edge_mask is not None else ("_pruned" if row_mask is not None else ""))
+    return f"spmm{'T' if addend is not None else ''}_d{x.shape[1]}{kind}"
 
 
 @_timed(_spmm_name)
 def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.Tensor | None = None, partials=None,
-         row_mask: torch.Tensor | None = None, edge_mask: torch.Tensor | None = None):
+         row_mask: torch.Tensor | None = None, edge_mask: torch.Tensor | None = None, rows: torch.Tensor | None = None,
+         n_rows_dev: torch.Tensor | None = None):
     """out = A @ x (+ addend); ``plan`` is a graph.SpmmPlan.  ``row_mask`` / ``edge_mask``: node bitmaps of a
-    ``frontier.Frontier`` level (only the rows in ``row_mask`` are computed; edges / addend rows outside ``edge_mask`` are dropped)."""
+    ``frontier.Frontier`` level (only the rows in ``row_mask`` are computed; edges / addend rows outside ``edge_mask`` are
+    dropped).  With the level's row list (``rows``, ``n_rows_dev``; needs ``row_mask`` too) or with an ``edge_mask`` alone the
+    persistent row-list kernel runs; a ``row_mask`` without a list uses the grid-per-task kernel."""
     lib = _lib.load()
     d = x.shape[1]
     if plan.n_heavy > 0:
@@ -207,7 +211,24 @@ def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.
         _ptr(addend, f32, "addend", True) if addend is not None else None, addend.stride(0) if addend is not None else 0, d,
         _ptr(partials, f32) if partials is not None else None,
     )
-    if row_mask is None and edge_mask is None:
+    use_rows_kernel = (rows is not None or (edge_mask is not None and row_mask is None)) and d in (16, 32, 64, 128)
+    if use_rows_kernel:
+        n_bits = max(x.shape[0], out.shape[0])
+        for m in (row_mask, edge_mask):
+            if m is not None and m.numel() * 32 < n_bits:
+                raise KgatLibraryError("spmm: node bitmap too small")
+        if rows is not None and (row_mask is None or n_rows_dev is None or plan.light_rank is None):
+            raise KgatLibraryError("spmm: a row list needs its bitmap, its device-side count and a plan with light_rank")
+        check(
+            lib.kgat_spmm_csr_rows(
+                _ptr(plan.tasks, i32), plan.n_tasks, plan.n_partials, _ptr(plan.light_rank, i32) if plan.light_rank is not None else None,
+                _ptr(plan.heavy, i32) if plan.n_heavy else None, plan.n_heavy, *args[4:],
+                _ptr(rows, i32) if rows is not None else None, _ptr(n_rows_dev, i32) if rows is not None else None,
+                _ptr(row_mask, i32) if row_mask is not None else None, _ptr(edge_mask, i32) if edge_mask is not None else None, n_bits, _stream(),
+            ),
+            "spmm_csr_rows",
+        )
+    elif row_mask is None and edge_mask is None:
         check(lib.kgat_spmm_csr(*args, _stream()), "spmm_csr")
     else:
         words = (max(x.shape[0], out.shape[0]) + 31) // 32

@@ -116,6 +116,25 @@ def test_masked_spmm_equals_dense_on_live_rows_and_never_reads_dead_ones(kb, d, 
             # surviving edges are packed before the gather, so they meet the lane groups in another order: fp32 rounding only
             assert rel_err(out[rm], ref[rm]) < 2e-6 and bool(torch.isfinite(out[rm]).all())
             assert bool((out[~rm] == 7.0).all())  # rows outside the row mask are not written
+        # the persistent row-list kernel: same masks plus the ascending list of the live rows and a device-side count
+        listed = np.nonzero(rmask)[0].astype(np.int32)
+        rows = torch.zeros(n, dtype=torch.int32, device="cuda")
+        rows[: listed.size] = torch.from_numpy(listed).cuda()
+        cnt = torch.tensor([listed.size], dtype=torch.int32, device="cuda")
+        rm = torch.from_numpy(rmask).cuda()
+        for t in (False, True):
+            mm = g.matmul_t if t else g.matmul
+            ref = mm(xz, addend=zz)
+            out = torch.full((n, d), 7.0, device="cuda")
+            mm(x, out=out, addend=z, row_mask=_bits(rmask, words), edge_mask=_bits(cmask, words), rows=rows, n_rows_dev=cnt)
+            assert rel_err(out[rm], ref[rm]) < 2e-6 and bool(torch.isfinite(out[rm]).all())
+            assert bool((out[~rm] == 7.0).all())
+            out = torch.full((n, d), 7.0, device="cuda")
+            mm(xz, out=out, row_mask=_bits(rmask, words), rows=rows, n_rows_dev=cnt)  # forward use: rows only
+            assert torch.equal(out[rm], mm(xz)[rm]) and bool((out[~rm] == 7.0).all())
+            out = torch.full((n, d), 7.0, device="cuda")
+            mm(x, out=out, addend=z, edge_mask=_bits(cmask, words))  # dense output, masked sources (the embedding gradient)
+            assert rel_err(out, ref) < 2e-6 and bool(torch.isfinite(out).all())
         # row mask only (the forward use): no edge filtering, no addend gating
         ref = g.matmul(xz)
         out = torch.full((n, d), 7.0, device="cuda")
