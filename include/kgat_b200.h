@@ -118,6 +118,15 @@ int kgat_spmm_csr_rows(const int32_t* tasks, int64_t n_tasks, int64_t n_heavy_ta
                        float* partials, const int32_t* rows, const int32_t* n_rows_dev, const uint32_t* row_mask,
                        const uint32_t* edge_mask, int64_t n_mask_bits, void* stream);
 
+/* Transposed product as a scatter over a needed-row list:  Y[c] += A[r, c] * G[r] for the *n_rows_dev listed rows r and
+ * their edges, and Y[r] += Z[r] (Z nullable) -- 128-bit vector reductions, so Y's destination rows must be zero on entry
+ * (kgat_frontier_zero_rows) and the fp32 summation order is not fixed.  tasks / n_heavy_tasks / light_rank / row_mask: the
+ * plan of A (not of its transpose) and the list's bitmap, as in kgat_spmm_csr_rows.  d in {16, 32, 64, 128}. */
+int kgat_spmm_scatter_rows(const int32_t* tasks, int64_t n_heavy_tasks, const int32_t* light_rank, const int32_t* rows,
+                           const int32_t* n_rows_dev, int64_t max_rows, const uint32_t* row_mask, const int32_t* col_idx,
+                           const float* vals, const float* G, int64_t ldg, const float* Z, int64_t ldz, float* Y, int64_t ldy,
+                           int32_t d, void* stream);
+
 /* ------------------------------------------------------------------------------------------- */
 /* Needed-row frontier of a TRAIN_CF step: exact pruning of model.py:188 (the full propagation   */
 /* is re-run per mini-batch although model.py:189-191 gathers only the <= 3B batch rows)         */
@@ -125,15 +134,22 @@ int kgat_spmm_csr_rows(const int32_t* tasks, int64_t n_tasks, int64_t n_heavy_ta
 /* F_L = {batch ids}, F_{l-1} = F_l U cols(A[F_l, :]): layer l is computed for the rows of F_l only; every row outside
  * has an exactly-zero gradient and is never read, so loss and gradients equal the reference's.  A level is a bitmap
  * over the nodes plus the ascending list of its rows with a device-side count (everything stream-ordered). */
-/* bitmap |= {ids64[i]}; ids outside [0, n_nodes) are skipped and counted in *bad_count_dev (nullable) */
-int kgat_frontier_mark_ids(const int64_t* ids64, int64_t n_ids, int64_t n_nodes, uint32_t* bitmap, int32_t* bad_count_dev,
+/* Membership is collected in `flags`, one BYTE per node (32 * ceil(n_nodes / 32) bytes, 16-byte aligned, all zero between
+ * builds) with plain idempotent stores, then folded into the level's bitmap by kgat_frontier_list, which clears the flags. */
+/* flags[ids64[i]] = 1; ids outside [0, n_nodes) are skipped and counted in *bad_count_dev (nullable) */
+int kgat_frontier_mark_ids(const int64_t* ids64, int64_t n_ids, int64_t n_nodes, uint8_t* flags, int32_t* bad_count_dev,
                            void* stream);
-/* bitmap_out |= {r} U cols(A[r, :]) for the *count_dev rows listed in `rows` (max_rows sizes the grid) */
-int kgat_frontier_expand(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* rows, const int32_t* count_dev,
-                         int64_t max_rows, uint32_t* bitmap_out, void* stream);
-/* rows[0 .. *count_dev) = ascending node ids of the set bits; scratch: kgat_frontier_scratch_ints(n_nodes) int32 */
+/* flags[r] = flags[c] = 1 for the *count_dev rows r listed in `rows` (their bitmap: level_bitmap) and every column c of
+ * A[r, :].  Work items are the SpMM plan's tasks (kgat_spmm_csr_rows: the first n_heavy_tasks chunk tasks filtered by
+ * level_bitmap, then the listed light rows through light_rank), so hub rows are spread over many warps. */
+int kgat_frontier_expand(const int32_t* tasks, int64_t n_heavy_tasks, const int32_t* light_rank, const int32_t* col_idx,
+                         const int32_t* rows, const int32_t* count_dev, int64_t max_rows, const uint32_t* level_bitmap,
+                         uint8_t* flags, void* stream);
+/* bitmap <- flags (every word written; flags cleared); rows[0 .. *count_dev) = ascending node ids of the set bits;
+ * scratch: kgat_frontier_scratch_ints(n_nodes) int32 */
 int64_t kgat_frontier_scratch_ints(int64_t n_nodes);
-int kgat_frontier_list(const uint32_t* bitmap, int64_t n_nodes, int32_t* scratch, int32_t* rows, int32_t* count_dev, void* stream);
+int kgat_frontier_list(uint8_t* flags, uint32_t* bitmap, int64_t n_nodes, int32_t* scratch, int32_t* rows, int32_t* count_dev,
+                       void* stream);
 /* T[rows[i], 0:d] = 0 for i < *count_dev (gradient rows of the last table before the BPR scatter) */
 int kgat_frontier_zero_rows(float* T, int64_t ld, int32_t d, const int32_t* rows, const int32_t* count_dev, int64_t max_rows,
                             void* stream);

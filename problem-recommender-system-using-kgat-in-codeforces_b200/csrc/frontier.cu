@@ -8,6 +8,9 @@
 // A frontier level is a bitmap over the nodes (one bit per node, tested by the masked SpMM, spmm.cu) plus the
 // ascending list of its rows (enumerated by the bi-interaction kernels).  All of it is stream-ordered device
 // work with device-side counts, so a whole step still replays as one CUDA graph.
+// Membership is collected in a BYTE-per-node flag array with plain stores (idempotent, so no atomics: 700 k edge
+// visits at the Amazon-book shape would otherwise serialise on the ~160 cache lines of a 20 KB bitmap -- measured
+// 98 us with atomicOr, see profiles/) and folded into the bitmap by the listing pass, which also clears the flags.
 #include "common.cuh"
 
 namespace kgat {
@@ -21,8 +24,8 @@ __device__ __forceinline__ int warp_sum_i(int v) {
     return v;
 }
 
-// bitmap |= {ids}; ids outside [0, n_nodes) are counted in *bad and skipped (the reference raises an IndexError)
-__global__ void frontier_mark_kernel(const int64_t* __restrict__ ids, int64_t n_ids, int64_t n_nodes, uint32_t* __restrict__ bitmap,
+// flags[id] = 1; ids outside [0, n_nodes) are counted in *bad and skipped (the reference raises an IndexError)
+__global__ void frontier_mark_kernel(const int64_t* __restrict__ ids, int64_t n_ids, int64_t n_nodes, uint8_t* __restrict__ flags,
                                      int32_t* __restrict__ bad) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_ids) return;
@@ -31,37 +34,63 @@ __global__ void frontier_mark_kernel(const int64_t* __restrict__ ids, int64_t n_
         if (bad != nullptr) atomicAdd(bad, 1);
         return;
     }
-    atomicOr(bitmap + (id >> 5), 1u << (id & 31));
+    flags[id] = 1;
 }
 
-// out |= {r} U cols(A[r, :]) for every listed row r (one warp per row, persistent grid, device-side count)
-__global__ void __launch_bounds__(128) frontier_expand_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+// flags[r] = flags[c] = 1 for every listed row r and every column c of A[r, :].  Work items are the SpMM plan's tasks
+// (<= chunk edges each, graph.py), enumerated like the row-list SpMM does: the chunk tasks of the heavy rows first
+// (filtered by the level's bitmap), then one task per listed light row -- so a hub row does not serialise on one warp.
+__global__ void __launch_bounds__(128) frontier_expand_kernel(const int4* __restrict__ tasks, int n_heavy_tasks,
+                                                              const int32_t* __restrict__ light_rank, const int32_t* __restrict__ col_idx,
                                                               const int32_t* __restrict__ rows, const int32_t* __restrict__ cnt_dev,
-                                                              uint32_t* __restrict__ out) {
+                                                              const uint32_t* __restrict__ level_mask, uint8_t* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    const int cnt = cnt_dev[0];
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < cnt; i += n_warps) {
-        const int r = rows[i];
-        if (lane == 0) {
-            const uint32_t bit = 1u << (r & 31);
-            if (!(out[r >> 5] & bit)) atomicOr(out + (r >> 5), bit);
+    const int total = n_heavy_tasks + cnt_dev[0];
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < total; i += n_warps) {
+        int4 t;
+        if (i < n_heavy_tasks) {
+            t = __ldg(tasks + i);
+            if (!((__ldg(level_mask + (t.x >> 5)) >> (t.x & 31)) & 1u)) continue;
+        } else {
+            const int lr = __ldg(light_rank + __ldg(rows + (i - n_heavy_tasks)));
+            if (lr < 0) continue;
+            t = __ldg(tasks + n_heavy_tasks + lr);
         }
-        const int b = row_ptr[r], e = row_ptr[r + 1];
-        for (int k = b + lane; k < e; k += 32) {
+        if (lane == 0) flags[t.x] = 1;
+        for (int k = t.y + lane; k < t.z; k += 32) {
             const int c = __ldg(col_idx + k);
-            const uint32_t bit = 1u << (c & 31);
-            // test before set: hub columns are hit thousands of times, one atomic is enough
-            if (!(__ldcg(out + (c >> 5)) & bit)) atomicOr(out + (c >> 5), bit);
+            // test before set: hub columns are hit thousands of times (a stale 0 only costs a redundant store of 1)
+            if (!__ldcg(flags + c)) flags[c] = 1;
         }
     }
 }
 
-__global__ void __launch_bounds__(kListBlock) frontier_count_kernel(const uint32_t* __restrict__ bitmap, int64_t n_words,
-                                                                   int32_t* __restrict__ block_total) {
+// bitmap word w <- flags[32 w .. 32 w + 32) (and the flags are cleared for the next build); block totals of the set bits
+__global__ void __launch_bounds__(kListBlock) frontier_count_kernel(uint8_t* __restrict__ flags, uint32_t* __restrict__ bitmap,
+                                                                   int64_t n_words, int32_t* __restrict__ block_total) {
     __shared__ int sh[kListBlock / 32];
     const int64_t w = blockIdx.x * (int64_t)kListBlock + threadIdx.x;
-    int c = w < n_words ? __popc(bitmap[w]) : 0;
+    int c = 0;
+    if (w < n_words) {
+        uint4* f4 = reinterpret_cast<uint4*>(flags + w * 32);
+        const uint4 a = f4[0], b = f4[1];
+        const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t bits = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            // byte j of v[q] non-zero -> bit 4 q + j
+            const uint32_t x = v[q];
+            bits |= ((x & 0xffu) ? 1u : 0u) << (4 * q) | ((x & 0xff00u) ? 1u : 0u) << (4 * q + 1) | ((x & 0xff0000u) ? 1u : 0u) << (4 * q + 2) |
+                    ((x & 0xff000000u) ? 1u : 0u) << (4 * q + 3);
+        }
+        bitmap[w] = bits;
+        if (bits) {
+            f4[0] = make_uint4(0u, 0u, 0u, 0u);
+            f4[1] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        c = __popc(bits);
+    }
     c = warp_sum_i(c);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
     __syncthreads();
@@ -138,28 +167,33 @@ int64_t kgat_frontier_scratch_ints(int64_t n_nodes) {
     return (n_words + kListBlock - 1) / kListBlock + 1;
 }
 
-int kgat_frontier_mark_ids(const int64_t* ids64, int64_t n_ids, int64_t n_nodes, uint32_t* bitmap, int32_t* bad_count_dev, void* stream) {
-    if (n_ids < 0 || n_nodes <= 0 || !bitmap) return KGAT_ERR_INVALID_ARGUMENT;
+int kgat_frontier_mark_ids(const int64_t* ids64, int64_t n_ids, int64_t n_nodes, uint8_t* flags, int32_t* bad_count_dev, void* stream) {
+    if (n_ids < 0 || n_nodes <= 0 || !flags) return KGAT_ERR_INVALID_ARGUMENT;
     if (n_ids == 0) return KGAT_OK;
-    frontier_mark_kernel<<<(unsigned)((n_ids + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ids64, n_ids, n_nodes, bitmap, bad_count_dev);
+    frontier_mark_kernel<<<(unsigned)((n_ids + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ids64, n_ids, n_nodes, flags, bad_count_dev);
     return check_launch();
 }
 
-int kgat_frontier_expand(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* rows, const int32_t* count_dev, int64_t max_rows,
-                         uint32_t* bitmap_out, void* stream) {
-    if (!row_ptr || !col_idx || !rows || !count_dev || !bitmap_out || max_rows <= 0) return KGAT_ERR_INVALID_ARGUMENT;
-    int64_t ctas = (max_rows + 3) / 4;
+int kgat_frontier_expand(const int32_t* tasks, int64_t n_heavy_tasks, const int32_t* light_rank, const int32_t* col_idx,
+                         const int32_t* rows, const int32_t* count_dev, int64_t max_rows, const uint32_t* level_bitmap, uint8_t* flags,
+                         void* stream) {
+    if (!tasks || !light_rank || !col_idx || !rows || !count_dev || !flags || max_rows <= 0 || n_heavy_tasks < 0 ||
+        (n_heavy_tasks > 0 && !level_bitmap) || n_heavy_tasks >= ((int64_t)1 << 30))
+        return KGAT_ERR_INVALID_ARGUMENT;
+    int64_t ctas = (max_rows + n_heavy_tasks + 3) / 4;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (ctas > cap) ctas = cap;
-    frontier_expand_kernel<<<(unsigned)ctas, 128, 0, (cudaStream_t)stream>>>(row_ptr, col_idx, rows, count_dev, bitmap_out);
+    frontier_expand_kernel<<<(unsigned)ctas, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int4*>(tasks), (int)n_heavy_tasks, light_rank,
+                                                                             col_idx, rows, count_dev, level_bitmap, flags);
     return check_launch();
 }
 
-int kgat_frontier_list(const uint32_t* bitmap, int64_t n_nodes, int32_t* scratch, int32_t* rows, int32_t* count_dev, void* stream) {
-    if (!bitmap || !scratch || !rows || !count_dev || n_nodes <= 0 || n_nodes >= ((int64_t)1 << 31)) return KGAT_ERR_INVALID_ARGUMENT;
+int kgat_frontier_list(uint8_t* flags, uint32_t* bitmap, int64_t n_nodes, int32_t* scratch, int32_t* rows, int32_t* count_dev, void* stream) {
+    if (!flags || !bitmap || !scratch || !rows || !count_dev || n_nodes <= 0 || n_nodes >= ((int64_t)1 << 31)) return KGAT_ERR_INVALID_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(flags) & 15) return KGAT_ERR_INVALID_ARGUMENT;
     const int64_t n_words = (n_nodes + 31) / 32;
     const unsigned blocks = (unsigned)((n_words + kListBlock - 1) / kListBlock);
-    frontier_count_kernel<<<blocks, kListBlock, 0, (cudaStream_t)stream>>>(bitmap, n_words, scratch);
+    frontier_count_kernel<<<blocks, kListBlock, 0, (cudaStream_t)stream>>>(flags, bitmap, n_words, scratch);
     frontier_write_kernel<<<blocks, kListBlock, 0, (cudaStream_t)stream>>>(bitmap, n_words, scratch, rows, count_dev);
     return check_launch();
 }

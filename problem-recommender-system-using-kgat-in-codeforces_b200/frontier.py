@@ -34,11 +34,17 @@ class Frontier:
         words = (self.n + 31) // 32
         self.words = (words + 3) // 4 * 4  # keep every level's bitmap 16-byte aligned
         self.bitmaps = torch.zeros(self.n_layers, self.words, dtype=torch.int32, device=dev)
+        # membership scratch of the level being built: one byte per node, written with plain stores by the mark / expand
+        # kernels, folded into the level's bitmap (and cleared) by the listing pass
+        self.flags = torch.zeros(self.words * 32, dtype=torch.uint8, device=dev)
         self.caps = [self.n] * (self.n_layers - 1) + [min(self.n, int(max_ids))]
         self.row_lists = [torch.zeros(c, dtype=torch.int32, device=dev) for c in self.caps]
         self.counts = torch.zeros(self.n_layers, dtype=torch.int32, device=dev)
         self.scratch = torch.zeros(ops.frontier_scratch_ints(self.n), dtype=torch.int32, device=dev)
         self.bad_ids = torch.zeros(1, dtype=torch.int32, device=dev)  # ids outside [0, n) seen so far (skipped)
+        # backward of the upper (sparse) layers: scatter the edges of the few source rows (fp32 vector reductions) instead of
+        # gathering over every destination row; False = the deterministic masked gather everywhere
+        self.scatter_backward = True
         self.serial = 0  # bumped by every user that (re)builds it, so a late backward can tell its levels were overwritten
 
     # level l in 1 .. L
@@ -58,13 +64,12 @@ class Frontier:
         """(Re)build every level from the batch ids (int64 device tensors).  Stream-ordered, no host sync."""
         g = self.graph
         top = self.n_layers
-        self.bitmaps.zero_()
         for ids in id_tensors:
-            ops.frontier_mark_ids(ids, self.n, self.mask(top), self.bad_ids)
-        ops.frontier_list(self.mask(top), self.n, self.scratch, self.rows(top), self.count(top))
+            ops.frontier_mark_ids(ids, self.n, self.flags, self.bad_ids)
+        ops.frontier_list(self.flags, self.mask(top), self.n, self.scratch, self.rows(top), self.count(top))
         for level in range(top - 1, 0, -1):
-            ops.frontier_expand(g.row_ptr, g.col_idx, self.rows(level + 1), self.count(level + 1), self.cap(level + 1), self.mask(level))
-            ops.frontier_list(self.mask(level), self.n, self.scratch, self.rows(level), self.count(level))
+            ops.frontier_expand(g.plan, g.col_idx, self.rows(level + 1), self.count(level + 1), self.cap(level + 1), self.mask(level + 1), self.flags)
+            ops.frontier_list(self.flags, self.mask(level), self.n, self.scratch, self.rows(level), self.count(level))
         return self
 
     def check_ids(self) -> None:

@@ -129,6 +129,13 @@ def propagate_backward(graph: AttentiveGraph, st: PropState, layers, g_last: tor
         param_grads[l - 1] = (gw1, gb1, gw2, gb2)
         if frontier is None:
             g_prev = graph.matmul_t(g_s, addend=g_e)  # dL/dE_{l-1} = g_E(direct) + A^T g_S
+        elif l > 1 and frontier.scatter_backward:
+            # few gradient sources (level l) feeding the rows of level l-1: scatter their edges instead of streaming every
+            # edge of every destination row past the source bitmap
+            g_prev = _buf(n, d_in, device=dev)
+            ops.frontier_zero_rows(g_prev, frontier.rows(l - 1), frontier.count(l - 1), frontier.cap(l - 1))
+            ops.spmm_scatter_rows(graph.plan, graph.col_idx, graph.vals, g_s, g_prev, frontier.rows(l), frontier.count(l), frontier.cap(l),
+                                  frontier.mask(l), addend=g_e)
         else:
             below = {"row_mask": frontier.mask(l - 1), "rows": frontier.rows(l - 1), "n_rows_dev": frontier.count(l - 1)} if l > 1 else {}
             g_prev = graph.matmul_t(g_s, out=_buf(n, d_in, device=dev), addend=g_e, edge_mask=frontier.mask(l), **below)

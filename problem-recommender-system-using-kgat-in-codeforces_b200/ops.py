@@ -240,6 +240,24 @@ def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.
     return out
 
 
+@_timed(lambda plan, col_idx, vals, g, out, *a, **k: f"spmmT_d{g.shape[1]}_scatter")
+def spmm_scatter_rows(plan, col_idx, vals, g: torch.Tensor, out: torch.Tensor, rows, n_rows_dev, max_rows: int, row_mask, addend=None):
+    """out[c] += A[r, c] * g[r] over the listed rows r (and out[r] += addend[r]); ``plan`` / ``col_idx`` / ``vals`` of A itself.
+    The destination rows of ``out`` must have been zeroed (frontier_zero_rows)."""
+    lib = _lib.load()
+    d = g.shape[1]
+    check(
+        lib.kgat_spmm_scatter_rows(
+            _ptr(plan.tasks, i32), plan.n_partials, _ptr(plan.light_rank, i32), _ptr(rows, i32), _ptr(n_rows_dev, i32), int(max_rows),
+            _ptr(row_mask, i32), _ptr(col_idx, i32), _ptr(vals, f32), _ptr(g, f32, "g", True), g.stride(0),
+            _ptr(addend, f32, "addend", True) if addend is not None else None, addend.stride(0) if addend is not None else 0,
+            _ptr(out, f32, "out", True), out.stride(0), d, _stream(),
+        ),
+        "spmm_scatter_rows",
+    )
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # needed-row frontier of a TRAIN_CF step (csrc/frontier.cu)
 # ----------------------------------------------------------------------------------------------
@@ -249,26 +267,29 @@ def frontier_scratch_ints(n_nodes: int) -> int:
     return int(_lib.load().kgat_frontier_scratch_ints(int(n_nodes)))
 
 
-def frontier_mark_ids(ids: torch.Tensor, n_nodes: int, bitmap: torch.Tensor, bad_count: torch.Tensor | None = None):
+def frontier_mark_ids(ids: torch.Tensor, n_nodes: int, flags: torch.Tensor, bad_count: torch.Tensor | None = None):
+    """flags (uint8, one byte per node, zero between builds)[ids] = 1"""
     lib = _lib.load()
-    if bitmap.numel() * 32 < n_nodes:
-        raise KgatLibraryError("frontier_mark_ids: bitmap too small")
-    check(lib.kgat_frontier_mark_ids(_ptr(ids, i64, "ids"), ids.numel(), int(n_nodes), _ptr(bitmap, i32),
+    if flags.numel() < (n_nodes + 31) // 32 * 32:
+        raise KgatLibraryError("frontier_mark_ids: flag array too small")
+    check(lib.kgat_frontier_mark_ids(_ptr(ids, i64, "ids"), ids.numel(), int(n_nodes), _ptr(flags, u8),
                                      _ptr(bad_count, i32) if bad_count is not None else None, _stream()), "frontier_mark_ids")
 
 
-def frontier_expand(row_ptr, col_idx, rows, count_dev, max_rows: int, bitmap_out):
+def frontier_expand(plan, col_idx, rows, count_dev, max_rows: int, level_bitmap, flags):
+    """flags[r] = flags[c] = 1 for the listed rows r and the columns c of their CSR rows; ``plan``: the graph's SpmmPlan."""
     lib = _lib.load()
-    check(lib.kgat_frontier_expand(_ptr(row_ptr, i32), _ptr(col_idx, i32), _ptr(rows, i32), _ptr(count_dev, i32), int(max_rows),
-                                   _ptr(bitmap_out, i32), _stream()), "frontier_expand")
+    check(lib.kgat_frontier_expand(_ptr(plan.tasks, i32), plan.n_partials, _ptr(plan.light_rank, i32), _ptr(col_idx, i32), _ptr(rows, i32),
+                                   _ptr(count_dev, i32), int(max_rows), _ptr(level_bitmap, i32), _ptr(flags, u8), _stream()), "frontier_expand")
 
 
-def frontier_list(bitmap, n_nodes: int, scratch, rows, count_dev):
+def frontier_list(flags, bitmap, n_nodes: int, scratch, rows, count_dev):
+    """bitmap <- flags (flags cleared), rows <- ascending set bits, count_dev <- their number"""
     lib = _lib.load()
-    if scratch.numel() < frontier_scratch_ints(n_nodes) or bitmap.numel() * 32 < n_nodes:
-        raise KgatLibraryError("frontier_list: scratch / bitmap too small")
-    check(lib.kgat_frontier_list(_ptr(bitmap, i32), int(n_nodes), _ptr(scratch, i32), _ptr(rows, i32), _ptr(count_dev, i32), _stream()),
-          "frontier_list")
+    if scratch.numel() < frontier_scratch_ints(n_nodes) or bitmap.numel() * 32 < n_nodes or flags.numel() < (n_nodes + 31) // 32 * 32:
+        raise KgatLibraryError("frontier_list: scratch / bitmap / flags too small")
+    check(lib.kgat_frontier_list(_ptr(flags, u8), _ptr(bitmap, i32), int(n_nodes), _ptr(scratch, i32), _ptr(rows, i32), _ptr(count_dev, i32),
+                                 _stream()), "frontier_list")
 
 
 def frontier_zero_rows(table: torch.Tensor, rows, count_dev, max_rows: int):

@@ -143,6 +143,36 @@ def test_masked_spmm_equals_dense_on_live_rows_and_never_reads_dead_ones(kb, d, 
         assert torch.equal(out[rm], ref[rm]) and bool((out[~rm] == 7.0).all())
 
 
+@pytest.mark.parametrize("d", [16, 32, 64, 128])
+@pytest.mark.parametrize("chunk", [8, 256])
+def test_scatter_rows_equals_transposed_gather(kb, d, chunk):
+    """Y[c] += A[r, c] G[r] over a row list (vector reductions) == the masked gather over A^T, up to fp32 summation order."""
+    from kgat_b200 import ops
+
+    n = 700
+    g = _random_graph(n, 9000, seed=3 * d + chunk, chunk=chunk, heavy=[(17, 800), (250, 40)])
+    rng = np.random.default_rng(d + 1)
+    words = (n + 31) // 32
+    for p_src in (0.02, 0.3, 1.0):
+        src = rng.random(n) < p_src
+        src[17] = True
+        listed = np.nonzero(src)[0].astype(np.int32)
+        rows = torch.zeros(n, dtype=torch.int32, device="cuda")
+        rows[: listed.size] = torch.from_numpy(listed).cuda()
+        cnt = torch.tensor([listed.size], dtype=torch.int32, device="cuda")
+        live = torch.from_numpy(src).cuda()
+        G, Z = torch.randn(n, d, device="cuda"), torch.randn(n, d, device="cuda")
+        Gz, Zz = G.clone(), Z.clone()
+        Gz[~live] = 0.0
+        Zz[~live] = 0.0
+        ref = g.matmul_t(Gz, addend=Zz)
+        G[~live] = float("nan")
+        Z[~live] = float("nan")
+        out = torch.zeros(n, d, device="cuda")
+        ops.spmm_scatter_rows(g.plan, g.col_idx, g.vals, G, out, rows, cnt, n, _bits(src, words), addend=Z)
+        assert bool(torch.isfinite(out).all()) and rel_err(out, ref) < 2e-6
+
+
 @pytest.mark.parametrize("d_in,d_out", [(64, 64), (64, 32), (32, 16), (128, 64)])
 @pytest.mark.parametrize("p", [0.0, 0.1])
 def test_biagg_row_list_equals_dense_kernels_on_listed_rows(kb, d_in, d_out, p):
@@ -220,14 +250,18 @@ def _small_model(kb, layer_size, seed=3):
 
 
 @pytest.mark.parametrize("layer_size", [[64, 32, 16], [64], [32, 32, 16, 16]])
-@pytest.mark.parametrize("mode", ["eval", "train-masks", "train-philox"])
+@pytest.mark.parametrize("mode", ["eval", "train-masks", "train-philox", "eval-gather"])
 def test_pruned_cf_step_equals_full_propagation(kb, layer_size, mode):
-    """model.cf_pruning on / off: same loss, same gradients; with every stale row poisoned by NaN."""
+    """model.cf_pruning on / off: same loss, same gradients; with every stale row poisoned by NaN.
+    ("eval-gather": the upper layers' backward as the deterministic masked gather instead of the edge scatter.)"""
     from kgat_b200 import functions
     from kgat_b200.model import KGATMode
 
     g, model = _small_model(kb, layer_size)
     model.api_graphs = False
+    if mode == "eval-gather":
+        model._frontier(model.cuda()._graph(), 3 * 6).scatter_backward = False
+        mode = "eval"
     rng = np.random.default_rng(len(layer_size))
     b = 6
     u = torch.from_numpy(rng.integers(0, g.user_num, b)).cuda()
