@@ -263,8 +263,7 @@ def run_reference_arm(args):
 def algorithmic_bytes(name: str, g, graph) -> float | None:
     """Compulsory-traffic model B_min of SURVEY.md section 8d, per launch of the named kernel."""
     n, nnz = g.node_num, graph.nnz
-    for suffix in ("_pruned", "_rows", "_edges", "_scatter"):
-        name = name.replace(suffix, "")
+    name = name.replace("_pruned", "")
     if name.startswith("spmm"):
         d = int(name.split("_d")[1])
         transposed = name.startswith("spmmT")
@@ -427,7 +426,7 @@ def main():
                 "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)", "algorithmic_bytes_per_launch": abytes,
                 "model": "B_min (every distinct byte once, SURVEY.md 8d); gather_gbs adds one neighbour-row read per edge (L2 traffic)"}
     if top.startswith("spmm"):
-        d = int(top.split("_d")[1].split("_")[0])
+        d = int(top.replace("_pruned", "").split("_d")[1])
         roofline["gather_gbs"] = (abytes + 4.0 * graph.nnz * d) / (per_epoch_ms[top]["avg_us"] * 1e-6) / 1e9
     # the dense Adam sweep of the KG phase (second-largest single kernel), timed back to back so launch gaps do not count
     ad = engine.kg_adam

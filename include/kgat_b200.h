@@ -111,14 +111,12 @@ int kgat_spmm_csr_masked(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_r
  * work = the plan's first n_heavy_tasks tasks (the chunks of the heavy rows; filtered by row_mask, required then) followed
  * by rows[0 .. *n_rows_dev) where a light row owns the single task n_heavy_tasks + light_rank[row] (light_rank[row] < 0
  * marks a heavy row); rows == NULL runs every task (dense output, e.g. the embedding gradient) and only masks edges.
- * edge_mask as above (staged in shared memory when n_mask_bits / 8 <= 32 KB).  d in {16, 32, 64, 128}.
- * work_counters (nullable): two int32, zero on entry and on exit, owned by the plan -- the tail of the items is handed out
- * through them one at a time (dynamic balance); NULL = fixed stride only. */
+ * edge_mask as above (staged in shared memory when n_mask_bits / 8 <= 32 KB).  d in {16, 32, 64, 128}. */
 int kgat_spmm_csr_rows(const int32_t* tasks, int64_t n_tasks, int64_t n_heavy_tasks, const int32_t* light_rank,
                        int32_t* heavy_rows, int64_t n_heavy, const int32_t* col_idx, const float* vals, const float* X,
                        int64_t n_cols, int64_t ldx, float* Y, int64_t ldy, const float* Z, int64_t ldz, int32_t d,
                        float* partials, const int32_t* rows, const int32_t* n_rows_dev, const uint32_t* row_mask,
-                       const uint32_t* edge_mask, int64_t n_mask_bits, int32_t* work_counters, void* stream);
+                       const uint32_t* edge_mask, int64_t n_mask_bits, void* stream);
 
 /* Transposed product as a scatter over a needed-row list:  Y[c] += A[r, c] * G[r] for the *n_rows_dev listed rows r and
  * their edges, and Y[r] += Z[r] (Z nullable) -- 128-bit vector reductions, so Y's destination rows must be zero on entry
@@ -143,11 +141,10 @@ int kgat_frontier_mark_ids(const int64_t* ids64, int64_t n_ids, int64_t n_nodes,
                            void* stream);
 /* flags[r] = flags[c] = 1 for the *count_dev rows r listed in `rows` (their bitmap: level_bitmap) and every column c of
  * A[r, :].  Work items are the SpMM plan's tasks (kgat_spmm_csr_rows: the first n_heavy_tasks chunk tasks filtered by
- * level_bitmap, then the listed light rows through light_rank), so hub rows are spread over many warps.  n_nodes > 0
- * enables the per-CTA shared-memory bitmap when n_nodes / 8 <= 96 KB (hub columns then cost one global store per CTA). */
+ * level_bitmap, then the listed light rows through light_rank), so hub rows are spread over many warps. */
 int kgat_frontier_expand(const int32_t* tasks, int64_t n_heavy_tasks, const int32_t* light_rank, const int32_t* col_idx,
                          const int32_t* rows, const int32_t* count_dev, int64_t max_rows, const uint32_t* level_bitmap,
-                         uint8_t* flags, int64_t n_nodes, void* stream);
+                         uint8_t* flags, void* stream);
 /* bitmap <- flags (every word written; flags cleared); rows[0 .. *count_dev) = ascending node ids of the set bits;
  * scratch: kgat_frontier_scratch_ints(n_nodes) int32 */
 int64_t kgat_frontier_scratch_ints(int64_t n_nodes);

@@ -81,10 +81,10 @@ SIGNATURES: dict[str, tuple] = {
     "kgat_ids64_to_i32": (_I32, [_P, _I64, _I64, _P, _P, _P]),
     "kgat_spmm_csr": (_I32, [_P, _I64, _P, _I64, _P, _P, _P, _I64, _I64, _P, _I64, _P, _I64, _I32, _P, _P]),
     "kgat_spmm_csr_masked": (_I32, [_P, _I64, _P, _I64, _P, _P, _P, _I64, _I64, _P, _I64, _P, _I64, _I32, _P, _P, _P, _P]),
-    "kgat_spmm_csr_rows": (_I32, [_P, _I64, _I64, _P, _P, _I64, _P, _P, _P, _I64, _I64, _P, _I64, _P, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P, _P]),
+    "kgat_spmm_csr_rows": (_I32, [_P, _I64, _I64, _P, _P, _I64, _P, _P, _P, _I64, _I64, _P, _I64, _P, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P]),
     "kgat_spmm_scatter_rows": (_I32, [_P, _I64, _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _P, _I64, _P, _I64, _I32, _P]),
     "kgat_frontier_mark_ids": (_I32, [_P, _I64, _I64, _P, _P, _P]),
-    "kgat_frontier_expand": (_I32, [_P, _I64, _P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
+    "kgat_frontier_expand": (_I32, [_P, _I64, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "kgat_frontier_scratch_ints": (_I64, [_I64]),
     "kgat_frontier_list": (_I32, [_P, _P, _I64, _P, _P, _P, _P]),
     "kgat_frontier_zero_rows": (_I32, [_P, _I64, _I32, _P, _P, _I64, _P]),

@@ -66,49 +66,6 @@ __global__ void __launch_bounds__(128) frontier_expand_kernel(const int4* __rest
     }
 }
 
-// The same with a per-CTA bitmap in shared memory (n_nodes / 8 bytes, used when it fits): the CTA's edge visits meet in
-// shared-memory atomics and every node is flagged in global memory at most once per CTA -- a hub column that thousands of
-// edges point at receives a few hundred stores instead of tens of thousands racing at one L2 sector (59 -> ~10 us at the
-// Amazon-book shape).
-__global__ void __launch_bounds__(512) frontier_expand_smem_kernel(const int4* __restrict__ tasks, int n_heavy_tasks,
-                                                                   const int32_t* __restrict__ light_rank, const int32_t* __restrict__ col_idx,
-                                                                   const int32_t* __restrict__ rows, const int32_t* __restrict__ cnt_dev,
-                                                                   const uint32_t* __restrict__ level_mask, uint8_t* __restrict__ flags,
-                                                                   int n_words) {
-    extern __shared__ uint32_t seen[];
-    for (int w = threadIdx.x; w < n_words; w += blockDim.x) seen[w] = 0u;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    const int total = n_heavy_tasks + cnt_dev[0];
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < total; i += n_warps) {
-        int4 t;
-        if (i < n_heavy_tasks) {
-            t = __ldg(tasks + i);
-            if (!((__ldg(level_mask + (t.x >> 5)) >> (t.x & 31)) & 1u)) continue;
-        } else {
-            const int lr = __ldg(light_rank + __ldg(rows + (i - n_heavy_tasks)));
-            if (lr < 0) continue;
-            t = __ldg(tasks + n_heavy_tasks + lr);
-        }
-        if (lane == 0) atomicOr(seen + (t.x >> 5), 1u << (t.x & 31));
-        for (int k = t.y + lane; k < t.z; k += 32) {
-            const int c = __ldg(col_idx + k);
-            const uint32_t bit = 1u << (c & 31);
-            if (!(seen[c >> 5] & bit)) atomicOr(seen + (c >> 5), bit);
-        }
-    }
-    __syncthreads();
-    for (int w = threadIdx.x; w < n_words; w += blockDim.x) {
-        uint32_t bits = seen[w];
-        while (bits) {
-            const int node = w * 32 + __ffs(bits) - 1;
-            bits &= bits - 1;
-            if (!__ldcg(flags + node)) flags[node] = 1;
-        }
-    }
-}
-
 // bitmap word w <- flags[32 w .. 32 w + 32) (and the flags are cleared for the next build); block totals of the set bits
 __global__ void __launch_bounds__(kListBlock) frontier_count_kernel(uint8_t* __restrict__ flags, uint32_t* __restrict__ bitmap,
                                                                    int64_t n_words, int32_t* __restrict__ block_total) {
@@ -219,26 +176,10 @@ int kgat_frontier_mark_ids(const int64_t* ids64, int64_t n_ids, int64_t n_nodes,
 
 int kgat_frontier_expand(const int32_t* tasks, int64_t n_heavy_tasks, const int32_t* light_rank, const int32_t* col_idx,
                          const int32_t* rows, const int32_t* count_dev, int64_t max_rows, const uint32_t* level_bitmap, uint8_t* flags,
-                         int64_t n_nodes, void* stream) {
+                         void* stream) {
     if (!tasks || !light_rank || !col_idx || !rows || !count_dev || !flags || max_rows <= 0 || n_heavy_tasks < 0 ||
         (n_heavy_tasks > 0 && !level_bitmap) || n_heavy_tasks >= ((int64_t)1 << 30))
         return KGAT_ERR_INVALID_ARGUMENT;
-    const int64_t n_words = (n_nodes + 31) / 32;
-    if (n_nodes > 0 && n_words * 4 <= 96 * 1024) {  // the node bitmap fits in shared memory: collect per CTA first
-        const size_t smem = (size_t)n_words * 4;
-        static bool configured = false;
-        if (!configured) {
-            KGAT_CUDA_TRY(cudaFuncSetAttribute(frontier_expand_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            configured = true;
-        }
-        int64_t ctas = (max_rows + n_heavy_tasks + 15) / 16;
-        const int64_t cap = (int64_t)sm_count() * (smem <= 48 * 1024 ? 2 : 1);
-        if (ctas > cap) ctas = cap;
-        frontier_expand_smem_kernel<<<(unsigned)ctas, 512, smem, (cudaStream_t)stream>>>(reinterpret_cast<const int4*>(tasks), (int)n_heavy_tasks,
-                                                                                       light_rank, col_idx, rows, count_dev, level_bitmap, flags,
-                                                                                       (int)n_words);
-        return check_launch();
-    }
     int64_t ctas = (max_rows + n_heavy_tasks + 3) / 4;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (ctas > cap) ctas = cap;

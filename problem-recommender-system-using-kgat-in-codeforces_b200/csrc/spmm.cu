@@ -8,8 +8,6 @@
 // lane).  (col, val) of 32 consecutive edges are read coalesced once and broadcast by shuffle.
 // Long rows are split by the host-side plan into chunks whose partial sums are reduced in a fixed
 // order by a second tiny kernel: deterministic, no atomics.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace kgat {
@@ -88,63 +86,32 @@ __device__ __forceinline__ void spmm_do_task(const int4 t, int2* __restrict__ eb
 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int base = t.y;
-    if (MASKED && edge_mask != nullptr) {
-        // 64 edges per round (two per lane): the edges whose source row is live are packed to the front of the 64-entry
-        // slab and padded to a whole unrolled step, so a round with ~58 % live edges still issues full gather groups.
-        // Padding entries carry weight 0 and the address of a LIVE row (dead rows may hold NaN garbage).
-        int c0 = 0, c1 = 0;
-        float v0 = 0.f, v1 = 0.f;
-        auto fetch = [&](int b) {
-            const int k0 = b + lane, k1 = b + 32 + lane;
-            c0 = ld_stream_i32(col_idx + min(k0, t.z - 1));
-            v0 = k0 < t.z ? ld_stream_f32(vals + k0) : 0.f;
-            c1 = ld_stream_i32(col_idx + min(k1, t.z - 1));
-            v1 = k1 < t.z ? ld_stream_f32(vals + k1) : 0.f;
-        };
-        if (base < t.z) fetch(base);
-        while (base < t.z) {
-            const bool live0 = (base + lane < t.z) && ((edge_mask[c0 >> 5] >> (c0 & 31)) & 1u);
-            const bool live1 = (base + 32 + lane < t.z) && ((edge_mask[c1 >> 5] >> (c1 & 31)) & 1u);
-            const unsigned m0 = __ballot_sync(kFull, live0), m1 = __ballot_sync(kFull, live1);
-            const int n0 = __popc(m0), cnt = n0 + __popc(m1);
-            const unsigned below = (1u << lane) - 1u;
-            const int off0 = WIDE ? c0 : (int)((uint32_t)c0 * row_bytes32), off1 = WIDE ? c1 : (int)((uint32_t)c1 * row_bytes32);
-            if (live0) eb[__popc(m0 & below)] = make_int2(off0, __float_as_int(v0));
-            if (live1) eb[n0 + __popc(m1 & below)] = make_int2(off1, __float_as_int(v1));
-            if (cnt > 0) {
-                const int live_off = m0 ? __shfl_sync(kFull, off0, __ffs(m0) - 1) : __shfl_sync(kFull, off1, __ffs(m1) - 1);
-                const int pad = (EPI - (cnt % EPI)) % EPI;
-                if (lane < pad) eb[cnt + lane] = make_int2(live_off, 0);
-            }
-            __syncwarp();
-            base += 64;
-            if (base < t.z) fetch(base);  // the next 64 (col, val) pairs travel while this round is gathered
-            for (int j = 0; j < cnt; j += EPI) {
-                float4 x[U];
-                float w[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int2 ev = eb[j + u * EPW + slot];
-                    w[u] = __int_as_float(ev.y);
-                    const char* src = WIDE ? xb + (int64_t)ev.x * row_bytes64 : xb + (uint32_t)ev.x;
-                    x[u] = __ldg(reinterpret_cast<const float4*>(src));
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) fma4(acc, w[u], x[u]);
-            }
-            __syncwarp();
-        }
-    }
     int c = 0;
     float v = 0.f;
-    if (!(MASKED && edge_mask != nullptr) && base < t.z) {
+    if (base < t.z) {
         const int k = base + lane;
         c = ld_stream_i32(col_idx + min(k, t.z - 1));
         v = k < t.z ? ld_stream_f32(vals + k) : 0.f;
     }
-    while (!(MASKED && edge_mask != nullptr) && base < t.z) {
-        eb[lane] = make_int2(WIDE ? c : (int)((uint32_t)c * row_bytes32), __float_as_int(v));
-        const int cnt = min(32, t.z - base);
+    while (base < t.z) {
+        int cnt;
+        if (MASKED && edge_mask != nullptr) {
+            // keep the edges whose source row is live, packed to the front of the slab; pad to a whole unrolled step
+            // (padding entries carry weight 0 and the address of a LIVE row: dead rows may hold NaN garbage)
+            const bool live = (base + lane < t.z) && ((edge_mask[c >> 5] >> (c & 31)) & 1u);
+            const unsigned m = __ballot_sync(kFull, live);
+            cnt = __popc(m);
+            const int off = WIDE ? c : (int)((uint32_t)c * row_bytes32);
+            if (live) eb[__popc(m & ((1u << lane) - 1u))] = make_int2(off, __float_as_int(v));
+            if (cnt > 0) {
+                const int live_off = __shfl_sync(kFull, off, __ffs(m) - 1);
+                const int pad = (EPI - (cnt % EPI)) % EPI;
+                if (lane < pad) eb[cnt + lane] = make_int2(live_off, 0);
+            }
+        } else {
+            eb[lane] = make_int2(WIDE ? c : (int)((uint32_t)c * row_bytes32), __float_as_int(v));
+            cnt = min(32, t.z - base);
+        }
         __syncwarp();
         base += 32;
         if (base < t.z) {  // prefetch the next 32 (col, val) pairs while this batch is gathered
@@ -197,7 +164,7 @@ __global__ void __launch_bounds__(128) spmm_task_kernel(const int4* __restrict__
                                                         int64_t ldy, const float* __restrict__ Z, int64_t ldz,
                                                         float* __restrict__ partials, int4* __restrict__ heavy, int n_heavy,
                                                         const uint32_t* __restrict__ row_mask, const uint32_t* __restrict__ edge_mask) {
-    __shared__ int2 ebuf[4][64];
+    __shared__ int2 ebuf[4][32];
     const int64_t task_id = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (task_id >= n_tasks) return;
     const int4 t = __ldg(tasks + task_id);  // {row, begin, end, partial_slot}
@@ -221,9 +188,9 @@ __global__ void __launch_bounds__(kRowsThreads, 5) spmm_rows_kernel(const int4* 
                                                                 float* __restrict__ Y, int64_t ldy, const float* __restrict__ Z, int64_t ldz,
                                                                 float* __restrict__ partials, int4* __restrict__ heavy, int n_heavy,
                                                                 const uint32_t* __restrict__ row_mask, const uint32_t* __restrict__ edge_mask,
-                                                                int mask_words_smem, int* __restrict__ work, int static_permille) {
+                                                                int mask_words_smem) {
     extern __shared__ __align__(16) uint32_t smem_mask[];
-    __shared__ int2 ebuf[kRowsThreads / 32][64];
+    __shared__ int2 ebuf[kRowsThreads / 32][32];
     const uint32_t* emask = edge_mask;
     if (edge_mask != nullptr && mask_words_smem > 0) {
         for (int i = threadIdx.x; i < mask_words_smem; i += kRowsThreads) smem_mask[i] = __ldg(edge_mask + i);
@@ -232,30 +199,15 @@ __global__ void __launch_bounds__(kRowsThreads, 5) spmm_rows_kernel(const int4* 
     }
     const int n_warps = (gridDim.x * kRowsThreads) >> 5;
     const int total = rows != nullptr ? n_heavy_tasks + n_rows_dev[0] : n_tasks;
-    // Work distribution: the first static_permille / 1000 of the items by a fixed stride (no synchronisation), the rest
-    // through a device-wide counter one item at a time, so the warps that drew short rows absorb the tail of the ones that
-    // drew hub chunks (items differ ~10x in length; a pure stride leaves the slowest warp ~1.6x behind the mean).
-    const int n_static = work != nullptr ? (int)(((int64_t)total * static_permille / 1000) / n_warps) * n_warps : total;
-    const int lane_ = threadIdx.x & 31;
-    int i = (blockIdx.x * kRowsThreads + threadIdx.x) >> 5;
-    while (true) {
-        if (i >= n_static) {
-            if (work == nullptr) break;
-            int next = 0;
-            if (lane_ == 0) next = n_static + atomicAdd(work, 1);
-            i = __shfl_sync(kFull, next, 0);
-            if (i >= total) break;
-        }
-        const int item = i;
-        i = i < n_static ? i + n_warps : n_static;  // after the static share every further item comes from the counter
+    for (int i = (blockIdx.x * kRowsThreads + threadIdx.x) >> 5; i < total; i += n_warps) {
         int4 t;
         if (rows == nullptr) {
-            t = __ldg(tasks + item);
-        } else if (item < n_heavy_tasks) {
-            t = __ldg(tasks + item);
+            t = __ldg(tasks + i);
+        } else if (i < n_heavy_tasks) {
+            t = __ldg(tasks + i);
             if (row_mask != nullptr && !((__ldg(row_mask + (t.x >> 5)) >> (t.x & 31)) & 1u)) continue;
         } else {
-            const int lr = __ldg(light_rank + __ldg(rows + (item - n_heavy_tasks)));
+            const int lr = __ldg(light_rank + __ldg(rows + (i - n_heavy_tasks)));
             if (lr < 0) continue;  // a heavy row: its chunks were taken above
             t = __ldg(tasks + n_heavy_tasks + lr);
         }
@@ -265,16 +217,6 @@ __global__ void __launch_bounds__(kRowsThreads, 5) spmm_rows_kernel(const int4* 
         else
             spmm_do_task<D, U, WIDE, false>(t, ebuf[threadIdx.x >> 5], col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, heavy, n_heavy, nullptr,
                                             nullptr);
-    }
-    if (work != nullptr) {  // the last CTA to leave re-arms the counters for the next launch
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            if (atomicAdd(work + 1, 1) == (int)gridDim.x - 1) {
-                work[0] = 0;
-                work[1] = 0;
-            }
-        }
     }
 }
 
@@ -467,7 +409,7 @@ extern "C" int kgat_spmm_csr_rows(const int32_t* tasks, int64_t n_tasks, int64_t
                                   int32_t* heavy_rows, int64_t n_heavy, const int32_t* col_idx, const float* vals, const float* X,
                                   int64_t n_cols, int64_t ldx, float* Y, int64_t ldy, const float* Z, int64_t ldz, int32_t d, float* partials,
                                   const int32_t* rows, const int32_t* n_rows_dev, const uint32_t* row_mask, const uint32_t* edge_mask,
-                                  int64_t n_mask_bits, int32_t* work_counters, void* stream_) {
+                                  int64_t n_mask_bits, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_tasks < 0 || n_heavy < 0 || n_heavy_tasks < 0 || n_heavy_tasks > n_tasks || n_tasks >= ((int64_t)1 << 31)) return KGAT_ERR_INVALID_ARGUMENT;
     if ((ldx & 3) || (ldy & 3) || (Z && (ldz & 3))) return KGAT_ERR_INVALID_ARGUMENT;
@@ -488,15 +430,8 @@ extern "C" int kgat_spmm_csr_rows(const int32_t* tasks, int64_t n_tasks, int64_t
     const unsigned blocks = (unsigned)(sm_count() * ctas_per_sm);
     const int4* t4 = reinterpret_cast<const int4*>(tasks);
     int4* h4 = reinterpret_cast<int4*>(heavy_rows);
-    static int static_permille = -1;
-    if (static_permille < 0) {
-        const char* e = getenv("KGAT_SPMM_STATIC_PERMILLE");
-        static_permille = e ? atoi(e) : 600;
-        if (static_permille < 0 || static_permille > 1000) static_permille = 600;
-    }
-    if (static_permille >= 1000) work_counters = nullptr;
 #define KGAT_ROWS_ARGS t4, (int)n_tasks, (int)n_heavy_tasks, light_rank, rows, n_rows_dev, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, h4, \
-                       (int)n_heavy, row_mask, edge_mask, mask_words, work_counters, static_permille
+                       (int)n_heavy, row_mask, edge_mask, mask_words
 #define KGAT_ROWS_LAUNCH(DD, UU)                                                                                  \
     do {                                                                                                          \
         if (use_wide) spmm_rows_kernel<DD, UU, true><<<blocks, kRowsThreads, smem, stream>>>(KGAT_ROWS_ARGS);      \

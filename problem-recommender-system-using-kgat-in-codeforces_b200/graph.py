@@ -35,7 +35,6 @@ class SpmmPlan:
     n_heavy: int
     n_partials: int  # = number of heavy-chunk tasks; they come first in `tasks`
     light_rank: torch.Tensor | None = None  # int32 [n_rows]: a light row's task is n_partials + light_rank[row]; -1 = heavy row
-    work: torch.Tensor | None = None  # int32 [2]: dynamic work counters of the row-list kernel (zero between launches)
 
 
 def spmm_plan_host(row_ptr: np.ndarray, chunk: int = DEFAULT_CHUNK):
@@ -80,7 +79,6 @@ def make_plan(row_ptr: torch.Tensor, chunk: int = DEFAULT_CHUNK) -> SpmmPlan:
         n_heavy=int(heavy.shape[0]),
         n_partials=n_partials,
         light_rank=torch.from_numpy(light_rank).to(dev).contiguous(),
-        work=torch.zeros(2, dtype=torch.int32, device=dev),
     )
 
 

@@ -224,8 +224,7 @@ def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.
                 _ptr(plan.tasks, i32), plan.n_tasks, plan.n_partials, _ptr(plan.light_rank, i32) if plan.light_rank is not None else None,
                 _ptr(plan.heavy, i32) if plan.n_heavy else None, plan.n_heavy, *args[4:],
                 _ptr(rows, i32) if rows is not None else None, _ptr(n_rows_dev, i32) if rows is not None else None,
-                _ptr(row_mask, i32) if row_mask is not None else None, _ptr(edge_mask, i32) if edge_mask is not None else None, n_bits,
-                _ptr(plan.work, i32) if plan.work is not None else None, _stream(),
+                _ptr(row_mask, i32) if row_mask is not None else None, _ptr(edge_mask, i32) if edge_mask is not None else None, n_bits, _stream(),
             ),
             "spmm_csr_rows",
         )
@@ -281,8 +280,7 @@ def frontier_expand(plan, col_idx, rows, count_dev, max_rows: int, level_bitmap,
     """flags[r] = flags[c] = 1 for the listed rows r and the columns c of their CSR rows; ``plan``: the graph's SpmmPlan."""
     lib = _lib.load()
     check(lib.kgat_frontier_expand(_ptr(plan.tasks, i32), plan.n_partials, _ptr(plan.light_rank, i32), _ptr(col_idx, i32), _ptr(rows, i32),
-                                   _ptr(count_dev, i32), int(max_rows), _ptr(level_bitmap, i32), _ptr(flags, u8), flags.numel(), _stream()),
-          "frontier_expand")
+                                   _ptr(count_dev, i32), int(max_rows), _ptr(level_bitmap, i32), _ptr(flags, u8), _stream()), "frontier_expand")
 
 
 def frontier_list(flags, bitmap, n_nodes: int, scratch, rows, count_dev):
