@@ -91,117 +91,129 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port of the reference's PyTorch-CPU path
+# reference arm / baselines: the UNMODIFIED reference KGAT (oracle/_ref, staged by oracle/build_ref.py) through its own
+# public API, on the host cores or -- the same-box incumbent -- on the B200 with stock ATen kernels.  The oracle port
+# (oracle/kgat_oracle.py) is the fallback when the staged reference is missing.
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_sample(g, params, data, n_cf_steps: int = 1, n_kg_steps: int = 3, refresh_relations: int = 2):
-    """Times a bounded sample of the epoch on the host cores with the oracle (a line-by-line port of
-    the reference's ATen call sequence: sparse-COO matmul, nn.Linear, bmm, CPU sparse softmax) and
-    extrapolates to the full epoch with the reference's batch counts.  Returns a dict."""
-    from oracle import kgat_oracle as O
-
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
+def _att_coo(g):
     n = g.node_num
-    att = torch.sparse_coo_tensor(torch.from_numpy(np.vstack([g.att_rows, g.att_cols])).long(), torch.from_numpy(g.att_vals), size=(n, n))
-    p = {k: v.detach().clone().cpu() for k, v in params.items()}
-    states = {"cf": {}, "kg": {}}
+    return torch.sparse_coo_tensor(torch.from_numpy(np.vstack([g.att_rows, g.att_cols])).long(), torch.from_numpy(g.att_vals), size=(n, n))
 
-    def step(kind, loss_fn, lr, step_no):
-        leaves = {k: v.requires_grad_(True) for k, v in p.items()}
+
+def reference_model(g, params, device):
+    """The staged, unmodified reference ``KGAT`` with our initial parameters; None when oracle/_ref is absent."""
+    from oracle import build_ref
+
+    mods = build_ref.load()
+    if mods is None:
+        return None
+    ref, _ = mods
+    m = ref.KGAT(ref.KGATArgs(user_num=g.user_num, entity_num=g.entity_num, relation_num=g.relation_num, attentive_matrix=_att_coo(g)))
+    m.load_state_dict(params, strict=False)
+    m = m.to(device)
+    m.build_optimizer(cf_lr=1e-3, kg_lr=1e-4)  # two torch.optim.Adam over all parameters (model.py:393-405)
+    m.train()
+    return m, ref.KGATMode
+
+
+class ReferenceRunner:
+    """Bounded samples of the reference epoch body (main.py:290-361) through the reference model's own API."""
+
+    def __init__(self, g, params, data, device="cpu", refresh_relations: int = 2):
+        self.g, self.data, self.device = g, data, torch.device(device)
+        if self.device.type == "cpu":
+            torch.set_num_threads(os.cpu_count() or 1)
+        built = reference_model(g, params, self.device)
+        self.kind = "reference" if built is not None else "port"
+        self.cf_i = self.kg_i = 0
+        self.warm = False
+        rels = np.asarray(g.adjacency_relations[:refresh_relations])
+        sel = np.isin(g.relations, rels)
+        self.share = float(sel.sum()) / max(g.nnz, 1)
+        if built is not None:
+            self.model, self.Mode = built
+            # main.py:351-353 hands over the whole edge list; relation_indices selects the relations to score
+            self.edges = (torch.from_numpy(g.heads.astype(np.int64)).to(self.device), torch.from_numpy(g.relations.astype(np.int64)).to(self.device),
+                          torch.from_numpy(g.tails.astype(np.int64)).to(self.device), torch.from_numpy(rels.astype(np.int64)).to(self.device))
+        else:
+            from oracle import kgat_oracle as O
+
+            self.O = O
+            self.att = _att_coo(g).to(self.device)
+            self.p = {k: v.detach().clone().to(self.device).requires_grad_(True) for k, v in params.items()}
+            self.opt = {"cf": torch.optim.Adam(list(self.p.values()), lr=1e-3), "kg": torch.optim.Adam(list(self.p.values()), lr=1e-4)}
+            self.sel, self.rels = sel, rels
+
+    def _sync(self):
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
+    def _step(self, kind):
+        d = self.data
+        if kind == "cf":
+            b = [torch.from_numpy(a[self.cf_i % d.n_cf]).to(self.device) for a in d.cf]
+            self.cf_i += 1
+        else:
+            b = [torch.from_numpy(a[self.kg_i % d.n_kg]).to(self.device) for a in d.kg]
+            self.kg_i += 1
+        self._sync()
         t0 = time.perf_counter()
-        loss = loss_fn(leaves)
-        loss.backward()
-        with torch.no_grad():
-            for k, leaf in leaves.items():
-                if leaf.grad is None:
-                    continue
-                m, v = states[kind].setdefault(k, (torch.zeros_like(leaf), torch.zeros_like(leaf)))
-                O.adam_step(leaf, leaf.grad, m, v, step_no, lr)
-                leaf.grad = None
-        float(loss)
+        if self.kind == "reference":
+            m = self.model
+            loss = m(*b, mode=self.Mode.TRAIN_CF if kind == "cf" else self.Mode.TRAIN_KG)
+            loss.backward()
+            (m.update_cf_weights if kind == "cf" else m.update_kg_weights)()
+            loss.item()  # main.py:314 / 343 read the loss every step
+        else:
+            loss = self.O.cf_loss(self.p, self.att, *b) if kind == "cf" else self.O.kg_loss(self.p, *b)
+            loss.backward()
+            self.opt[kind].step()
+            self.opt[kind].zero_grad()
+            float(loss)
+        self._sync()
         return time.perf_counter() - t0
 
-    cf_t = []
-    for i in range(n_cf_steps):
-        b = [torch.from_numpy(a[i]) for a in data.cf]
-        cf_t.append(step("cf", lambda q: O.cf_loss(q, att, *b), 1e-3, i + 1))
-    kg_t = []
-    for i in range(n_kg_steps):
-        b = [torch.from_numpy(a[i]) for a in data.kg]
-        kg_t.append(step("kg", lambda q: O.kg_loss(q, *b), 1e-4, i + 1))
-    # attention refresh on the edges of the first `refresh_relations` relation ids, scaled by edge share
-    rels = np.asarray(g.adjacency_relations[:refresh_relations])
-    sel = np.isin(g.relations, rels)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        pp = {k: v.detach() for k, v in p.items()}
-        O.attention_refresh(pp, g.heads[sel].astype(np.int64), g.relations[sel], g.tails[sel].astype(np.int64), rels, n)
-    t_ref_part = time.perf_counter() - t0
-    share = float(sel.sum()) / max(g.nnz, 1)
-    t_refresh = t_ref_part / max(share, 1e-9)
-    t_cf, t_kg = float(np.mean(cf_t)), float(np.mean(kg_t))
-    epoch = data.n_cf * t_cf + data.n_kg * t_kg + t_refresh
-    return {
-        "epoch_s_extrapolated": epoch, "cf_step_s": t_cf, "kg_step_s": t_kg, "refresh_s_extrapolated": t_refresh,
-        "cores": threads,
-        "sample": f"{n_cf_steps} CF step(s) + {n_kg_steps} KG steps + refresh of {share:.1%} of the edges, extrapolated x({data.n_cf}, {data.n_kg}, 1/share)",
-        "sample_wall_s": float(sum(cf_t) + sum(kg_t) + t_ref_part),
-    }
+    def _refresh(self):
+        self._sync()
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            m = self.model
+            keep = m.attentive_matrix.data
+            m(*self.edges, mode=self.Mode.UPDATE_ATTENTION)  # train() mode, no no_grad: as main.py:350-361
+            m.attentive_matrix.data = keep  # the sample scored a subset of the relations: keep the full matrix for the CF steps
+        else:
+            g, O = self.g, self.O
+            with torch.no_grad():
+                q = {k: v.detach() for k, v in self.p.items()}
+                heads = torch.from_numpy(g.heads[self.sel].astype(np.int64)).to(self.device)
+                tails = torch.from_numpy(g.tails[self.sel].astype(np.int64)).to(self.device)
+                rel_of = torch.from_numpy(g.relations[self.sel].astype(np.int64)).to(self.device)
+                rows, cols, vals = [], [], []
+                for r in self.rels.tolist():
+                    idx = torch.where(rel_of == r)[0]
+                    rows.append(heads[idx])
+                    cols.append(tails[idx])
+                    vals.append(O.attention_by_relation(q, heads[idx], tails[idx], r, g.node_num))
+                mtx = torch.sparse_coo_tensor(torch.stack([torch.cat(rows), torch.cat(cols)]), torch.cat(vals), size=(g.node_num, g.node_num))
+                torch.sparse.softmax(mtx.cpu(), dim=1).to(self.device)
+        self._sync()
+        return (time.perf_counter() - t0) / max(self.share, 1e-9)
 
-
-def aten_gpu_sample(g, params, data, device, n_cf_steps: int = 3, n_kg_steps: int = 10, refresh_relations: int = 2):
-    """The same oracle port (the reference's ATen call sequence) with every tensor on the B200: what stock PyTorch
-    -- cuSPARSE SpMM, cuBLAS, ~100 elementwise kernels per step, torch.optim.Adam, the device -> host -> device round
-    trip around the CPU sparse softmax of model.py:364-366 -- makes of this epoch on the same box (SURVEY.md 8d:
-    "the real kernel to beat").  Part of the baseline leg: bounded sample, extrapolated like the CPU one."""
-    from oracle import kgat_oracle as O
-
-    n = g.node_num
-    att = torch.sparse_coo_tensor(torch.from_numpy(np.vstack([g.att_rows, g.att_cols])).long(), torch.from_numpy(g.att_vals),
-                                  size=(n, n)).to(device)
-    p = {k: v.detach().clone().to(device).requires_grad_(True) for k, v in params.items()}
-    opt = {"cf": torch.optim.Adam(list(p.values()), lr=1e-3), "kg": torch.optim.Adam(list(p.values()), lr=1e-4)}
-
-    def run(kind, batches, loss_fn):
-        ts = []
-        for i, b in enumerate(batches):
-            b = [torch.from_numpy(a).to(device) for a in b]
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            loss = loss_fn(p, b)
-            loss.backward()
-            opt[kind].step()
-            opt[kind].zero_grad()
-            float(loss)  # main.py:314 / 343 read the loss every step
-            ts.append(time.perf_counter() - t0)
-        return float(np.mean(ts[1:]))  # first step = warm-up (cuSPARSE / cuBLAS handles, allocator)
-
-    t_cf = run("cf", [[a[i] for a in data.cf] for i in range(n_cf_steps + 1)], lambda q, b: O.cf_loss(q, att, *b))
-    t_kg = run("kg", [[a[i] for a in data.kg] for i in range(n_kg_steps + 1)], lambda q, b: O.kg_loss(q, *b))
-    rels = np.asarray(g.adjacency_relations[:refresh_relations])
-    sel = np.isin(g.relations, rels)
-    heads = torch.from_numpy(g.heads[sel].astype(np.int64)).to(device)
-    tails = torch.from_numpy(g.tails[sel].astype(np.int64)).to(device)
-    rel_of = torch.from_numpy(g.relations[sel].astype(np.int64)).to(device)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        q = {k: v.detach() for k, v in p.items()}
-        rows, cols, vals = [], [], []
-        for r in rels.tolist():  # model.py:342-353
-            idx = torch.where(rel_of == r)[0]
-            rows.append(heads[idx])
-            cols.append(tails[idx])
-            vals.append(O.attention_by_relation(q, heads[idx], tails[idx], r, n))
-        m = torch.sparse_coo_tensor(torch.stack([torch.cat(rows), torch.cat(cols)]), torch.cat(vals), size=(n, n))
-        m = torch.sparse.softmax(m.cpu(), dim=1).to(device)  # model.py:364-366
-    torch.cuda.synchronize()
-    share = float(sel.sum()) / max(g.nnz, 1)
-    t_refresh = (time.perf_counter() - t0) / max(share, 1e-9)
-    return {"value": data.n_cf * t_cf + data.n_kg * t_kg + t_refresh, "unit": UNIT,
-            "kind": "oracle port with all tensors on cuda:0 (stock ATen / cuSPARSE / torch.optim.Adam kernels, loss read every step)",
-            "cf_step_s": t_cf, "kg_step_s": t_kg, "refresh_s": t_refresh,
-            "sample": f"{n_cf_steps} CF + {n_kg_steps} KG steps after one warm-up step each + refresh of {share:.1%} of the edges, extrapolated"}
+    def sample(self, n_cf: int = 3, n_kg: int = 3):
+        """One bounded sample: (one warm-up CF + KG step the first time,) n_cf CF steps, n_kg KG steps, the refresh of a
+        relation subset -- extrapolated to one epoch with the reference's own batch counts."""
+        if not self.warm:
+            self._step("cf")
+            self._step("kg")
+            self.warm = True
+        t_cf = float(np.mean([self._step("cf") for _ in range(n_cf)]))
+        t_kg = float(np.mean([self._step("kg") for _ in range(n_kg)]))
+        t_ref = self._refresh()
+        d = self.data
+        return {"epoch_s_extrapolated": d.n_cf * t_cf + d.n_kg * t_kg + t_ref, "cf_step_s": t_cf, "kg_step_s": t_kg, "refresh_s_extrapolated": t_ref,
+                "cores": (os.cpu_count() or 1) if self.device.type == "cpu" else 0, "kind": self.kind,
+                "sample": f"{n_cf} CF + {n_kg} KG steps (after one warm-up step each) + attention refresh of {self.share:.1%} of the edges, "
+                          f"extrapolated x({d.n_cf}, {d.n_kg}, 1/share)"}
 
 
 def make_workload(workload: str, seed: int = 2024):
@@ -227,7 +239,11 @@ def config_dict(g, data, n_gpus):
         "workload": f"synthetic {WORKLOAD}-shaped CKG (configs[2]): users={g.user_num} items={g.item_num} entities={g.entity_num} "
                     f"relations={g.relation_num} nodes={g.node_num} nnz={g.nnz}; 3 layers 64->64->32->16, d=64, fp32",
         "epoch": f"{data.n_cf} CF steps (B=256) + {data.n_kg} KG steps (B=512) + 1 attention refresh",
-        "l2_policy": "inputs larger than L2: the epoch streams >1 TB through 126 MB of L2; every step rewrites the 41 MB table, its Adam moments and ~0.5 GB of activations",
+        "batches": "one epoch of batches is sampled up front (seed 2024) and replayed by every bench step (step s uses batch s mod n), so "
+                   "the losses keep falling across bench steps; timing does not depend on it",
+        "l2_policy": "inputs larger than L2: the epoch streams >1 TB through 126 MB of L2; every step rewrites the 41 MB table, its Adam moments and ~0.3 GB of activations",
+        "cf_pruning": "each CF step computes layer l only for the rows the batch can reach (exact; frontier.py): same loss and gradients as "
+                      "the reference's full-graph propagation per batch",
         "parallelism": f"row-sharded x{n_gpus}" if n_gpus > 1 else "single GPU",
     }
 
@@ -237,22 +253,23 @@ def run_reference_arm(args):
     if rank != 0:
         return
     g, data = make_workload(WORKLOAD)
-    params = init_params(g)
-    vals = []
-    last = None
+    runner = ReferenceRunner(g, init_params(g), data, "cpu")
+    vals, last = [], None
     for i in range(args.warmup + args.steps):
-        last = cpu_reference_sample(g, params, data)
+        last = runner.sample()
         if i >= args.warmup:
             vals.append(last["epoch_s_extrapolated"])
-    v = float(np.mean(vals))
+    v = float(np.mean(vals)) if vals else last["epoch_s_extrapolated"]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(g, data, 1),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "detail": {k: last[k] for k in ("cf_step_s", "kg_step_s", "refresh_s_extrapolated")},
+        "note": "the unmodified reference KGAT (oracle/_ref: src/model/KGAT/{model,aggregator,multi_head_attention}.py) driven through its own "
+                "API with torch.optim.Adam on the host cores" if last["kind"] == "reference" else "oracle port (oracle/_ref not staged)",
     }
     print(json.dumps(line))
 
@@ -260,27 +277,174 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
-def algorithmic_bytes(name: str, g, graph) -> float | None:
-    """Compulsory-traffic model B_min of SURVEY.md section 8d, per launch of the named kernel."""
+def frontier_stats(engine, graph):
+    """Rows and edges per frontier level of the engine's last CF step (host side, from the device row lists)."""
+    f = getattr(engine, "frontier", None)
+    if f is None:
+        return None
+    deg = (graph.row_ptr[1:] - graph.row_ptr[:-1]).to(torch.int64)
+    deg_t = (graph.t_ptr[1:] - graph.t_ptr[:-1]).to(torch.int64)
+    out = {}
+    counts = f.counts.cpu().tolist()
+    for level in range(1, f.n_layers + 1):
+        rows = f.rows(level)[: counts[level - 1]].long()
+        out[f"L{level}"] = {"rows": counts[level - 1], "edges": int(deg[rows].sum()), "edges_t": int(deg_t[rows].sum())}
+    return out
+
+
+def algorithmic_bytes(name: str, g, graph, fr) -> float | None:
+    """Compulsory-traffic model B_min of SURVEY.md section 8d per launch of the named kernel (every distinct byte once),
+    restricted to the rows / edges the pruned step touches (``fr``: frontier_stats)."""
     n, nnz = g.node_num, graph.nnz
-    name = name.replace("_pruned", "")
-    if name.startswith("spmm"):
-        d = int(name.split("_d")[1])
-        transposed = name.startswith("spmmT")
-        plan = graph.t_plan if transposed else graph.plan
-        b = 8.0 * nnz + 16.0 * plan.n_tasks + 4.0 * n * d * 2  # (col, val) + task list + read X once + write Y
-        if transposed:
-            b += 4.0 * n * d  # addend (direct gradient) read
-        return b
-    if name.startswith("biagg_fwd_"):
-        di, do = (int(x) for x in name[len("biagg_fwd_"):].split("x"))
-        return n * (4.0 * (2 * di + do) + 4 + do)
-    if name.startswith("biagg_bwd_"):
-        di, do = (int(x) for x in name[len("biagg_bwd_"):].split("x"))
-        return n * (4.0 * (2 * do + 2 * di + 2 * di) + 4 + do)
-    if name == "adam_apply":
-        return None  # depends on the tensor set; reported separately
+    m = __import__("re").match(r"(spmmT?)_d(\d+)(?:_(rows|edges|scatter|pruned))?(?:_L(\d+))?$", name)
+    if m:
+        kind, d, var, lvl = m.group(1), int(m.group(2)), m.group(3), int(m.group(4)) if m.group(4) else None
+        t = kind == "spmmT"
+        if var is None or fr is None or lvl is None:
+            plan = graph.t_plan if t else graph.plan
+            return 8.0 * nnz + 16.0 * plan.n_tasks + 4.0 * n * d * (3 if t else 2)
+        cur = fr[f"L{lvl}"]
+        if not t:  # forward rows of level l: their edges, the distinct source rows (level l-1, or all of E0), the outputs
+            src_rows = fr[f"L{lvl - 1}"]["rows"] if lvl > 1 else n
+            return 8.0 * cur["edges"] + 16.0 * cur["rows"] + 4.0 * d * (min(src_rows, cur["edges"]) + cur["rows"])
+        if var == "scatter":  # edges of the source rows (level l), their g rows, zero + reduce into level l-1 rows
+            dst = fr[f"L{lvl - 1}"]["rows"]
+            return 8.0 * cur["edges"] + 16.0 * cur["rows"] + 4.0 * d * (2 * cur["rows"] + 2 * dst)
+        dst_rows, dst_edges = (fr[f"L{lvl - 1}"]["rows"], fr[f"L{lvl - 1}"]["edges_t"]) if lvl > 1 else (n, nnz)
+        return 8.0 * dst_edges + 16.0 * dst_rows + 4.0 * d * (2 * cur["rows"] + dst_rows)  # gather: all edges of the dst rows are streamed
+    m = __import__("re").match(r"biagg_(fwd|bwd)_(\d+)x(\d+)(?:_rows)?(?:_L(\d+))?$", name)
+    if m:
+        di, do = int(m.group(2)), int(m.group(3))
+        rows = fr[f"L{int(m.group(4))}"]["rows"] if (fr is not None and m.group(4)) else n
+        if m.group(1) == "fwd":
+            return rows * (4.0 * (2 * di + do) + 4 + do)
+        return rows * (4.0 * (2 * do + 2 * di + 2 * di) + 4 + do)
     return None
+
+
+def gathered_bytes(name: str, g, graph, fr) -> float | None:
+    """Bytes the gather moves from L2 to the SMs: one d-wide row per live edge (the L2-resident regime's real traffic)."""
+    m = __import__("re").match(r"(spmmT?)_d(\d+)(?:_(rows|edges|scatter|pruned))?(?:_L(\d+))?$", name)
+    if not m:
+        return None
+    d, var, lvl = int(m.group(2)), m.group(3), int(m.group(4)) if m.group(4) else None
+    if var is None or fr is None or lvl is None:
+        return 4.0 * d * graph.nnz
+    key = "edges" if (m.group(1) == "spmm" or var == "scatter") else "edges_t"
+    # transposed gather over the level below: live edges = edges out of this level's rows (A is structurally symmetric)
+    return 4.0 * d * fr[f"L{lvl}"]["edges" if key == "edges" else "edges"]
+
+
+def l2_gather_peak():
+    """Measured L2 -> SM random row-gather peak of this GPU (tools/microbench/l2_gather, ~2 s); None if the binary is absent."""
+    exe = ROOT / "tools" / "microbench" / "l2_gather"
+    if not exe.exists():
+        return None
+    try:
+        out = subprocess.run([str(exe), "--json"], capture_output=True, text=True, timeout=120, check=True).stdout.strip().splitlines()[-1]
+        return json.loads(out)
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
+def time_cuda(fn, reps: int, warm: int = 2) -> float:
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / 1e3 / reps
+
+
+def extra_shape_block(shape: str, dev, n_cf: int = 20, n_kg: int = 100, topk_users: bool = False):
+    """A secondary BASELINE.json configuration on this GPU: measured CF / KG step and refresh through the CUDA-graph engine,
+    extrapolated to that shape's epoch with the reference's batch counts; optionally the full-graph top-20 for all users."""
+    from kgat_b200 import synthetic
+    from kgat_b200.engine import TrainEngine
+    from kgat_b200.trainer import EpochData, build_model
+
+    t0 = time.perf_counter()
+    g = synthetic.make_ckg(shape, with_dicts=topk_users)
+    data = EpochData.sample(g, n_cf=n_cf, n_kg=n_kg)
+    model = build_model(g, dev)
+    eng = TrainEngine(model)
+    eng.bind_resident(data.tensors())
+    eng.run_epoch(n_cf=2, n_kg=2)  # captures the graphs, first refresh
+    eng.run_epoch(n_cf=n_cf, n_kg=n_kg)
+    ph = dict(eng.last_phase_ms)
+    from kgat_b200.sampler import BatchSampler
+
+    s = BatchSampler(g)
+    e_cf, e_kg = s.cf_batches_per_epoch(256), s.kg_batches_per_epoch(512)
+    cf_us, kg_us = 1e3 * ph["cf"] / n_cf, 1e3 * ph["kg"] / n_kg
+    out = {"shape": shape, "nodes": g.node_num, "nnz": g.nnz, "cf_step_us": cf_us, "kg_step_us": kg_us, "refresh_ms": ph["refresh"],
+           "epoch_steps": [e_cf, e_kg], "epoch_s_extrapolated": (e_cf * cf_us + e_kg * kg_us) / 1e6 + ph["refresh"] / 1e3,
+           "frontier": frontier_stats(eng, model._graph()), "setup_s": None,
+           "measured": f"{n_cf} CF + {n_kg} KG graph-replayed steps and one refresh; epoch = steps x the reference's batch counts (main.py:297, 324)"}
+    if topk_users:
+        from kgat_b200.metrics import InteractionCSR, evaluate
+
+        model.eval()
+        train = InteractionCSR(g.train_dict, g.user_num, g.item_num, dev)
+        test = InteractionCSR(g.test_dict, g.user_num, g.item_num, dev)
+        users = np.arange(g.user_num)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        res, _ = evaluate(model, train, test, k_list=(20,), batch_size=256, users=users)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t1
+        out["full_graph_top20"] = {"users": int(g.user_num), "items": int(g.item_num), "seconds": dt, "users_per_s": g.user_num / dt,
+                                   "recall@20": float(res[20]["recall"]), "ndcg@20": float(res[20]["ndcg"]), "precision@20": float(res[20]["precision"]),
+                                   "what": "one propagation (cached across batches) + per 256 users: score GEMM, train-positive mask, exact top-20, metrics"}
+    out["setup_s"] = time.perf_counter() - t0
+    del eng, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def c5_scaled_block(dev, peak):
+    """configs[4] scaled 5x down (2.2 M nodes, 40 M edges, d = 128, layers 128-64-32-16): one full propagation step, forward +
+    backward, where the 1.1 GB table no longer fits the L2 and HBM is the bound."""
+    from kgat_b200 import synthetic
+    from kgat_b200.functions import DropoutSpec, propagate_backward, propagate_forward
+    from kgat_b200.graph import AttentiveGraph
+
+    n5, d5 = 2_200_000, 128
+    h5, _, t5 = synthetic.make_edges_only(n5, 40_000_000, 64)
+    deg5 = np.bincount(h5, minlength=n5).astype(np.float32)
+    g5 = AttentiveGraph.from_coo(torch.from_numpy(h5.astype(np.int64)).to(dev), torch.from_numpy(t5.astype(np.int64)).to(dev),
+                                 torch.from_numpy((1.0 / deg5[h5]).astype(np.float32)).to(dev), n5)
+    dims = [d5, 128, 64, 32, 16]
+    torch.manual_seed(0)
+    layers = [(torch.randn(dims[i + 1], dims[i], device=dev) * 0.1, torch.zeros(dims[i + 1], device=dev),
+               torch.randn(dims[i + 1], dims[i], device=dev) * 0.1, torch.zeros(dims[i + 1], device=dev)) for i in range(4)]
+    e0 = torch.randn(n5, d5, device=dev) * 0.1
+    drop = DropoutSpec(ps=[0.1] * 4, seed=1)
+
+    def step():
+        st = propagate_forward(g5, e0, layers, drop, save=True)
+        g_last = torch.ones_like(st.tables[-1])
+        propagate_backward(g5, st, layers, g_last, lambda l, buf: None)
+
+    x5 = e0
+    y5 = torch.empty_like(x5)
+    t_spmm = time_cuda(lambda: g5.matmul(x5, out=y5), 5)
+    t_step = time_cuda(step, 3, warm=1)
+    b_gather = 8.0 * g5.nnz + 16.0 * g5.plan.n_tasks + 4.0 * g5.nnz * d5 + 4.0 * n5 * d5
+    out = {"nodes": n5, "nnz": g5.nnz, "dims": dims, "table_bytes": 4.0 * n5 * d5,
+           "propagation_step_ms": t_step * 1e3, "propagated_edges_per_s": g5.nnz * 4 * 2 / t_step,
+           "spmm_d128": {"ms": t_spmm * 1e3, "algorithmic_bytes": b_gather, "achieved": b_gather / t_spmm / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": b_gather / t_spmm / 1e9 / peak, "edges_per_s": g5.nnz / t_spmm,
+                         "model": "B_gather (SURVEY.md 8d): the table is 9x the L2, one 512 B neighbour row per edge is compulsory HBM traffic; "
+                                  "Zipf hubs still hit the L2, so the figure can exceed the copy peak"},
+           "what": "full (unpruned) 4-layer propagation forward + backward with message dropout, one GPU; the sharded run is in the N > 1 lines"}
+    del g5, e0, layers
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -292,10 +456,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-hbm-regime", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary shapes (Yelp2018 top-20, scaled C5, full Codeforces)")
+    ap.add_argument("--budget-s", type=float, default=330.0, help="wall-clock budget: optional blocks are skipped once it is spent")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    t_start = time.perf_counter()
 
     import kgat_b200  # noqa: F401
     from kgat_b200 import _lib, ops
@@ -303,7 +470,6 @@ def main():
     from kgat_b200.trainer import build_model, run_epoch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
@@ -358,12 +524,15 @@ def main():
     phases = dict(engine.last_phase_ms)
     epoch_s = t0.elapsed_time(t1) / 1e3 / max(args.steps, 1)
     clk = clocks.summary()
+    graph = model._graph()
+    fr = frontier_stats(engine, graph)
 
     # ---- e2e: one epoch through the reference-facing model API (model(...), loss.backward(),
     #      update_*_weights(), loss.item()) from pinned host buffers; and the same through the engine ----
     e2e = None
     if not args.no_e2e:
         steps_in_epoch = data.n_cf + data.n_kg
+        run_epoch(model, host_data, read_loss_every_step=True, n_cf=8, n_kg=8, refresh=False)  # capture the API graphs (untimed)
         barrier()
         w0 = time.perf_counter()
         _, _, h2d, d2h = run_epoch(model, host_data, read_loss_every_step=True)
@@ -380,18 +549,16 @@ def main():
         e2e = {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "api": "model(..., mode=TRAIN_CF/TRAIN_KG/UPDATE_ATTENTION) + loss.backward() + update_*_weights() + loss.item()",
                "engine_value": e2e_engine_s,
-               "note": f"bytes are per epoch (= one bench step: {steps_in_epoch} model steps; ids copied host->device and the loss read back every model step); "
-                       "engine_value = same host buffers through the CUDA-graph TrainEngine"}
+               "note": f"bytes are per epoch (= one bench step: {steps_in_epoch} model steps; every model step copies its ids from pinned host "
+                       "memory and reads its loss back on the host); engine_value = same host buffers through the CUDA-graph TrainEngine"}
 
     # ---- per-kernel split + roofline of the dominant kernel (live CUDA events, same process) ----
     n_probe_cf, n_probe_kg = 30, 60
     # eager (un-captured) launches so that every kernel can be bracketed by its own pair of CUDA events
-    model.api_graphs = False
-    model._cf_optimizer.use_graphs = model._kg_optimizer.use_graphs = False
+    probe = TrainEngine(model, use_graphs=False)
+    probe.bind_resident(data.tensors())
     with ops.KernelTimer() as kt:
-        run_epoch(model, dev_data, n_cf=n_probe_cf, n_kg=n_probe_kg, refresh=False)
-    model.api_graphs = True
-    model._cf_optimizer.use_graphs = model._kg_optimizer.use_graphs = True
+        probe.run_epoch(n_cf=n_probe_cf, n_kg=n_probe_kg, refresh=False)
     ksum = kt.summary()
     per_epoch_ms = {}
     for name, (cnt, ms) in ksum.items():
@@ -400,104 +567,118 @@ def main():
             continue
         scale = (data.n_cf / n_probe_cf) if cf_kernel else (data.n_kg / n_probe_kg)
         per_epoch_ms[name] = {"launches_per_epoch": int(cnt * scale), "avg_us": 1e3 * ms / cnt, "epoch_ms": ms * scale}
-    # adam_apply runs in both phases with different tensor sets: split by position
     if "adam_apply" in kt.events:
         ev = kt.events["adam_apply"]
         cf_ms = sum(a.elapsed_time(b) for a, b in ev[:n_probe_cf])
         kg_ms = sum(a.elapsed_time(b) for a, b in ev[n_probe_cf:])
         per_epoch_ms["adam_apply_cf"] = {"launches_per_epoch": data.n_cf, "avg_us": 1e3 * cf_ms / n_probe_cf, "epoch_ms": cf_ms * data.n_cf / n_probe_cf}
         per_epoch_ms["adam_apply_kg"] = {"launches_per_epoch": data.n_kg, "avg_us": 1e3 * kg_ms / max(n_probe_kg, 1), "epoch_ms": kg_ms * data.n_kg / max(n_probe_kg, 1)}
-    # dominant kernel = the propagation kernel (north_star) with the largest share of the epoch; the eager probe inflates
-    # the ~50 us kernels of the KG phase (launch gaps between the two events), so they are reported separately below
-    top = max((k for k in per_epoch_ms if k.startswith("spmm")), key=lambda k: per_epoch_ms[k]["epoch_ms"])
+    # dominant kernel = the propagation kernel (north_star) with the largest share of the epoch
+    prop = [k for k in per_epoch_ms if k.startswith("spmm") or k.startswith("biagg_fwd") or k.startswith("biagg_bwd")]
+    top = max(prop, key=lambda k: per_epoch_ms[k]["epoch_ms"])
+    top_spmm = max((k for k in prop if k.startswith("spmm")), key=lambda k: per_epoch_ms[k]["epoch_ms"])
     peak, peak_kind = peaks()
-    graph = model._graph()
-    emb_numel = model._user_entity_embedding.weight.numel()
-    if top.startswith("adam_apply"):
-        abytes = 7.0 * 4 * emb_numel
-    else:
-        abytes = algorithmic_bytes(top, g, graph)
-    achieved = abytes / (per_epoch_ms[top]["avg_us"] * 1e-6) / 1e9 if abytes else None
-    traffic = None
+    traffic_all = {}
     tfile = ROOT / "profiles" / "ncu_traffic.json"
     if tfile.exists():
-        traffic = json.loads(tfile.read_text()).get(top)
-    roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)", "algorithmic_bytes_per_launch": abytes,
-                "model": "B_min (every distinct byte once, SURVEY.md 8d); gather_gbs adds one neighbour-row read per edge (L2 traffic)"}
-    if top.startswith("spmm"):
-        d = int(top.replace("_pruned", "").split("_d")[1])
-        roofline["gather_gbs"] = (abytes + 4.0 * graph.nnz * d) / (per_epoch_ms[top]["avg_us"] * 1e-6) / 1e9
-    # the dense Adam sweep of the KG phase (second-largest single kernel), timed back to back so launch gaps do not count
+        traffic_all = json.loads(tfile.read_text())
+
+    def roof(name):
+        abytes = algorithmic_bytes(name, g, graph, fr)
+        us = per_epoch_ms[name]["avg_us"]
+        ach = abytes / (us * 1e-6) / 1e9 if abytes else None
+        return {"kernel": name, "bound": "hbm", "avg_us": us, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+                "traffic": traffic_all.get(name), "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                "algorithmic_bytes_per_launch": abytes,
+                "model": "B_min (every distinct byte once, SURVEY.md 8d) over the rows / edges the pruned step touches"}
+
+    roofline = roof(top)
+    roofline_all = {k: {kk: vv for kk, vv in roof(k).items() if kk in ("avg_us", "achieved", "frac", "algorithmic_bytes_per_launch")} for k in prop}
+    # the same kernel against what actually bounds it while the 41 MB table sits in the L2: the L2 -> SM gather fabric
+    l2 = l2_gather_peak()
+    roofline_l2 = None
+    if l2 and "gather_peak_gbs" in l2:
+        gb = gathered_bytes(top_spmm, g, graph, fr)
+        ab = algorithmic_bytes(top_spmm, g, graph, fr)
+        us = per_epoch_ms[top_spmm]["avg_us"]
+        ach = (gb + ab) / (us * 1e-6) / 1e9
+        roofline_l2 = {"kernel": top_spmm, "bound": "l2_gather", "avg_us": us, "achieved": ach, "peak": l2["gather_peak_gbs"], "unit": "GB/s",
+                       "frac": ach / l2["gather_peak_gbs"], "gathered_bytes_per_launch": gb, "streamed_bytes_per_launch": ab,
+                       "peak_source": "tools/microbench/l2_gather run in this process's job: random 256 B rows out of a 41 MB table, all SMs, no compute",
+                       "microbench": l2}
+    elif l2:
+        roofline_l2 = l2
+    # the dense Adam sweep of the KG phase (largest single kernel of the epoch), timed back to back so launch gaps do not count
     ad = engine.kg_adam
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     snap = ad.snapshot()
-    e0.record()
-    for _ in range(20):
-        ad.apply(engine.kg_grads)
-    e1.record()
-    torch.cuda.synchronize()
+    adam_s = time_cuda(lambda: ad.apply(engine.kg_grads), 20, warm=1)
     ad.restore(snap)
-    adam_us = 1e3 * e0.elapsed_time(e1) / 20
     adam_bytes = 7.0 * 4 * sum(p.numel() for p in ad.params)
-    roofline_adam = {"kernel": "adam_kernel (KG phase, dense sweep)", "bound": "hbm", "avg_us": adam_us, "algorithmic_bytes_per_launch": adam_bytes,
-                     "achieved": adam_bytes / (adam_us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s", "frac": adam_bytes / (adam_us * 1e-6) / 1e9 / peak}
+    roofline_adam = {"kernel": "adam_kernel (KG phase, dense sweep)", "bound": "hbm", "avg_us": adam_s * 1e6, "algorithmic_bytes_per_launch": adam_bytes,
+                     "achieved": adam_bytes / adam_s / 1e9, "peak": peak, "unit": "GB/s", "frac": adam_bytes / adam_s / 1e9 / peak}
 
-    # ---- the same SpMM kernel where HBM, not L2, is the binding roofline: C5-style graph (configs[4] scaled 5x down:
-    #      2.2 M nodes, 40 M edges, d = 128 -> 1.1 GB table >> 126 MB L2, every neighbour row is fetched from HBM) ----
-    hbm_regime = None
-    if not args.no_hbm_regime:
-        from kgat_b200 import synthetic
-        from kgat_b200.graph import AttentiveGraph
+    def left():
+        return args.budget_s - (time.perf_counter() - t_start)
 
-        n5, d5 = 2_200_000, 128
-        h5, _, t5 = synthetic.make_edges_only(n5, 40_000_000, 64)
-        deg5 = np.bincount(h5, minlength=n5).astype(np.float32)
-        g5 = AttentiveGraph.from_coo(torch.from_numpy(h5.astype(np.int64)).to(dev), torch.from_numpy(t5.astype(np.int64)).to(dev),
-                                     torch.from_numpy((1.0 / deg5[h5]).astype(np.float32)).to(dev), n5)
-        x5 = torch.randn(n5, d5, device=dev)
-        y5 = torch.empty_like(x5)
-        for _ in range(3):
-            g5.matmul(x5, out=y5)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        e0.record()
-        for _ in range(reps):
-            g5.matmul(x5, out=y5)
-        e1.record()
-        torch.cuda.synchronize()
-        t5s = e0.elapsed_time(e1) / 1e3 / reps
-        b_gather = 8.0 * g5.nnz + 16.0 * g5.plan.n_tasks + 4.0 * g5.nnz * d5 + 4.0 * n5 * d5  # edges + one 512 B row per edge + output
-        hbm_regime = {"kernel": "spmm_d128", "nodes": n5, "nnz": g5.nnz, "d": d5, "table_bytes": 4.0 * n5 * d5, "ms": t5s * 1e3,
-                      "algorithmic_bytes": b_gather, "achieved": b_gather / t5s / 1e9, "peak": peak, "unit": "GB/s",
-                      "frac": b_gather / t5s / 1e9 / peak, "edges_per_s": g5.nnz / t5s,
-                      "model": "B_gather (SURVEY.md 8d: the table is 9x the L2, so one neighbour-row read per edge is compulsory HBM traffic)"}
-        del g5, x5, y5
-
-    # ---- CPU baseline (oracle port, bounded sample) ----
-    cpu = None
+    # ---- baselines: the unmodified reference on the host cores (bounded sample) and on this GPU (the same-box incumbent) ----
+    cpu = incumbent = None
     if not args.no_cpu_baseline:
-        c = cpu_reference_sample(g, init_state, data)
-        cpu = {"value": c["epoch_s_extrapolated"], "unit": UNIT, "cores": c["cores"], "kind": "port", "sample": c["sample"],
-               "cf_step_s": c["cf_step_s"], "kg_step_s": c["kg_step_s"], "refresh_s": c["refresh_s_extrapolated"]}
-        try:  # the same port on the GPU itself (stock ATen kernels): reported next to the CPU figure
-            cpu["same_port_on_gpu"] = aten_gpu_sample(g, init_state, data, dev)
+        try:
+            r = ReferenceRunner(g, init_state, data, "cpu")
+            c = r.sample(n_cf=3, n_kg=3)
+            cpu = {"value": c["epoch_s_extrapolated"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"], "sample": c["sample"],
+                   "cf_step_s": c["cf_step_s"], "kg_step_s": c["kg_step_s"], "refresh_s": c["refresh_s_extrapolated"]}
+            del r
         except Exception as e:  # noqa: BLE001 - a baseline must never take the bench line down
-            cpu["same_port_on_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+            cpu = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        try:
+            r = ReferenceRunner(g, init_state, data, dev)
+            c = r.sample(n_cf=3, n_kg=10)
+            incumbent = {"value": c["epoch_s_extrapolated"], "unit": UNIT, "kind": c["kind"],
+                         "what": "the unmodified reference KGAT moved to this B200 (.to('cuda'): stock ATen / cuSPARSE kernels, torch.optim.Adam, the "
+                                 "device -> host -> device round trip of model.py:364-366, loss read every step)",
+                         "cf_step_s": c["cf_step_s"], "kg_step_s": c["kg_step_s"], "refresh_s": c["refresh_s_extrapolated"], "sample": c["sample"]}
+            del r
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            incumbent = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+    # ---- secondary configurations (BASELINE.json configs[3], [4] scaled, [1]) while the wall-clock budget lasts ----
+    extras = {}
+    if not args.no_extra:
+        for key, cost, fn in (("c4_yelp2018", 40, lambda: extra_shape_block("yelp2018", dev, topk_users=True)),
+                              ("c5_scaled", 60, lambda: c5_scaled_block(dev, peak)),
+                              ("c2_codeforces_full", 150, lambda: extra_shape_block("codeforces-full", dev, n_cf=10, n_kg=50))):
+            if key == "c5_scaled" and args.no_hbm_regime:
+                continue
+            if left() < cost:
+                extras[key] = {"skipped": f"wall-clock budget ({args.budget_s:.0f} s) spent; run with a larger --budget-s"}
+                continue
+            try:
+                extras[key] = fn()
+            except Exception as e:  # noqa: BLE001
+                extras[key] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
     n_layers = 3
-    edges_per_epoch = graph.nnz * n_layers * 2 * data.n_cf
+    ref_edges_per_epoch = graph.nnz * n_layers * 2 * data.n_cf
+    touched = sum(v["edges"] for v in fr.values()) * 2 * data.n_cf if fr else ref_edges_per_epoch
     line = {
         "metric": METRIC, "value": epoch_s, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": epoch_s * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(g, data, 1),
-        "propagation_edges_per_s": edges_per_epoch / epoch_s,
+        "propagation_edges_per_s": ref_edges_per_epoch / epoch_s,
+        "propagation_edges_per_s_note": "reference-equivalent: nnz x 3 layers x (fwd + bwd) x CF steps of the reference's full-graph propagation per "
+                                        "batch, divided by the measured epoch; edges_touched_per_s counts only the frontier's edges actually processed",
+        "edges_touched_per_s": touched / epoch_s, "frontier": fr,
         "cf_loss": losses[0], "kg_loss": losses[1],
         "phases": {"cf_phase_s": phases["cf"] / 1e3, "kg_phase_s": phases["kg"] / 1e3, "refresh_s": phases["refresh"] / 1e3,
                    "cf_step_us": 1e3 * phases["cf"] / max(phases["n_cf"], 1), "kg_step_us": 1e3 * phases["kg"] / max(phases["n_kg"], 1)},
         "e2e": e2e, "gpu_launches": launches, "clocks": clk,
-        "roofline": roofline, "roofline_hbm_regime": hbm_regime, "roofline_adam": roofline_adam, "cpu_baseline": cpu,
+        "roofline": roofline, "roofline_l2": roofline_l2, "roofline_adam": roofline_adam, "roofline_propagation_kernels": roofline_all,
+        "cpu_baseline": cpu, "gpu_incumbent": incumbent,
+        **extras,
         "kernels": {k: {kk: round(vv, 3) if isinstance(vv, float) else vv for kk, vv in v.items()} for k, v in sorted(per_epoch_ms.items(), key=lambda kv: -kv[1]["epoch_ms"])},
+        "bench_wall_s": time.perf_counter() - t_start,
     }
     print(json.dumps(line))
 

@@ -201,6 +201,14 @@ int kgat_biagg_backward_rows(const float* g_out, int64_t ld_gout, const float* o
  * clearing a whole n_rows x d gradient table per step (model.py:211-261 touches <= 3B of the N embedding rows) */
 int kgat_zero_rows_i64(float* T, int64_t n_rows, int64_t ld, int32_t d, const int64_t* ids64, int64_t n_ids, void* stream);
 
+/* Dense view of the compact TransR gradient rows (kgat_transr_step): dense[id, :] = g_rows[row_slot[id], :] for the batch's
+ * ids -- what autograd hands out as embedding.weight.grad (model.py:204-261), zero outside those rows, kept valid by
+ * kgat_transr_release_rows(previous batch's ids) = clear those rows and free their row_slot claims. */
+int kgat_transr_rows_to_dense(const float* g_rows, const int32_t* row_slot, const int64_t* heads, const int64_t* pos_tails,
+                              const int64_t* neg_tails, int32_t batch, int32_t d, float* dense, int64_t ld, void* stream);
+int kgat_transr_release_rows(float* dense, int64_t n_rows, int64_t ld, int32_t d, const int64_t* ids64, int64_t n_ids,
+                             int32_t* row_slot, void* stream);
+
 /* ------------------------------------------------------------------------------------------- */
 /* K4: BPR loss over the layer tables      reference model.py:189-202, 142-163                   */
 /* ------------------------------------------------------------------------------------------- */

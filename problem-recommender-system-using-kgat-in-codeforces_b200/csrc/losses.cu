@@ -347,12 +347,55 @@ __global__ void zero_rows_i64_kernel(float* __restrict__ T, int64_t ld, int d4, 
     reinterpret_cast<float4*>(T + r * ld)[i % d4] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// dense[id, :] = g_rows[slot, :] for every batch id whose claim this entry won (row_slot[id] == its index): the dense
+// embedding gradient autograd would hand out, restricted to the <= 3B rows that are not zero
+__global__ void transr_rows_to_dense_kernel(const float4* __restrict__ g_rows, const int32_t* __restrict__ row_slot,
+                                            const int64_t* __restrict__ heads, const int64_t* __restrict__ pt, const int64_t* __restrict__ nt,
+                                            int batch, int d4, float* __restrict__ dense, int64_t ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * batch * d4) return;
+    const int e = i / d4, q = i % d4;
+    const int64_t id = e < batch ? heads[e] : (e < 2 * batch ? pt[e - batch] : nt[e - 2 * batch]);
+    if (row_slot[id] != e) return;
+    reinterpret_cast<float4*>(dense + id * ld)[q] = g_rows[(int64_t)e * d4 + q];
+}
+
+// dense[ids[i], :] = 0 and row_slot[ids[i]] = -1: undo what the previous batch left behind
+__global__ void transr_release_rows_kernel(float* __restrict__ dense, int64_t ld, int d4, const int64_t* __restrict__ ids, int64_t n_ids,
+                                           int64_t n_rows, int32_t* __restrict__ row_slot) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_ids * d4) return;
+    const int64_t r = ids[i / d4];
+    if (r < 0 || r >= n_rows) return;
+    reinterpret_cast<float4*>(dense + r * ld)[i % d4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i % d4 == 0) row_slot[r] = -1;
+}
+
 }  // namespace
 }  // namespace kgat
 
 using namespace kgat;
 
 extern "C" {
+
+int kgat_transr_rows_to_dense(const float* g_rows, const int32_t* row_slot, const int64_t* heads, const int64_t* pos_tails,
+                              const int64_t* neg_tails, int32_t batch, int32_t d, float* dense, int64_t ld, void* stream) {
+    if (!g_rows || !row_slot || !heads || !pos_tails || !neg_tails || !dense || batch <= 0 || d <= 0 || (d & 3) || (ld & 3))
+        return KGAT_ERR_INVALID_ARGUMENT;
+    const int total = 3 * batch * (d / 4);
+    transr_rows_to_dense_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(g_rows), row_slot, heads,
+                                                                                    pos_tails, neg_tails, batch, d / 4, dense, ld);
+    return check_launch();
+}
+
+int kgat_transr_release_rows(float* dense, int64_t n_rows, int64_t ld, int32_t d, const int64_t* ids64, int64_t n_ids, int32_t* row_slot,
+                             void* stream) {
+    if (!dense || !ids64 || !row_slot || n_rows <= 0 || d <= 0 || (d & 3) || (ld & 3) || n_ids < 0) return KGAT_ERR_INVALID_ARGUMENT;
+    if (n_ids == 0) return KGAT_OK;
+    const int64_t total = n_ids * (d / 4);
+    transr_release_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dense, ld, d / 4, ids64, n_ids, n_rows, row_slot);
+    return check_launch();
+}
 
 int kgat_zero_rows_i64(float* T, int64_t n_rows, int64_t ld, int32_t d, const int64_t* ids64, int64_t n_ids, void* stream) {
     if (!T || !ids64 || n_rows <= 0 || d <= 0 || (d & 3) || (ld & 3) || n_ids < 0) return KGAT_ERR_INVALID_ARGUMENT;

@@ -55,7 +55,7 @@ def _buf(*shape, dtype=f32, device=None) -> torch.Tensor:
 def _row_args(frontier, level: int) -> dict:
     if frontier is None:
         return {}
-    return {"rows": frontier.rows(level), "n_rows_dev": frontier.count(level), "max_rows": frontier.cap(level)}
+    return {"rows": frontier.rows(level), "n_rows_dev": frontier.count(level), "max_rows": frontier.cap(level), "tag": f"_L{level}"}
 
 
 def propagate_forward(graph: AttentiveGraph, e0: torch.Tensor, layers, drop: DropoutSpec, save: bool = True, frontier=None) -> PropState:
@@ -73,7 +73,7 @@ def propagate_forward(graph: AttentiveGraph, e0: torch.Tensor, layers, drop: Dro
             side = graph.matmul(x, out=_buf(n, x.shape[1], device=dev))
         else:
             side = graph.matmul(x, out=_buf(n, x.shape[1], device=dev), row_mask=frontier.mask(l + 1), rows=frontier.rows(l + 1),
-                                n_rows_dev=frontier.count(l + 1))
+                                n_rows_dev=frontier.count(l + 1), tag=f"_L{l + 1}")
         out = _buf(n, d_out, device=dev)
         inv = _buf(n, device=dev) if save else None
         flags = _buf(n, d_out, dtype=torch.uint8, device=dev) if save else None
@@ -135,10 +135,10 @@ def propagate_backward(graph: AttentiveGraph, st: PropState, layers, g_last: tor
             g_prev = _buf(n, d_in, device=dev)
             ops.frontier_zero_rows(g_prev, frontier.rows(l - 1), frontier.count(l - 1), frontier.cap(l - 1))
             ops.spmm_scatter_rows(graph.plan, graph.col_idx, graph.vals, g_s, g_prev, frontier.rows(l), frontier.count(l), frontier.cap(l),
-                                  frontier.mask(l), addend=g_e)
+                                  frontier.mask(l), addend=g_e, tag=f"_L{l}")
         else:
             below = {"row_mask": frontier.mask(l - 1), "rows": frontier.rows(l - 1), "n_rows_dev": frontier.count(l - 1)} if l > 1 else {}
-            g_prev = graph.matmul_t(g_s, out=_buf(n, d_in, device=dev), addend=g_e, edge_mask=frontier.mask(l), **below)
+            g_prev = graph.matmul_t(g_s, out=_buf(n, d_in, device=dev), addend=g_e, edge_mask=frontier.mask(l), tag=f"_L{l}", **below)
         inject(l - 1, g_prev)
         g = g_prev
     return g, param_grads
@@ -279,6 +279,8 @@ class GraphedStep:
         self.adopted = 0  # serial whose gradients were handed to the parameters
         self.updated = 0  # serial whose gradients went through the fused optimiser step
         self.grads = None
+        self.adam_grads = None  # optional: the gradient tensors the fused optimiser replay reads instead of `grads` ...
+        self.adam_row_slot0 = None  # ... with compact rows for the first parameter (ops.adam_apply row_slot0)
         self._adam = {}
         self._lib = _lib.load()
         # the captured graph bakes in the addresses of every buffer the bodies' closures own (needed-row frontier, static
@@ -367,7 +369,8 @@ class GraphedStep:
         for p, g in zip(self.params, self.grads):
             if p.grad is not g:
                 return False
-        plan = opt.fast_plan(self.params, self.grads, self._grad_key)
+        plan = opt.fast_plan(self.params, self.adam_grads if self.adam_grads is not None else self.grads, self._grad_key,
+                             row_slot0=self.adam_row_slot0)
         if plan is None:
             return False
         opt.fast_replay(plan, self.params)

@@ -315,21 +315,28 @@ class KGAT(nn.Module):
             def make_bodies():
                 reg = float(self._regularization_params[1])
                 emb, rel, w = (p.detach() for p in params)
-                # static dense gradients (what autograd would hand out, model.py:204-261).  The N x d embedding gradient is
-                # all-zero outside the <= 3B rows of the previous batch, which are re-zeroed instead of clearing 41 MB a step.
-                kg_grads = [torch.zeros_like(p) for p in (emb, rel, w)]
-                prev_ids = torch.zeros(4, ids[0].numel(), dtype=torch.int64, device=emb.device)
+                b = ids[0].numel()
+                # One pass computes loss and gradients (csrc/losses.cu: kgat_transr_step): the embedding gradient lands in <= 3B
+                # compact rows (row_slot: node -> row), which the fused Adam replay reads directly.  The dense N x d
+                # ``embedding.weight.grad`` autograd would hand out (model.py:204-261) is kept valid as well -- zero outside the
+                # batch's rows, which are copied in after the pass and cleared again before the next one -- so anything that
+                # inspects ``.grad`` or steps another optimiser sees the reference's gradient.
+                g_dense = torch.zeros_like(emb)
+                g_rel, g_w = torch.zeros_like(rel), torch.zeros_like(w)
+                row_slot = torch.full((emb.shape[0],), -1, dtype=torch.int32, device=emb.device)
+                g_rows = torch.zeros(3 * b, emb.shape[1], dtype=torch.float32, device=emb.device)
+                prev_ids = torch.zeros(4, b, dtype=torch.int64, device=emb.device)
 
                 def body_fwd(st):
-                    ops.transr_forward(emb, rel, w, st.ids[0], st.ids[1], st.ids[2], st.ids[3], reg, st.loss, st.scratch)
+                    ops.transr_release_rows(g_dense, prev_ids.view(-1), row_slot)  # the previous batch's rows and slot claims
+                    ops.transr_step(emb, rel, w, st.ids[0], st.ids[1], st.ids[2], st.ids[3], reg, st.loss, None, st.scratch, row_slot, g_rows,
+                                    g_rel, g_w)
 
                 def body_bwd(st):
-                    ops.zero_rows_(kg_grads[0], prev_ids.view(-1))
-                    ops.fill_(kg_grads[1], 0.0)
-                    ops.fill_(kg_grads[2], 0.0)
-                    ops.transr_backward(emb, rel, w, st.ids[0], st.ids[1], st.ids[2], st.ids[3], reg, st.scratch, st.g_loss, *kg_grads)
+                    ops.transr_rows_to_dense(g_rows, row_slot, st.ids[0], st.ids[2], st.ids[3], g_dense)
                     prev_ids.copy_(st.ids)
-                    return kg_grads
+                    st.adam_grads, st.adam_row_slot0 = [g_rows, g_rel, g_w], row_slot
+                    return [g_dense, g_rel, g_w]
                 return body_fwd, body_bwd
 
             step = self._api_step("kg", ids[0].numel(), params, None, 4, make_bodies)

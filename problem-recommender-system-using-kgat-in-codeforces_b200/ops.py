@@ -186,15 +186,15 @@ def fill_(t: torch.Tensor, value: float = 0.0):
 # ----------------------------------------------------------------------------------------------
 
 
-def _spmm_name(plan, col_idx, vals, x, out, addend=None, partials=None, row_mask=None, edge_mask=None, rows=None, n_rows_dev=None):
+def _spmm_name(plan, col_idx, vals, x, out, addend=None, partials=None, row_mask=None, edge_mask=None, rows=None, n_rows_dev=None, tag=""):
     kind = "_rows" if rows is not None else ("_edges" if edge_mask is not None else ("_pruned" if row_mask is not None else ""))
-    return f"spmm{'T' if addend is not None else ''}_d{x.shape[1]}{kind}"
+    return f"spmm{'T' if addend is not None else ''}_d{x.shape[1]}{kind}{tag}"
 
 
 @_timed(_spmm_name)
 def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.Tensor | None = None, partials=None,
          row_mask: torch.Tensor | None = None, edge_mask: torch.Tensor | None = None, rows: torch.Tensor | None = None,
-         n_rows_dev: torch.Tensor | None = None):
+         n_rows_dev: torch.Tensor | None = None, tag: str = ""):
     """out = A @ x (+ addend); ``plan`` is a graph.SpmmPlan.  ``row_mask`` / ``edge_mask``: node bitmaps of a
     ``frontier.Frontier`` level (only the rows in ``row_mask`` are computed; edges / addend rows outside ``edge_mask`` are
     dropped).  With the level's row list (``rows``, ``n_rows_dev``; needs ``row_mask`` too) or with an ``edge_mask`` alone the
@@ -240,8 +240,9 @@ def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.
     return out
 
 
-@_timed(lambda plan, col_idx, vals, g, out, *a, **k: f"spmmT_d{g.shape[1]}_scatter")
-def spmm_scatter_rows(plan, col_idx, vals, g: torch.Tensor, out: torch.Tensor, rows, n_rows_dev, max_rows: int, row_mask, addend=None):
+@_timed(lambda plan, col_idx, vals, g, out, *a, **k: f"spmmT_d{g.shape[1]}_scatter{k.get('tag', '')}")
+def spmm_scatter_rows(plan, col_idx, vals, g: torch.Tensor, out: torch.Tensor, rows, n_rows_dev, max_rows: int, row_mask, addend=None,
+                      tag: str = ""):
     """out[c] += A[r, c] * g[r] over the listed rows r (and out[r] += addend[r]); ``plan`` / ``col_idx`` / ``vals`` of A itself.
     The destination rows of ``out`` must have been zeroed (frontier_zero_rows)."""
     lib = _lib.load()
@@ -303,9 +304,9 @@ def frontier_zero_rows(table: torch.Tensor, rows, count_dev, max_rows: int):
 # ----------------------------------------------------------------------------------------------
 
 
-@_timed(lambda E, S, W1, *a, **k: f"biagg_fwd_{E.shape[1]}x{W1.shape[0]}{'_pruned' if k.get('rows') is not None else ''}")
+@_timed(lambda E, S, W1, *a, **k: f"biagg_fwd_{E.shape[1]}x{W1.shape[0]}{'_rows' if k.get('rows') is not None else ''}{k.get('tag', '')}")
 def biagg_forward(E, S, W1, b1, W2, b2, out, inv_norm, flags, dropout_p=0.0, seed=0, offset=0, keep_bits=None, seed_dev=None,
-                  peer_out=None, rows=None, n_rows_dev=None, max_rows=None):
+                  peer_out=None, rows=None, n_rows_dev=None, max_rows=None, tag: str = ""):
     """``peer_out``: int64 device tensor of pointers to this rank's rows in every peer's copy of ``out`` (peer.PeerArena).
     ``rows`` / ``n_rows_dev`` / ``max_rows``: needed-row list of a ``frontier.Frontier`` level (arrays stay node-indexed)."""
     lib = _lib.load()
@@ -344,9 +345,9 @@ def biagg_backward_ctas(n: int, d_in: int, d_out: int, rows: bool = False) -> in
     return lib.kgat_biagg_backward_rows_ctas(n, d_in, d_out) if rows else lib.kgat_biagg_backward_ctas(n, d_in, d_out)
 
 
-@_timed(lambda g_out, out, inv_norm, flags, E, S, W1, *a, **k: f"biagg_bwd_{E.shape[1]}x{W1.shape[0]}{'_pruned' if k.get('rows') is not None else ''}")
+@_timed(lambda g_out, out, inv_norm, flags, E, S, W1, *a, **k: f"biagg_bwd_{E.shape[1]}x{W1.shape[0]}{'_rows' if k.get('rows') is not None else ''}{k.get('tag', '')}")
 def biagg_backward(g_out, out, inv_norm, flags, E, S, W1, W2, dropout_p, g_S, g_E, partials, n_ctas, peer_out=None, rows=None,
-                   n_rows_dev=None, max_rows=None):
+                   n_rows_dev=None, max_rows=None, tag: str = ""):
     lib = _lib.load()
     n, d_in = E.shape
     d_out = W1.shape[0]
@@ -465,6 +466,21 @@ def transr_step(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, loss, loss_sum,
                                _ptr(heads, i64), _ptr(rels, i64), _ptr(pos_t, i64), _ptr(neg_t, i64), heads.numel(), float(reg),
                                _ptr(loss, f32), _ptr(loss_sum, f32) if loss_sum is not None else None, _ptr(scratch, f32),
                                _ptr(row_slot, i32), _ptr(g_rows, f32), _ptr(g_rel, f32), _ptr(g_W, f32), _stream()), "transr_step")
+
+
+def transr_rows_to_dense(g_rows, row_slot, heads, pos_t, neg_t, dense):
+    """dense[id] = g_rows[row_slot[id]] for the batch's ids (the dense ``embedding.weight.grad`` of a TransR step)."""
+    lib = _lib.load()
+    check(lib.kgat_transr_rows_to_dense(_ptr(g_rows, f32), _ptr(row_slot, i32), _ptr(heads, i64), _ptr(pos_t, i64), _ptr(neg_t, i64),
+                                        heads.numel(), dense.shape[1], _ptr(dense, f32, "dense", True), dense.stride(0), _stream()),
+          "transr_rows_to_dense")
+
+
+def transr_release_rows(dense, ids, row_slot):
+    """dense[ids] = 0 and row_slot[ids] = -1 (the previous batch's rows)."""
+    lib = _lib.load()
+    check(lib.kgat_transr_release_rows(_ptr(dense, f32, "dense", True), dense.shape[0], dense.stride(0), dense.shape[1], _ptr(ids, i64),
+                                       ids.numel(), _ptr(row_slot, i32), _stream()), "transr_release_rows")
 
 
 def transr_backward(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, scratch, g_loss, g_emb, g_rel, g_W, row_slot=None):

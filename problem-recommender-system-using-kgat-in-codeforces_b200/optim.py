@@ -65,7 +65,7 @@ class FusedAdam(torch.optim.Optimizer):
         return True
 
     # -- the API fast path (functions.GraphedStep.try_fused_update) ---------------------------------
-    def fast_plan(self, ps, grads, grads_key=None):
+    def fast_plan(self, ps, grads, grads_key=None, row_slot0=None):
         """Captured ``adam_advance + adam_apply`` over exactly ``(ps, grads)`` (static gradient buffers of a graphed step),
         or None when it cannot be used yet: first sighting (the generic path creates the state and warms the kernels up),
         parameters with different step counts, graphs disabled, or some other parameter of the group holds a gradient."""
@@ -99,7 +99,7 @@ class FusedAdam(torch.optim.Optimizer):
             torch.cuda.synchronize()
             with torch.cuda.graph(plan["graph"]):
                 ops.adam_advance(plan["step_dev"], group["lr"], beta1, beta2, group["eps"], plan["hyper"])
-                ops.adam_apply(params, list(grads), ms, vs, plan["hyper"])
+                ops.adam_apply(params, list(grads), ms, vs, plan["hyper"], row_slot0=row_slot0)
             plan["exec"] = plan["graph"].raw_cuda_graph_exec()
             self._fast[key] = plan
         states = plan["states"]
