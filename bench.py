@@ -478,9 +478,9 @@ def main():
         dist.init_process_group("nccl")
         if args.gpus != world:
             raise SystemExit(f"--gpus {args.gpus} != WORLD_SIZE {world}")
-        from kgat_b200 import sharding
+        from kgat_b200 import sharded_pruned
 
-        sharding.bench_main(args, METRIC, UNIT, WORKLOAD, make_workload, config_dict, ClockSampler)
+        sharded_pruned.bench_main(args, METRIC, UNIT, WORKLOAD, make_workload, config_dict, ClockSampler)
         return
     if args.gpus != 1:
         raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")

@@ -150,6 +150,11 @@ int kgat_frontier_expand(const int32_t* tasks, int64_t n_heavy_tasks, const int3
 int64_t kgat_frontier_scratch_ints(int64_t n_nodes);
 int kgat_frontier_list(uint8_t* flags, uint32_t* bitmap, int64_t n_nodes, int32_t* scratch, int32_t* rows, int32_t* count_dev,
                        void* stream);
+/* The part of a level inside the node range [lo, hi) (lo a multiple of 32; hi a multiple of 32 or n_nodes): out_rows / out_count_dev
+ * = that segment of the ascending row list, out_bitmap = the level's bitmap with every word outside the range cleared.
+ * (Row-sharded runs: a rank computes the dense first layer for "level 1 AND my rows".) */
+int kgat_frontier_segment(const int32_t* rows, const int32_t* count_dev, const uint32_t* bitmap, int64_t n_nodes, int64_t lo, int64_t hi,
+                          int32_t* out_rows, int32_t* out_count_dev, uint32_t* out_bitmap, void* stream);
 /* T[rows[i], 0:d] = 0 for i < *count_dev (gradient rows of the last table before the BPR scatter) */
 int kgat_frontier_zero_rows(float* T, int64_t ld, int32_t d, const int32_t* rows, const int32_t* count_dev, int64_t max_rows,
                             void* stream);

@@ -155,12 +155,51 @@ __global__ void frontier_zero_rows_kernel(float* __restrict__ T, int64_t ld, int
     }
 }
 
+// The part of a level that falls into a node range [lo, hi) (both multiples of 32): its rows -- a contiguous segment of the
+// ascending list -- and its bitmap words.  Row-sharded multi-GPU runs compute a layer for "level AND my range".
+__global__ void __launch_bounds__(256) frontier_segment_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ cnt_dev,
+                                                               const uint32_t* __restrict__ mask, int lo, int hi, int n_words,
+                                                               int32_t* __restrict__ out_rows, int32_t* __restrict__ out_cnt,
+                                                               uint32_t* __restrict__ out_mask) {
+    __shared__ int seg[2];
+    if (threadIdx.x < 2) {  // first list position holding a row >= lo (thread 0) / >= hi (thread 1)
+        const int key = threadIdx.x == 0 ? lo : hi;
+        int a = 0, b = cnt_dev[0];
+        while (a < b) {
+            const int m = (a + b) >> 1;
+            if (rows[m] < key) a = m + 1; else b = m;
+        }
+        seg[threadIdx.x] = a;
+    }
+    __syncthreads();
+    const int begin = seg[0], n = seg[1] - seg[0];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (int i = tid; i < n; i += stride) out_rows[i] = rows[begin + i];
+    for (int w = tid; w < n_words; w += stride) out_mask[w] = (w >= (lo >> 5) && w < (hi >> 5)) ? mask[w] : 0u;
+    if (tid == 0) out_cnt[0] = n;
+}
+
 }  // namespace
 }  // namespace kgat
 
 using namespace kgat;
 
 extern "C" {
+
+int kgat_frontier_segment(const int32_t* rows, const int32_t* count_dev, const uint32_t* bitmap, int64_t n_nodes, int64_t lo, int64_t hi,
+                          int32_t* out_rows, int32_t* out_count_dev, uint32_t* out_bitmap, void* stream) {
+    if (!rows || !count_dev || !bitmap || !out_rows || !out_count_dev || !out_bitmap || n_nodes <= 0 || lo < 0 || hi < lo || (lo & 31) ||
+        ((hi & 31) && hi != n_nodes) || hi > ((n_nodes + 31) / 32) * 32 || n_nodes >= ((int64_t)1 << 31))
+        return KGAT_ERR_INVALID_ARGUMENT;
+    const int n_words = (int)((n_nodes + 31) / 32);
+    const int64_t hi_w = (hi + 31) / 32 * 32;  // the last range may end at n_nodes: its final word is whole anyway (no bits beyond n)
+    int ctas = (int)(((hi - lo) + 255) / 256);
+    if (ctas < 1) ctas = 1;
+    if (ctas > sm_count()) ctas = sm_count();
+    frontier_segment_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(rows, count_dev, bitmap, (int)lo, (int)hi_w, n_words, out_rows, out_count_dev,
+                                                                   out_bitmap);
+    return check_launch();
+}
 
 int64_t kgat_frontier_scratch_ints(int64_t n_nodes) {
     const int64_t n_words = (n_nodes + 31) / 32;

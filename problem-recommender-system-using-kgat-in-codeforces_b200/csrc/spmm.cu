@@ -8,6 +8,8 @@
 // lane).  (col, val) of 32 consecutive edges are read coalesced once and broadcast by shuffle.
 // Long rows are split by the host-side plan into chunks whose partial sums are reduced in a fixed
 // order by a second tiny kernel: deterministic, no atomics.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace kgat {
@@ -343,6 +345,16 @@ __global__ void __launch_bounds__(128) spmm_heavy_reduce_kernel(const int4* __re
 
 using namespace kgat;
 
+// loads in flight per lane for d = 64 (KGAT_SPMM_U = 4 | 8; A/B switch for the profiling runs)
+static int spmm_unroll64() {
+    static int u = 0;
+    if (u == 0) {
+        const char* e = getenv("KGAT_SPMM_U");
+        u = (e != nullptr && atoi(e) == 8) ? 8 : 4;
+    }
+    return u;
+}
+
 static int spmm_launch(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_rows, int64_t n_heavy, const int32_t* col_idx,
                        const float* vals, const float* X, int64_t n_cols, int64_t ldx, float* Y, int64_t ldy, const float* Z, int64_t ldz,
                        int32_t d, float* partials, const uint32_t* row_mask, const uint32_t* edge_mask, void* stream_) {
@@ -374,7 +386,10 @@ static int spmm_launch(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_row
     switch (d) {
         case 16: KGAT_SPMM_LAUNCH(16, 2); break;
         case 32: KGAT_SPMM_LAUNCH(32, 4); break;
-        case 64: KGAT_SPMM_LAUNCH(64, 4); break;
+        case 64:
+            if (spmm_unroll64() == 8) KGAT_SPMM_LAUNCH(64, 8);
+            else KGAT_SPMM_LAUNCH(64, 4);
+            break;
         case 128: KGAT_SPMM_LAUNCH(128, 4); break;
         default:
             if (masked) return KGAT_ERR_UNSUPPORTED;
@@ -440,7 +455,10 @@ extern "C" int kgat_spmm_csr_rows(const int32_t* tasks, int64_t n_tasks, int64_t
     switch (d) {
         case 16: KGAT_ROWS_LAUNCH(16, 2); break;
         case 32: KGAT_ROWS_LAUNCH(32, 4); break;
-        case 64: KGAT_ROWS_LAUNCH(64, 4); break;
+        case 64:
+            if (spmm_unroll64() == 8) KGAT_ROWS_LAUNCH(64, 8);
+            else KGAT_ROWS_LAUNCH(64, 4);
+            break;
         default: KGAT_ROWS_LAUNCH(128, 4); break;
     }
 #undef KGAT_ROWS_LAUNCH

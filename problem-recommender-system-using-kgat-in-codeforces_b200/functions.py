@@ -41,6 +41,10 @@ class PropState:
     ps: list = field(default_factory=list)
 
 
+import os as _os
+
+_L1_GRID = _os.environ.get("KGAT_L1_GRID") == "1"  # A/B switch: first layer through the grid-per-task kernel (early exit on dead rows)
+
 # Test hook: fill every freshly allocated propagation buffer with NaN (0xFF for flag bytes), so that a pruned step that
 # read a row outside its frontier would poison the loss / gradients (tests/test_gpu_pruning.py).
 POISON_STALE_ROWS = False
@@ -71,6 +75,8 @@ def propagate_forward(graph: AttentiveGraph, e0: torch.Tensor, layers, drop: Dro
         d_out = w1.shape[0]
         if frontier is None:
             side = graph.matmul(x, out=_buf(n, x.shape[1], device=dev))
+        elif l == 0 and _L1_GRID:
+            side = graph.matmul(x, out=_buf(n, x.shape[1], device=dev), row_mask=frontier.mask(1), tag="_L1")
         else:
             side = graph.matmul(x, out=_buf(n, x.shape[1], device=dev), row_mask=frontier.mask(l + 1), rows=frontier.rows(l + 1),
                                 n_rows_dev=frontier.count(l + 1), tag=f"_L{l + 1}")

@@ -293,6 +293,15 @@ def frontier_list(flags, bitmap, n_nodes: int, scratch, rows, count_dev):
                                  _stream()), "frontier_list")
 
 
+def frontier_segment(rows, count_dev, bitmap, n_nodes: int, lo: int, hi: int, out_rows, out_count_dev, out_bitmap):
+    """The part of a frontier level inside the node range [lo, hi): its row-list segment, count and bitmap words."""
+    lib = _lib.load()
+    if out_rows.numel() < hi - lo or out_bitmap.numel() * 32 < n_nodes:
+        raise KgatLibraryError("frontier_segment: output buffers too small")
+    check(lib.kgat_frontier_segment(_ptr(rows, i32), _ptr(count_dev, i32), _ptr(bitmap, i32), int(n_nodes), int(lo), int(hi), _ptr(out_rows, i32),
+                                    _ptr(out_count_dev, i32), _ptr(out_bitmap, i32), _stream()), "frontier_segment")
+
+
 def frontier_zero_rows(table: torch.Tensor, rows, count_dev, max_rows: int):
     lib = _lib.load()
     check(lib.kgat_frontier_zero_rows(_ptr(table, f32, "table", True), table.stride(0), table.shape[1], _ptr(rows, i32), _ptr(count_dev, i32),

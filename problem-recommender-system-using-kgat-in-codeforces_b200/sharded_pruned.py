@@ -1,0 +1,625 @@
+"""Row-sharded multi-GPU epoch on top of the needed-row pruning (frontier.py): one process per GPU.
+
+What shards.  After pruning, a TRAIN_CF step is dominated by its FIRST layer (the frontier of a 256-sample batch reaches
+~73 % of the nodes there, ~2 % in the second layer, < 1 % in the third) and by the dense Adam sweep over the embedding
+table; the upper layers, the BPR loss and their backward are a few thousand rows.  So
+
+  * every rank owns a CONTIGUOUS range of node rows (boundaries multiples of 32, balanced by a per-row cost of
+    "edges in A + edges in A^T + a constant" so neither the gather nor the per-row GEMM work is skewed by the node types
+    sitting in contiguous id blocks), the matching slice of the embedding table and of its Adam moments;
+  * per step a rank computes the first layer forward (SpMM + bi-interaction) and backward (bi-interaction backward, the
+    transposed gather, Adam) for "level 1 AND my rows" only;
+  * the upper layers, the loss and their backward are computed redundantly by every rank (identical inputs);
+  * three row exchanges per step over NVLink peer memory (peer.PeerArena: store kernel into every peer's copy of the
+    table + flag handshake, all stream-ordered, so the whole step is ONE captured CUDA graph per rank):
+        E1 rows   after the first layer's forward        (the sparse layers read them)
+        g_S rows  after the first layer's backward       (the transposed gather of my rows reads all of them)
+        E0 rows   after Adam                             (next step's first layer reads the whole table)
+    and one all-reduce of the 53 KB dense-parameter gradients (first layer: partial sums over the rows; upper layers:
+    replicas, averaged so that fp32 atomics noise cannot make the ranks drift apart).
+
+Tables keep the global node-id layout (no permutation), so every kernel of the single-GPU pruned step is reused as is;
+"my part of level 1" is a segment of the ascending row list plus the bitmap words of my range (kgat_frontier_segment).
+
+The KG phase and the refresh are replicated, as before (a TransR batch touches <= 1536 rows; the dense KG Adam sweep
+is what would have to shard, and every rank needs every updated row in the next step) -- the replicated parameters
+are re-broadcast from rank 0 once per epoch.  Strong scaling at the Amazon-book size is therefore bounded by the
+replicated part (KG phase + sparse layers) and by 3 x 36 MB of inbound rows per step; see DESIGN.md section 6.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from .engine import TrainEngine
+from .frontier import Frontier
+from .functions import DropoutSpec, _buf, last_table_grad
+from .model import KGATMode
+from .peer import PeerArena
+
+f32 = torch.float32
+
+
+def balanced_ranges(row_ptr: np.ndarray, t_ptr: np.ndarray, world: int, row_cost: float = 48.0) -> list[tuple[int, int]]:
+    """Contiguous node ranges [lo, hi) with lo a multiple of 32, balanced by edges(A) + edges(A^T) + row_cost per row."""
+    n = row_ptr.shape[0] - 1
+    cost = np.diff(row_ptr).astype(np.float64) + np.diff(t_ptr).astype(np.float64) + row_cost
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    cuts = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        i = int(np.searchsorted(cum, target))
+        i = min(max((i + 16) // 32 * 32, cuts[-1] + 32), n)
+        cuts.append(i)
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+class _LocalArena:
+    """Single-rank stand-in for peer.PeerArena (plain device tensors, no exchange): the engine's code path is the same."""
+
+    def __init__(self, device, tables):
+        self._t = {k: torch.zeros(r, d, dtype=f32, device=device) for k, (r, d) in tables.items()}
+
+    def table(self, name):
+        return self._t[name]
+
+    def push(self, *a, **k):
+        pass
+
+    def signal_wait(self, channel):
+        pass
+
+    def check(self):
+        pass
+
+    def close(self):
+        self._t.clear()
+
+
+class RangeShardedEngine:
+    def __init__(self, model, world: int, rank: int, use_graphs: bool = True, cf_batch: int = 256):
+        if not model.cf_pruning:
+            raise RuntimeError("RangeShardedEngine builds on the needed-row pruning (model.cf_pruning = True)")
+        self.model, self.world, self.rank, self.use_graphs = model, world, rank, use_graphs
+        self.dev = model._device()
+        self.cf_batch = cf_batch
+        self.single = TrainEngine(model, use_graphs=True)  # KG phase (replicated) and the refresh reuse the 1-GPU engine
+        self.dims = [model._cf_embedding_dim, *model._layer_dims]
+        self.layers = [tuple(t.detach() for t in grp) for grp in model._layers()]
+        self.n_flat = sum(t.numel() for grp in self.layers for t in grp)
+        n = model.node_num
+        self.n = n
+        spec = {"e0": (n, self.dims[0]), "e1": (n, self.dims[1]), "gs0": (n, self.dims[0]), "flat": (world, self.n_flat)}
+        self.arena = PeerArena(rank, world, self.dev, spec, n_channels=5) if world > 1 else _LocalArena(self.dev, spec)
+        self.cf_ids = torch.zeros(3, cf_batch, dtype=torch.int64, device=self.dev)
+        self.loss = torch.zeros(1, dtype=f32, device=self.dev)
+        self.loss_sum = torch.zeros(1, dtype=f32, device=self.dev)
+        self.scratch = torch.empty(2 * cf_batch, dtype=f32, device=self.dev)
+        self.one = torch.ones(1, dtype=f32, device=self.dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.hyper = torch.empty(8, dtype=f32, device=self.dev)
+        self._graph_id = None
+        self._cf_graph = None
+        self._cf_graph_key = None
+        self._cf_kernels = 0
+        self._resident = None
+        self._setup_graph()
+        self._sync_adam_from_model()
+        self.scatter_from_model()
+
+    # ------------------------------------------------------------------------------------------
+    def _setup_graph(self):
+        g = self.model._graph()
+        self._graph_id = (id(g), g.vals.data_ptr())
+        self.graph = g
+        self.bounds = balanced_ranges(g.row_ptr.cpu().numpy(), g.t_ptr.cpu().numpy(), self.world)
+        self.lo, self.hi = self.bounds[self.rank]
+        self.frontier = Frontier(g, len(self.layers), 3 * self.cf_batch)
+        words = self.frontier.words
+        cap = max(self.hi - self.lo, 1)
+        self.own_rows = torch.zeros(cap, dtype=torch.int32, device=self.dev)  # level 1 AND my range
+        self.own_cnt = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.own_mask = torch.zeros(words, dtype=torch.int32, device=self.dev)
+        # my whole range as a (static) level: rows, count and bitmap for the transposed gather that produces my gradient rows
+        self.range_rows = torch.arange(self.lo, self.hi, dtype=torch.int32, device=self.dev)
+        self.range_cnt = torch.tensor([self.hi - self.lo], dtype=torch.int32, device=self.dev)
+        bits = np.zeros(words * 32, dtype=bool)
+        bits[self.lo : self.hi] = True
+        self.range_mask = torch.from_numpy(np.packbits(bits, bitorder="little").view(np.int32).copy()).to(self.dev)
+        self._cf_graph = None
+
+    def _sync_adam_from_model(self):
+        """Adam state of the CF optimiser (model._cf_optimizer) as device views: my slice of the embedding moments + the dense ones."""
+        m = self.model
+        opt = m._cf_optimizer
+        emb = m._user_entity_embedding.weight
+        self.cf_params_model = [emb] + [t for grp in m._layers() for t in grp]
+        steps = set()
+        for p in self.cf_params_model:
+            st = opt.state[p]
+            if not st:
+                st["step"] = 0
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            steps.add(int(st["step"]))
+        if len(steps) != 1:
+            raise RuntimeError("all CF parameters must share one Adam step count")
+        self.step_dev.fill_(steps.pop())
+        self.emb_m, self.emb_v = opt.state[emb]["exp_avg"], opt.state[emb]["exp_avg_sq"]
+        self.dense_m = [opt.state[p]["exp_avg"] for p in self.cf_params_model[1:]]
+        self.dense_v = [opt.state[p]["exp_avg_sq"] for p in self.cf_params_model[1:]]
+        g = opt.param_groups[0]
+        self.lr, (self.b1, self.b2), self.eps = g["lr"], g["betas"], g["eps"]
+
+    def scatter_from_model(self):
+        self.arena.table("e0").copy_(self.model._user_entity_embedding.weight.detach())
+        self.arena.signal_wait(4)  # nobody stores rows into a table its owner is still overwriting
+
+    def gather_to_model(self, n_steps: int):
+        """Embedding table (complete on every rank after the last exchange) and the Adam moments of the other ranks' rows."""
+        m = self.model
+        emb = m._user_entity_embedding.weight
+        emb.data.copy_(self.arena.table("e0"))
+        w = emb.detach().double()
+        self.replica_checksum = torch.stack([w.sum(), w.abs().sum(), (w * w).sum()])  # must be identical on every rank (before any broadcast)
+        if self.world > 1:
+            for t in (self.emb_m, self.emb_v):  # every rank broadcasts its slice of the moments (once per epoch, outside the graphs)
+                for r, (lo, hi) in enumerate(self.bounds):
+                    if hi > lo:
+                        dist.broadcast(t[lo:hi], src=r)
+        for p in self.cf_params_model:
+            m._cf_optimizer.state[p]["step"] += n_steps
+            torch.autograd.graph.increment_version(p)
+
+    # ------------------------------------------------------------------------------------------
+    def _all_reduce_flat(self, flat: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return flat
+        slots = self.arena.table("flat")
+        slots[self.rank].copy_(flat)
+        self.arena.push("flat", self.rank, 1)
+        self.arena.signal_wait(2)
+        torch.sum(slots, dim=0, out=flat)  # rank order: bit-identical on every rank
+        return flat
+
+    def cf_step(self):
+        m, g, f = self.model, self.graph, self.frontier
+        L = len(self.layers)
+        u, p, q = self.cf_ids[0], self.cf_ids[1], self.cf_ids[2]
+        ps = [float(a.message_dropout.p) if m.training else 0.0 for a in m._aggregator_layers]
+        seed = 12345
+        reg = float(m._regularization_params[0])
+        n, dev = self.n, self.dev
+        lo, hi = self.lo, self.hi
+        E0, E1, GS0 = self.arena.table("e0"), self.arena.table("e1"), self.arena.table("gs0")
+        f.build([self.cf_ids.view(-1)])
+        ops.frontier_segment(f.rows(1), f.count(1), f.mask(1), n, lo, hi, self.own_rows, self.own_cnt, self.own_mask)
+        own = {"rows": self.own_rows, "n_rows_dev": self.own_cnt}
+        # ---- first layer, my rows of level 1
+        w1, b1, w2, b2 = self.layers[0]
+        S0 = g.matmul(E0, out=_buf(n, self.dims[0], device=dev), row_mask=self.own_mask, tag="_L1", **own)
+        inv1, flags1 = _buf(n, device=dev), _buf(n, self.dims[1], dtype=torch.uint8, device=dev)
+        ops.biagg_forward(E0, S0, w1, b1, w2, b2, E1, inv1, flags1, dropout_p=ps[0], seed=seed, offset=1 << 40, seed_dev=self.step_dev,
+                          max_rows=max(hi - lo, 1), tag="_L1", **own)
+        if hi > lo:
+            self.arena.push("e1", lo, hi - lo)
+        self.arena.signal_wait(0)
+        # ---- upper layers: replicated
+        tables, sides, invs, flagss = [E0, E1], [S0], [inv1], [flags1]
+        for l in range(1, L):
+            w1, b1, w2, b2 = self.layers[l]
+            lvl = l + 1
+            x = tables[-1]
+            side = g.matmul(x, out=_buf(n, x.shape[1], device=dev), row_mask=f.mask(lvl), rows=f.rows(lvl), n_rows_dev=f.count(lvl), tag=f"_L{lvl}")
+            out = _buf(n, self.dims[lvl], device=dev)
+            inv, flags = _buf(n, device=dev), _buf(n, self.dims[lvl], dtype=torch.uint8, device=dev)
+            ops.biagg_forward(x, side, w1, b1, w2, b2, out, inv, flags, dropout_p=ps[l], seed=seed, offset=lvl << 40, seed_dev=self.step_dev,
+                              rows=f.rows(lvl), n_rows_dev=f.count(lvl), max_rows=f.cap(lvl), tag=f"_L{lvl}")
+            tables.append(out)
+            sides.append(side)
+            invs.append(inv)
+            flagss.append(flags)
+        ops.bpr_forward(tables, u, p, q, reg, self.loss, self.scratch)
+
+        def inject(level, buf):
+            grads = [None] * (L + 1)
+            grads[level] = buf
+            ops.bpr_backward(tables, grads, u, p, q, reg, self.scratch, self.one)
+
+        class _St:
+            pass
+
+        st = _St()
+        st.tables = tables
+        grad = last_table_grad(st, f)
+        inject(L, grad)
+        pgrads = [None] * L
+        for l in range(L, 1, -1):  # layers L .. 2, replicated
+            w1, b1, w2, b2 = self.layers[l - 1]
+            x = tables[l - 1]
+            d_in, d_out = x.shape[1], w1.shape[0]
+            n_ctas = ops.biagg_backward_ctas(f.cap(l), d_in, d_out, rows=True)
+            partials = torch.empty(n_ctas * (2 * d_in * d_out + 2 * d_out), dtype=f32, device=dev)
+            g_s, g_e = _buf(n, d_in, device=dev), _buf(n, d_in, device=dev)
+            ops.biagg_backward(grad, tables[l], invs[l - 1], flagss[l - 1], x, sides[l - 1], w1, w2, ps[l - 1], g_s, g_e, partials, n_ctas,
+                               rows=f.rows(l), n_rows_dev=f.count(l), max_rows=f.cap(l), tag=f"_L{l}")
+            gw = [torch.empty_like(t) for t in (w1, b1, w2, b2)]
+            ops.biagg_reduce_param_grads(partials, n_ctas, d_in, d_out, *gw)
+            pgrads[l - 1] = gw
+            g_prev = _buf(n, d_in, device=dev)
+            ops.frontier_zero_rows(g_prev, f.rows(l - 1), f.count(l - 1), f.cap(l - 1))
+            ops.spmm_scatter_rows(g.plan, g.col_idx, g.vals, g_s, g_prev, f.rows(l), f.count(l), f.cap(l), f.mask(l), addend=g_e, tag=f"_L{l}")
+            inject(l - 1, g_prev)
+            grad = g_prev
+        # ---- first layer backward, my rows of level 1
+        w1, b1, w2, b2 = self.layers[0]
+        d_in, d_out = self.dims[0], self.dims[1]
+        n_ctas = ops.biagg_backward_ctas(max(hi - lo, 1), d_in, d_out, rows=True)
+        partials = torch.empty(n_ctas * (2 * d_in * d_out + 2 * d_out), dtype=f32, device=dev)
+        g_e0 = _buf(n, d_in, device=dev)
+        ops.biagg_backward(grad, E1, inv1, flags1, E0, S0, w1, w2, ps[0], GS0, g_e0, partials, n_ctas, max_rows=max(hi - lo, 1), tag="_L1", **own)
+        gw = [torch.empty_like(t) for t in (w1, b1, w2, b2)]
+        ops.biagg_reduce_param_grads(partials, n_ctas, d_in, d_out, *gw)
+        pgrads[0] = gw
+        if hi > lo:
+            self.arena.push("gs0", lo, hi - lo)
+        self.arena.signal_wait(1)
+        g_t0 = g.matmul_t(GS0, out=_buf(n, d_in, device=dev), addend=g_e0, row_mask=self.range_mask, rows=self.range_rows,
+                          n_rows_dev=self.range_cnt, edge_mask=f.mask(1), tag="_L1")
+        inject(0, g_t0)  # (the direct BPR part lands in every batch row; only my rows are read below)
+        # ---- dense-parameter gradients: layer 1 = partial sums over the ranks' rows, upper layers = replicas (averaged)
+        scale = 1.0 / self.world
+        flat = torch.cat([t.reshape(-1) for t in pgrads[0]] + [(t * scale).reshape(-1) for grp in pgrads[1:] for t in grp])
+        flat = self._all_reduce_flat(flat)
+        dense_grads, off = [], 0
+        for grp in self.layers:
+            for t in grp:
+                dense_grads.append(flat[off : off + t.numel()].view_as(t))
+                off += t.numel()
+        # ---- Adam: my slice of the embedding table (and of its moments) + the replicated dense parameters
+        ops.adam_advance(self.step_dev, self.lr, self.b1, self.b2, self.eps, self.hyper)
+        params = [t for grp in self.layers for t in grp]
+        grads, ms, vs = dense_grads, list(self.dense_m), list(self.dense_v)
+        if hi > lo:
+            params = [E0[lo:hi]] + params
+            grads = [g_t0[lo:hi]] + grads
+            ms = [self.emb_m[lo:hi]] + ms
+            vs = [self.emb_v[lo:hi]] + vs
+        ops.adam_apply(params, grads, ms, vs, self.hyper)
+        if hi > lo:
+            self.arena.push("e0", lo, hi - lo)
+        self.arena.signal_wait(3)
+        self.loss_sum.add_(self.loss)
+
+    def _cf_graphed_step(self):
+        ops.select_batch(self._resident.cf, self.step_dev, self.cf_ids.view(-1))
+        self.cf_step()
+
+    def _cf_runner(self):
+        if not self.use_graphs:
+            return self._cf_graphed_step
+        key = (self._graph_id, id(self._resident), self.model.training)
+        if self._cf_graph is None or key != self._cf_graph_key:
+            E0 = self.arena.table("e0")
+            live = [E0, self.emb_m, self.emb_v, self.step_dev, self.loss_sum] + [t for grp in self.layers for t in grp] + self.dense_m + self.dense_v
+            snap = [t.clone() for t in live]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._cf_graphed_step()  # warm-up step (lazy kernel attributes, allocator pools); undone below
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for dst, src in zip(live, snap):
+                dst.copy_(src)
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier()
+            self.arena.signal_wait(4)
+            g = torch.cuda.CUDAGraph()
+            before = _lib.LaunchCounter.count
+            with torch.cuda.graph(g):
+                self._cf_graphed_step()
+            self._cf_kernels = _lib.LaunchCounter.count - before
+            _lib.LaunchCounter.count = before
+            self._cf_graph, self._cf_graph_key = g, key
+
+        def replay(g=self._cf_graph, kernels=self._cf_kernels):
+            _lib.LaunchCounter.count += kernels
+            g.replay()
+
+        return replay
+
+    # ------------------------------------------------------------------------------------------
+    def bind_resident(self, data):
+        self._resident = self.single.bind_resident(data)
+        return self._resident
+
+    def run_epoch(self, n_cf=None, n_kg=None, refresh=True, epoch_seed: int = 0):
+        """One reference epoch body (main.py:290-361) on the batches bound with ``bind_resident``.
+        Returns (mean CF loss, mean KG loss)."""
+        m = self.model
+        m.train()
+        data = self._resident
+        g = m._graph()
+        if (id(g), g.vals.data_ptr()) != self._graph_id:
+            self._setup_graph()
+            self.scatter_from_model()
+        n_cf = data.cf.shape[0] if n_cf is None else n_cf
+        n_kg = data.kg.shape[0] if n_kg is None else n_kg
+        self.loss_sum.zero_()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        step = self._cf_runner() if n_cf else None
+        for _ in range(n_cf):
+            step()
+        cf_loss = float(self.loss_sum.item()) / max(n_cf, 1)
+        self.arena.check()
+        self.gather_to_model(n_cf)
+        ev[1].record()
+        kg_loss = 0.0
+        if n_kg:
+            kg_loss = self.single.run_epoch(None, n_cf=0, n_kg=n_kg, refresh=False)[1]
+        if self.world > 1:  # replicas of the replicated parameters: rank 0 wins (ulp-level drift from fp32 atomics) -- BEFORE the
+            for t in (m._relation_embedding.weight, m._trans_matrix, m._user_entity_embedding.weight):  # refresh, so every rank scores the same A
+                dist.broadcast(t.data, src=0)
+        ev[2].record()
+        if refresh:
+            torch.manual_seed(1_000_003 * (epoch_seed + 1) + 17)  # the refresh draws its dropout seed from torch's CPU generator: same on every rank
+            eh, er, et, ri = data.edges
+            m(eh, er, et, ri, mode=KGATMode.UPDATE_ATTENTION)
+            g = m._graph()
+            if (id(g), g.vals.data_ptr()) != self._graph_id:
+                self._setup_graph()
+        ev[3].record()
+        self._sync_adam_from_model()
+        self.scatter_from_model()
+        torch.cuda.synchronize()
+        self.last_phase_ms = {"cf": ev[0].elapsed_time(ev[1]), "kg": ev[1].elapsed_time(ev[2]), "refresh": ev[2].elapsed_time(ev[3]), "n_cf": n_cf, "n_kg": n_kg}
+        return cf_loss, kg_loss
+
+    def close(self):
+        self._cf_graph = None
+        self.single._graphs.clear()
+        torch.cuda.synchronize()
+        self.arena.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# bench entry for N > 1 (bench.py --gpus N under torchrun)
+# ----------------------------------------------------------------------------------------------
+def parity_check(g, data, dev, world, rank, n_steps: int = 3):
+    """Before timing: n_steps CF steps of the sharded engine against the single-GPU engine from the same seeded state, message
+    dropout off (deterministic).  Returns (max normwise relative error over the CF parameters, replicas identical?)."""
+    from .trainer import build_model
+
+    kw = dict(message_dropout=[0.0, 0.0, 0.0])
+
+    def fresh():
+        m = build_model(g, dev, seed=11, **kw)
+        eng = TrainEngine(m, use_graphs=False)
+        holder = eng.bind_resident(data.tensors())
+        m(*holder.edges, mode=KGATMode.UPDATE_ATTENTION)
+        return m, eng
+
+    ref, ref_eng = fresh()
+    ref_loss = ref_eng.run_epoch(n_cf=n_steps, n_kg=0, refresh=False)[0]
+    m, _ = fresh()
+    eng = RangeShardedEngine(m, world, rank, use_graphs=True)
+    eng.bind_resident(data.tensors())
+    loss = eng.run_epoch(n_cf=n_steps, n_kg=0, refresh=False)[0]
+    # mean loss of the steps and every CF parameter after them (Frobenius-relative: Adam turns an fp32 summation-order difference
+    # in an entry whose gradient is ~1e-8 into a visible change of that single entry, which a max-norm would report as a mismatch)
+    worst = abs(loss - ref_loss) / max(abs(ref_loss), 1e-30)
+    for (k, a), (_, b) in zip(m.named_parameters(), ref.named_parameters()):
+        if a.is_sparse or "_multi_head" in k or "_relation" in k or "_trans" in k:
+            continue
+        worst = max(worst, float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)))
+    chk = eng.replica_checksum
+    lo, hi = chk.clone(), chk.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    equal = bool(torch.equal(lo, hi))
+    t = torch.tensor([worst], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    eng.close()
+    del eng, m, ref, ref_eng
+    torch.cuda.empty_cache()
+    return float(t.item()), equal
+
+
+def c5_sharded_block(dev, world, rank):
+    """configs[4] scaled 5x down (2.2 M nodes, 40 M edges, d = 128, layers 128-64-32-16): one FULL (unpruned) propagation step
+    -- forward, BPR, backward, Adam -- with the rows sharded over the ranks (sharding.ShardedEngine: cyclic rows, one row exchange
+    per layer and direction over NVLink peer memory).  This is the regime the row sharding is for: the 1.1 GB table does not fit
+    the L2 and a layer is milliseconds of HBM traffic per rank, not tens of microseconds."""
+    from . import sharding, synthetic
+    from .model import KGAT, KGATArgs
+
+    n5, d5 = 2_200_000, 128
+    h5, _, t5 = synthetic.make_edges_only(n5, 40_000_000, 64)
+    deg5 = np.bincount(h5, minlength=n5).astype(np.float32)
+    att = torch.sparse_coo_tensor(torch.from_numpy(np.vstack([h5, t5]).astype(np.int64)), torch.from_numpy((1.0 / deg5[h5]).astype(np.float32)),
+                                  size=(n5, n5))
+    torch.manual_seed(7)
+    m = KGAT(KGATArgs(user_num=1_000_000, entity_num=n5 - 1_000_000, relation_num=64, cf_embedding_dim=d5, kg_embedding_dim=d5,
+                      attentive_matrix=att, layer_size=[128, 64, 32, 16], message_dropout=[0.1] * 4)).to(dev)
+    m.build_optimizer(1e-3, 1e-4)
+    m.cf_pruning = False
+    m.train()
+    part = sharding.CyclicPartition(n5, world, rank)
+    eng = sharding.ShardedEngine(m, part)
+    rng = np.random.default_rng(5)
+    ids = torch.from_numpy(part.to_padded(rng.integers(0, 1_000_000, size=(3, 256)))).to(dev)
+
+    def step():
+        eng.cf_step(ids[0], ids[1], ids[2])
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    a.record()
+    for _ in range(reps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b) / reps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    nnz = int(m._graph().nnz)
+    out = {"nodes": n5, "nnz": nnz, "dims": [128, 128, 64, 32, 16], "step_ms": float(ms.item()), "propagated_edges_per_s": nnz * 4 * 2 / (float(ms.item()) * 1e-3),
+           "what": "full 4-layer propagation forward + BPR + backward + Adam, rows sharded cyclically over the ranks, eager launches, max over ranks"}
+    if eng.exchange is not None:
+        eng.exchange.close()
+    del eng, m
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_main(args, metric, unit, workload, make_workload, config_dict, ClockSampler):
+    """``bench.py --gpus N`` under torchrun: strong scaling of the epoch on the fixed C3-shaped CKG."""
+    import json
+    import os
+    import sys
+    import time
+
+    from .trainer import build_model
+
+    t_start = time.perf_counter()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    # NCCL prints its version banner on stdout: keep stdout clean for the single JSON line
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    g, data = make_workload(workload)
+    # ---- parity first: the sharded step against the single-GPU engine (3 CF steps, dropout off); fail the run if it is off
+    par_err, replicas_equal = parity_check(g, data, dev, world, rank)
+    if par_err > 2e-5 or not replicas_equal:
+        if rank == 0:
+            os.write(json_fd, (json.dumps({"metric": metric, "n_gpus": world, "error": "sharded step does not match the single-GPU engine",
+                                           "parity_max_rel_err": par_err, "replicas_equal": replicas_equal}) + "\n").encode())
+        sys.stderr.flush()
+        os._exit(1)
+    model = build_model(g, dev)
+    holder_eng = TrainEngine(model, use_graphs=False)
+    holder = holder_eng.bind_resident(data.tensors())
+    model(*holder.edges, mode=KGATMode.UPDATE_ATTENTION)  # the first refresh swaps the attentive structure: before the sharded set-up
+    eng = RangeShardedEngine(model, world, rank)
+    eng.bind_resident(data.tensors())
+    for _ in range(2):  # set-up (never timed): capture the step graphs on two 2-step mini-epochs
+        eng.run_epoch(n_cf=2, n_kg=2)
+    for i in range(max(args.warmup, 0)):
+        eng.run_epoch(epoch_seed=i)
+    torch.cuda.synchronize()
+    dist.barrier()
+    _lib.LaunchCounter.count = 0
+    with ClockSampler(dev.index or 0) as clocks:
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        losses = None
+        for i in range(args.steps):
+            losses = eng.run_epoch(epoch_seed=100 + i)
+        t1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+    ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    epoch_s = float(ms.item()) / 1e3 / max(args.steps, 1)
+    launches = _lib.LaunchCounter.count
+    phases = dict(eng.last_phase_ms)
+    # ---- exchange cost: the step's three row pushes + handshakes alone, back to back (what the N-GPU step pays on top of compute)
+    lo, hi = eng.lo, eng.hi
+
+    def exchange_only():
+        for ch, name in ((0, "e1"), (1, "gs0"), (3, "e0")):
+            if hi > lo:
+                eng.arena.push(name, lo, hi - lo)
+            eng.arena.signal_wait(ch)
+
+    for _ in range(3):
+        exchange_only()
+    torch.cuda.synchronize()
+    dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
+        exchange_only()
+    b.record()
+    torch.cuda.synchronize()
+    ex = torch.tensor([a.elapsed_time(b) / 20 * 1e3], device=dev)
+    dist.all_reduce(ex, op=dist.ReduceOp.MAX)
+    out_bytes = sum(eng.dims[i] for i in (1, 0, 0)) * 4 * (hi - lo) * (world - 1)
+    # ---- end to end at N GPUs: every bench step (= epoch) first copies its inputs -- the pre-sampled batch blocks and the refresh
+    #      edge list -- from pinned host memory to the device, and the epoch's losses are read back
+    e2e = None
+    try:
+        host = data.tensors(pin=True)
+        res = eng._resident
+        pairs = [(res.cf, host.cf_block), (res.kg, host.kg_block)] + list(zip(res.edges, host.edges))
+        h2d = sum(src.numel() * src.element_size() for _, src in pairs)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            for dst, src in pairs:
+                dst.copy_(src, non_blocking=True)
+            eng.run_epoch(epoch_seed=200 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        e2e = {"value": float(ms2.item()) / 1e3 / max(args.steps, 1), "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+               "api": "RangeShardedEngine.run_epoch after copying the epoch's pre-sampled batch blocks and edge list from pinned host memory "
+                      "(every rank); the two mean losses are read back per epoch.  The per-step public-API figure is the N = 1 line's e2e."}
+    except Exception as e:  # noqa: BLE001 - never lose the bench line over the secondary measurement
+        e2e = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    c5 = None
+    budget = getattr(args, "budget_s", 330.0)
+    if not getattr(args, "no_extra", False) and time.perf_counter() - t_start < budget - 120:
+        try:
+            eng.close()
+            eng = None
+            c5 = c5_sharded_block(dev, world, rank)
+        except Exception as e:  # noqa: BLE001
+            c5 = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    if rank == 0:
+        graph = model._graph()
+        line = {
+            "metric": metric, "value": epoch_s, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": epoch_s * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(g, data, world),
+            "propagation_edges_per_s": graph.nnz * 3 * 2 * data.n_cf / epoch_s,
+            "cf_loss": losses[0], "kg_loss": losses[1], "gpu_launches": launches, "clocks": clocks.summary(),
+            "phases": {"cf_phase_s": phases["cf"] / 1e3, "kg_phase_s": phases["kg"] / 1e3, "refresh_s": phases["refresh"] / 1e3,
+                       "cf_step_us": 1e3 * phases["cf"] / max(phases["n_cf"], 1), "kg_step_us": 1e3 * phases["kg"] / max(phases["n_kg"], 1)},
+            "parity_max_rel_err": par_err, "replicas_equal": replicas_equal,
+            "parity": "3 CF steps (dropout off) of the sharded engine vs the single-GPU engine from the same seeded state, every CF parameter, max over ranks",
+            "exchange": {"kind": "NVLink peer memory (store kernel + flag handshake)", "us_per_step": float(ex.item()), "row_exchanges_per_step": 3,
+                         "outbound_bytes_per_rank_and_step": out_bytes,
+                         "achieved_gbs_per_rank": out_bytes / (float(ex.item()) * 1e-6) / 1e9 if float(ex.item()) > 0 else None,
+                         "nvlink_peak_gbs": 770.0, "what": "the step's three row pushes (E1, g_S, E0 slices to every peer) + handshakes alone, back to back, max over ranks"},
+            "row_ranges": eng.bounds if eng is not None else None,
+            "e2e": e2e, "roofline": None, "cpu_baseline": None, "c5_scaled": c5,
+            "note": "first propagation layer + Adam row-sharded over contiguous cost-balanced node ranges, upper (pruned) layers replicated, 3 row "
+                    "exchanges + 1 gradient all-reduce per step over NVLink peer memory, the whole step one CUDA graph per rank; KG phase and "
+                    "refresh replicated; timed on the device, max over ranks.  roofline / cpu_baseline: see the N = 1 line (same kernels).",
+        }
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    torch.cuda.synchronize()
+    dist.barrier()
+    if eng is not None:
+        eng.close()
+    sys.stderr.flush()
+    os._exit(0)
