@@ -416,6 +416,11 @@ int kgat_peer_close(void* ptr);
  * array of n_peers device pointers into the peers' mapped allocations.  max_ctas > 0 bounds the grid (a push that
  * runs beside compute kernels on another stream needs few SMs to fill the links); 0 = 8 CTAs per SM. */
 int kgat_peer_push(const float* src, float* const* peer_dst, int32_t n_peers, int64_t n_floats, int32_t max_ctas, void* stream);
+/* The *count_dev rows listed in `rows` (node ids) of `table` (row stride ld floats) -> the same rows of every peer's table
+ * (DEVICE array of n_peers base pointers).  The row-list form of kgat_peer_push: a pruned step exchanges only the rows of
+ * "level 1 AND my range", not the whole slab. */
+int kgat_peer_push_rows(const float* table, float* const* peer_tables, int32_t n_peers, const int32_t* rows,
+                        const int32_t* count_dev, int64_t max_rows, int32_t d, int64_t ld, void* stream);
 /* The same transfer on a copy engine (cudaMemcpyAsync into a peer mapping): no SM is involved, so it can run on a
  * side stream beside compute kernels without slowing them down.  One destination per call. */
 int kgat_peer_copy(void* dst, const void* src, int64_t bytes, void* stream);

@@ -39,6 +39,19 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const float4* __restrict
     }
 }
 
+// the listed rows (node ids, device-side count) of a table -> the same rows of every peer's table; d / 4 lanes per row
+__global__ void __launch_bounds__(256) peer_push_rows_kernel(const float* __restrict__ table, float* const* __restrict__ peer_tables, int n_peers,
+                                                             const int32_t* __restrict__ rows, const int32_t* __restrict__ cnt_dev, int d4,
+                                                             int64_t ld) {
+    const int64_t total = (int64_t)cnt_dev[0] * d4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t off = (int64_t)__ldg(rows + i / d4) * ld + (i % d4) * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(table + off));
+        for (int q = 0; q < n_peers; ++q) *reinterpret_cast<float4*>(peer_tables[q] + off) = v;
+    }
+}
+
 // thread q: seq = ++my sequence number (thread 0 publishes it), raise it at peer q, wait for peer q's
 __global__ void peer_signal_wait_kernel(int32_t* const* __restrict__ peer_flags /* my slot in peer q's pad */,
                                         const int32_t* __restrict__ my_flags /* slot q of my pad: written by peer q */, int n_peers,
@@ -119,6 +132,18 @@ int kgat_peer_close(void* ptr) {
 
 int kgat_peer_push(const float* src, float* const* peer_dst, int32_t n_peers, int64_t n_floats, int32_t max_ctas, void* stream) {
     return peer_push_launch(src, peer_dst, n_peers, n_floats, (cudaStream_t)stream, max_ctas);
+}
+
+int kgat_peer_push_rows(const float* table, float* const* peer_tables, int32_t n_peers, const int32_t* rows, const int32_t* count_dev,
+                        int64_t max_rows, int32_t d, int64_t ld, void* stream) {
+    if (!table || !rows || !count_dev || n_peers < 0 || max_rows < 0 || d <= 0 || (d & 3) || (ld & 3) || (n_peers && !peer_tables))
+        return KGAT_ERR_INVALID_ARGUMENT;
+    if (n_peers == 0 || max_rows == 0) return KGAT_OK;
+    const int64_t want = (max_rows * (d / 4) + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    peer_push_rows_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(table, peer_tables, n_peers, rows, count_dev,
+                                                                                                 d / 4, ld);
+    return check_launch();
 }
 
 int kgat_peer_copy(void* dst, const void* src, int64_t bytes, void* stream) {

@@ -93,6 +93,14 @@ class PeerArena:
         check(self.lib.kgat_peer_push(src.data_ptr(), self.peer_ptrs(name, row_offset).data_ptr(), len(self.peers), src.numel(),
                                       int(max_ctas), torch.cuda.current_stream().cuda_stream), "peer_push")
 
+    def push_rows(self, name: str, rows: torch.Tensor, count_dev: torch.Tensor, max_rows: int) -> None:
+        """Copy the listed rows (int32 node ids, device-side count) of my table to the same rows of every peer's table."""
+        if not self.peers:
+            return
+        t = self._views[name]
+        check(self.lib.kgat_peer_push_rows(t.data_ptr(), self.peer_ptrs(name, 0).data_ptr(), len(self.peers), rows.data_ptr(), count_dev.data_ptr(),
+                                           int(max_rows), t.shape[1], t.stride(0), torch.cuda.current_stream().cuda_stream), "peer_push_rows")
+
     def copy(self, name: str, row_offset: int, n_rows: int) -> None:
         """Same transfer as ``push`` on the copy engines (one cudaMemcpyAsync per peer): no SM involved."""
         d = self._shape[name][1]

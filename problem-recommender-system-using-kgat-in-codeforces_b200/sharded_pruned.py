@@ -70,6 +70,9 @@ class _LocalArena:
     def push(self, *a, **k):
         pass
 
+    def push_rows(self, *a, **k):
+        pass
+
     def signal_wait(self, channel):
         pass
 
@@ -107,6 +110,7 @@ class RangeShardedEngine:
         self._cf_graph_key = None
         self._cf_kernels = 0
         self._resident = None
+        self.side = torch.cuda.Stream(device=self.dev) if world > 1 else None
         self._setup_graph()
         self._sync_adam_from_model()
         self.scatter_from_model()
@@ -196,8 +200,17 @@ class RangeShardedEngine:
         n, dev = self.n, self.dev
         lo, hi = self.lo, self.hi
         E0, E1, GS0 = self.arena.table("e0"), self.arena.table("e1"), self.arena.table("gs0")
+        # my embedding rows as the previous step's Adam left them go to the peers on a side stream while the frontier of this
+        # step's batch is built (it does not read the table)
+        cur = torch.cuda.current_stream()
+        if self.world > 1:
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                self._exchange_e0()
         f.build([self.cf_ids.view(-1)])
         ops.frontier_segment(f.rows(1), f.count(1), f.mask(1), n, lo, hi, self.own_rows, self.own_cnt, self.own_mask)
+        if self.world > 1:
+            cur.wait_stream(self.side)
         own = {"rows": self.own_rows, "n_rows_dev": self.own_cnt}
         # ---- first layer, my rows of level 1
         w1, b1, w2, b2 = self.layers[0]
@@ -206,7 +219,7 @@ class RangeShardedEngine:
         ops.biagg_forward(E0, S0, w1, b1, w2, b2, E1, inv1, flags1, dropout_p=ps[0], seed=seed, offset=1 << 40, seed_dev=self.step_dev,
                           max_rows=max(hi - lo, 1), tag="_L1", **own)
         if hi > lo:
-            self.arena.push("e1", lo, hi - lo)
+            self.arena.push_rows("e1", self.own_rows, self.own_cnt, hi - lo)  # only the rows of level 1 were computed
         self.arena.signal_wait(0)
         # ---- upper layers: replicated
         tables, sides, invs, flagss = [E0, E1], [S0], [inv1], [flags1]
@@ -266,7 +279,7 @@ class RangeShardedEngine:
         ops.biagg_reduce_param_grads(partials, n_ctas, d_in, d_out, *gw)
         pgrads[0] = gw
         if hi > lo:
-            self.arena.push("gs0", lo, hi - lo)
+            self.arena.push_rows("gs0", self.own_rows, self.own_cnt, hi - lo)
         self.arena.signal_wait(1)
         g_t0 = g.matmul_t(GS0, out=_buf(n, d_in, device=dev), addend=g_e0, row_mask=self.range_mask, rows=self.range_rows,
                           n_rows_dev=self.range_cnt, edge_mask=f.mask(1), tag="_L1")
@@ -289,11 +302,13 @@ class RangeShardedEngine:
             grads = [g_t0[lo:hi]] + grads
             ms = [self.emb_m[lo:hi]] + ms
             vs = [self.emb_v[lo:hi]] + vs
-        ops.adam_apply(params, grads, ms, vs, self.hyper)
-        if hi > lo:
-            self.arena.push("e0", lo, hi - lo)
-        self.arena.signal_wait(3)
+        ops.adam_apply(params, grads, ms, vs, self.hyper)  # (my updated rows travel at the start of the next step / in finish_exchange)
         self.loss_sum.add_(self.loss)
+
+    def _exchange_e0(self):
+        if self.hi > self.lo:
+            self.arena.push("e0", self.lo, self.hi - self.lo)
+        self.arena.signal_wait(3)
 
     def _cf_graphed_step(self):
         ops.select_batch(self._resident.cf, self.step_dev, self.cf_ids.view(-1))
@@ -356,6 +371,7 @@ class RangeShardedEngine:
         step = self._cf_runner() if n_cf else None
         for _ in range(n_cf):
             step()
+        self._exchange_e0()  # the last step's rows
         cf_loss = float(self.loss_sum.item()) / max(n_cf, 1)
         self.arena.check()
         self.gather_to_model(n_cf)
@@ -540,11 +556,12 @@ def bench_main(args, metric, unit, workload, make_workload, config_dict, ClockSa
     # ---- exchange cost: the step's three row pushes + handshakes alone, back to back (what the N-GPU step pays on top of compute)
     lo, hi = eng.lo, eng.hi
 
-    def exchange_only():
-        for ch, name in ((0, "e1"), (1, "gs0"), (3, "e0")):
+    def exchange_only():  # the last step's level-1 rows of my range (E1, g_S) and my whole slice of the embedding table
+        for ch, name in ((0, "e1"), (1, "gs0")):
             if hi > lo:
-                eng.arena.push(name, lo, hi - lo)
+                eng.arena.push_rows(name, eng.own_rows, eng.own_cnt, hi - lo)
             eng.arena.signal_wait(ch)
+        eng._exchange_e0()
 
     for _ in range(3):
         exchange_only()
@@ -558,7 +575,8 @@ def bench_main(args, metric, unit, workload, make_workload, config_dict, ClockSa
     torch.cuda.synchronize()
     ex = torch.tensor([a.elapsed_time(b) / 20 * 1e3], device=dev)
     dist.all_reduce(ex, op=dist.ReduceOp.MAX)
-    out_bytes = sum(eng.dims[i] for i in (1, 0, 0)) * 4 * (hi - lo) * (world - 1)
+    own_l1 = int(eng.own_cnt.item())
+    out_bytes = ((eng.dims[1] + eng.dims[0]) * own_l1 + eng.dims[0] * (hi - lo)) * 4 * (world - 1)
     # ---- end to end at N GPUs: every bench step (= epoch) first copies its inputs -- the pre-sampled batch blocks and the refresh
     #      edge list -- from pinned host memory to the device, and the epoch's losses are read back
     e2e = None
