@@ -442,8 +442,14 @@ def c5_scaled_block(dev, peak):
                          "model": "B_gather (SURVEY.md 8d): the table is 9x the L2, one 512 B neighbour row per edge is compulsory HBM traffic; "
                                   "Zipf hubs still hit the L2, so the figure can exceed the copy peak"},
            "what": "full (unpruned) 4-layer propagation forward + backward with message dropout, one GPU; the sharded run is in the N > 1 lines"}
-    del g5, e0, layers
+    del g5, e0, layers, x5, y5
     torch.cuda.empty_cache()
+    try:  # the same full training step the N > 1 lines report (sharding.ShardedEngine), here with one rank: the N-GPU c5_scaled.step_ms compare to it
+        from kgat_b200.sharded_pruned import c5_sharded_block
+
+        out["sharded_step_world1"] = c5_sharded_block(dev, 1, 0)
+    except Exception as e:  # noqa: BLE001
+        out["sharded_step_world1"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     return out
 
 
