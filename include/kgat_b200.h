@@ -295,6 +295,16 @@ typedef struct {
 int kgat_mha_forward(const float* tail_embedding, int64_t n, int32_t d, const kgat_mha_t* mha, float dropout_p,
                      const uint8_t* head_bits, uint64_t seed, uint64_t offset, float* out, void* stream);
 
+/* Canonical KGAT score (north_star (1); the paper's pi(h, r, t) = (W_r e_t)^T tanh(W_r e_h + e_r), row-vector convention
+ * x = e W_r of model.py:291-298) -- an OPTION (model.score_mode = "kgat"); the reference itself scores edges with the value path
+ * of its multi-head attention (below).  x_out[p] = emb[pair_node[p]] W[pair_rel[p]] for unique (node, relation) pairs, then
+ * score[e] = sum_j x_tail[tail_pair[e]][j] * tanh(x_head[head_pair[e]][j] + rel_emb[edge_rel[e]][j]). */
+int kgat_att_pair_project(const float* emb, const float* W, int32_t d, const int32_t* pair_node, const int32_t* pair_rel,
+                          int64_t n_pairs, float* x_out, void* stream);
+int kgat_att_edge_scores_kgat(const float* x_head, const int32_t* head_pair, const float* x_tail, const int32_t* tail_pair,
+                              const float* rel_emb, const int32_t* edge_rel, int64_t n_edges, int32_t d, float* score_out,
+                              void* stream);
+
 /* Per unique (tail, relation) pair: x = e_t W_r, v = Wv x + bv.  If v_out != NULL stores v (n_pairs x d).
  * If score_out != NULL also o = Wo v + bo, LayerNorm, score = sum tanh  (the eval-mode edge score
  * before the degree weight: the reference's query/key path cancels). d = k = 64. */

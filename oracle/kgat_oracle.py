@@ -446,3 +446,31 @@ def sample_kg_batch(rng, kg_dict, node_num: int, batch_size: int):
         np.asarray(pos_b, np.int64),
         np.asarray(neg_b, np.int64),
     )
+
+
+# ----------------------------------------------------------------------------------------------
+# canonical KGAT attention (north_star item (1)); NOT what the reference computes -- the oracle of model.score_mode = "kgat"
+# ----------------------------------------------------------------------------------------------
+
+
+def attention_refresh_kgat(params, heads, rels, tails, relation_indices, node_num: int):
+    """The KGAT paper's pi(h, r, t) = (W_r e_t)^T tanh(W_r e_h + e_r) (arXiv 1905.07854, eq. 4) in the reference's row-vector
+    convention x = e W_r (src/model/KGAT/model.py:291-298), then exactly the reference's assembly (model.py:355-366): per-relation
+    batches concatenated into a COO, duplicates (h, t) summed by the coalesce inside ``torch.sparse.softmax``, row softmax.
+    No degree weights, no multi-head attention.  Plain PyTorch; pinned by construction (it IS the formula), used to check the kernel."""
+    heads = torch.as_tensor(heads).long()
+    tails = torch.as_tensor(tails).long()
+    rels = torch.as_tensor(rels).long()
+    emb, rel_emb, w = params["_user_entity_embedding.weight"], params["_relation_embedding.weight"], params["_trans_matrix"]
+    rows, cols, vals = [], [], []
+    for r in torch.as_tensor(relation_indices).long().tolist():
+        sel = torch.where(rels == r)[0]
+        h, t = heads[sel], tails[sel]
+        x_h = torch.matmul(emb[h], w[r])
+        x_t = torch.matmul(emb[t], w[r])
+        rows.append(h)
+        cols.append(t)
+        vals.append(torch.sum(x_t * torch.tanh(x_h + rel_emb[r]), dim=1))
+    m = torch.sparse_coo_tensor(torch.stack([torch.cat(rows), torch.cat(cols)]), torch.cat(vals), size=(node_num, node_num))
+    m = torch.sparse.softmax(m, dim=1)
+    return m.indices()[0].clone(), m.indices()[1].clone(), m.values().clone()

@@ -322,6 +322,60 @@ def golden_model(tag: str, shape: str, dup: int, cf_b: int, kg_b: int, n_pred_us
     print(f"model_{tag}: N={n} nnz={g.nnz} att_nnz={g.att_rows.size} R={g.relation_num} file={size / 1e6:.2f} MB losses={losses}")
 
 
+# ----------------------------------------------------------------------------------------------
+# 3. end-to-end training tier: the unmodified reference trained for a few epochs in train() mode
+#    (message dropout and attention dropout live), several seeds -> the band the drop-in's metrics must fall into
+# ----------------------------------------------------------------------------------------------
+
+
+def golden_training(tag: str = "train_small", shape: str = "small", epochs: int = 3, seeds=(0, 1, 2, 3, 4, 5, 6, 7)):
+    trainer = importlib.import_module("problem-recommender-system-using-kgat-in-codeforces_b200.trainer")
+    g = pkg.make_ckg(shape, seed=SEED)
+    users = np.array(sorted(u for u, v in g.test_dict.items() if len(v) > 0), np.int64)
+    items = np.arange(g.item_num)
+    recs, ndcgs, cf_losses, kg_losses = [], [], [], []
+    for seed in seeds:
+        torch.manual_seed(1000 + seed)  # parameter init + every dropout draw of the run
+        model = KGAT(KGATArgs(user_num=g.user_num, entity_num=g.entity_num, relation_num=g.relation_num, attentive_matrix=coo_from_graph(g)))
+        model.build_optimizer(cf_lr=1e-3, kg_lr=1e-4)
+        heads = torch.tensor(list(g.heads))  # int32, like main.py:351-353
+        rels = torch.tensor(g.relations.tolist())
+        tails = torch.tensor(list(g.tails))
+        rel_idx = torch.tensor(g.adjacency_relations)
+        cf_l, kg_l = [], []
+        for ep in range(epochs):
+            data = trainer.EpochData.sample(g, seed=7000 + 100 * seed + ep)  # the batches the drop-in test regenerates
+            model.train()
+            tot = 0.0
+            for i in range(data.n_cf):
+                b = [torch.from_numpy(a[i]) for a in data.cf]
+                loss = model(*b, mode=KGATMode.TRAIN_CF)
+                loss.backward()
+                model.update_cf_weights()
+                tot += loss.item()
+            cf_l.append(tot / data.n_cf)
+            tot = 0.0
+            for i in range(data.n_kg):
+                b = [torch.from_numpy(a[i]) for a in data.kg]
+                loss = model(*b, mode=KGATMode.TRAIN_KG)
+                loss.backward()
+                model.update_kg_weights()
+                tot += loss.item()
+            kg_l.append(tot / data.n_kg)
+            model(heads, rels, tails, rel_idx, mode=KGATMode.UPDATE_ATTENTION)  # still in train(): attention dropout live (Q2)
+        model.eval()
+        with torch.no_grad():
+            scores = model(torch.from_numpy(users), torch.from_numpy(items), mode=KGATMode.PREDICT)
+        md = metrics_at_k(scores.clone(), g.train_dict, g.test_dict, users, items, [20])
+        recs.append(float(np.nanmean(md[20][Metrics.RECALL])))
+        ndcgs.append(float(np.nanmean(md[20][Metrics.NDCG])))
+        cf_losses.append(cf_l)
+        kg_losses.append(kg_l)
+        print(f"train[{tag}] seed {seed}: recall@20 {recs[-1]:.4f} ndcg@20 {ndcgs[-1]:.4f} cf {cf_l} kg {kg_l}")
+    np.savez_compressed(OUT / f"{tag}.npz", shape=np.array(shape), epochs=np.array(epochs), seeds=np.array(seeds), recall20=np.array(recs),
+                        ndcg20=np.array(ndcgs), cf_loss=np.array(cf_losses), kg_loss=np.array(kg_losses))
+
+
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(4)
@@ -329,3 +383,4 @@ if __name__ == "__main__":
     golden_model("tiny", "tiny", dup=0, cf_b=16, kg_b=32, n_pred_users=8)
     golden_model("tiny_dup", "tiny", dup=40, cf_b=16, kg_b=32, n_pred_users=8)
     golden_model("small", "small", dup=0, cf_b=64, kg_b=128, n_pred_users=16)
+    golden_training()

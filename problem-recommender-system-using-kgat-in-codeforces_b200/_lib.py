@@ -106,6 +106,8 @@ SIGNATURES: dict[str, tuple] = {
     "kgat_transr_claim_rows": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P]),
     "kgat_transr_step": (_I32, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _I32, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     "kgat_mha_forward": (_I32, [_P, _I64, _I32, C.POINTER(MhaT), _F, _P, _U64, _U64, _P, _P]),
+    "kgat_att_pair_project": (_I32, [_P, _P, _I32, _P, _P, _I64, _P, _P]),
+    "kgat_att_edge_scores_kgat": (_I32, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P]),
     "kgat_att_pair_scores": (_I32, [_P, _P, _I32, _P, _P, _I64, C.POINTER(MhaT), _P, _P, _P]),
     "kgat_att_edge_scores_dropout": (_I32, [_P, _P, _I64, _I32, C.POINTER(MhaT), _F, _P, _U64, _U64, _P, _P, _P]),
     "kgat_att_row_softmax": (_I32, [_P, _I64, _P, _P, _P, _P, _P, _P, _P]),
@@ -147,7 +149,7 @@ KERNELS_PER_CALL = {
     "kgat_ids64_to_i32": 1, "kgat_spmm_csr": 1, "kgat_spmm_csr_masked": 1, "kgat_spmm_csr_rows": 1, "kgat_spmm_scatter_rows": 1, "kgat_frontier_mark_ids": 1, "kgat_frontier_expand": 1,
     "kgat_frontier_list": 2, "kgat_frontier_zero_rows": 1, "kgat_frontier_segment": 1, "kgat_biagg_forward_rows": 1, "kgat_biagg_backward_rows": 1, "kgat_biagg_forward": 1, "kgat_biagg_backward": 1,
     "kgat_biagg_reduce_param_grads": 1, "kgat_bpr_forward": 2, "kgat_bpr_backward": 1, "kgat_transr_forward": 2,
-    "kgat_transr_backward": 1, "kgat_att_pair_scores": 1, "kgat_mha_forward": 1, "kgat_att_edge_scores_dropout": 1, "kgat_att_row_softmax": 1,
+    "kgat_transr_backward": 1, "kgat_att_pair_scores": 1, "kgat_mha_forward": 1, "kgat_att_pair_project": 1, "kgat_att_edge_scores_kgat": 1, "kgat_att_edge_scores_dropout": 1, "kgat_att_row_softmax": 1,
     "kgat_att_edge_weights": 1, "kgat_gather_concat": 1, "kgat_sgemm_nt": 1, "kgat_mask_scores": 1, "kgat_topk_rows": 1,
     "kgat_adam_advance": 1, "kgat_adam_set_hyper": 1, "kgat_adam_apply": 1, "kgat_adam_hyper_table": 1, "kgat_adam_lazy_catchup": 1, "kgat_adam_sparse_rows": 1,
     "kgat_adam_lazy_flush": 1, "kgat_fill_f32": 1, "kgat_select_batch_i64": 1, "kgat_sample_cf_batch": 1, "kgat_sample_kg_batch": 1,

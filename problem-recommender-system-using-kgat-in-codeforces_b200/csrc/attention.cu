@@ -229,6 +229,58 @@ __global__ void __launch_bounds__(128) mha_forward_kernel(const float* __restric
     }
 }
 
+// Canonical KGAT attention score (north_star item (1), the paper's pi(h, r, t) = (W_r e_t)^T tanh(W_r e_h + e_r), in the
+// reference's row-vector convention x = e W_r, model.py:291-298) -- NOT what the reference computes; offered as
+// model.score_mode = "kgat".  Step 1: x = e W_r once per unique (node, relation) pair; step 2: one warp per edge gathers its
+// two projections and e_r.
+template <int DM>
+__global__ void __launch_bounds__(128) pair_project_kernel(const float* __restrict__ emb, const float* __restrict__ W,
+                                                           const int32_t* __restrict__ pair_node, const int32_t* __restrict__ pair_rel,
+                                                           int64_t n_pairs, float* __restrict__ x_out) {
+    constexpr int D = DM * 32;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t pr = warp0; pr < n_pairs; pr += nwarps) {
+        const int64_t t = pair_node[pr], r = pair_rel[pr];
+        float e[DM], x[DM];
+#pragma unroll
+        for (int m = 0; m < DM; ++m) {
+            e[m] = __ldg(emb + t * D + lane + 32 * m);
+            x[m] = 0.f;
+        }
+        const float* Wr = W + r * (int64_t)D * D;
+#pragma unroll
+        for (int jm = 0; jm < DM; ++jm) {
+#pragma unroll 8
+            for (int jj = 0; jj < 32; ++jj) {
+                const float a = __shfl_sync(kFull, e[jm], jj);
+                const float* wrow = Wr + (jm * 32 + jj) * D + lane;
+#pragma unroll
+                for (int m = 0; m < DM; ++m) x[m] = fmaf(a, __ldg(wrow + 32 * m), x[m]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < DM; ++m) x_out[pr * D + lane + 32 * m] = x[m];
+    }
+}
+
+__global__ void __launch_bounds__(128) edge_scores_kgat_kernel(const float* __restrict__ x_head, const int32_t* __restrict__ head_pair,
+                                                               const float* __restrict__ x_tail, const int32_t* __restrict__ tail_pair,
+                                                               const float* __restrict__ rel_emb, const int32_t* __restrict__ edge_rel,
+                                                               int64_t n_edges, int d, float* __restrict__ score_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t e = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (e >= n_edges) return;
+    const float* xh = x_head + (int64_t)head_pair[e] * d;
+    const float* xt = x_tail + (int64_t)tail_pair[e] * d;
+    const float* er = rel_emb + (int64_t)edge_rel[e] * d;
+    float s = 0.f;
+    for (int j = lane; j < d; j += 32) s = fmaf(__ldg(xt + j), tanhf(__ldg(xh + j) + __ldg(er + j)), s);
+    s = warp_sum(s);
+    if (lane == 0) score_out[e] = s;
+}
+
 __global__ void __launch_bounds__(128) row_softmax_kernel(const int32_t* __restrict__ row_ptr, int64_t n_rows,
                                                           const int32_t* __restrict__ slot_ptr, const float* __restrict__ pair_score,
                                                           const int32_t* __restrict__ pair_of_edge,
@@ -349,6 +401,31 @@ int kgat_mha_forward(const float* tail_embedding, int64_t n, int32_t d, const kg
         case 128: return launch_mha<4>(tail_embedding, n, P, dropout_p, head_bits, seed, offset, out, (cudaStream_t)stream);
         default: return KGAT_ERR_UNSUPPORTED;
     }
+}
+
+int kgat_att_pair_project(const float* emb, const float* W, int32_t d, const int32_t* pair_node, const int32_t* pair_rel, int64_t n_pairs,
+                          float* x_out, void* stream) {
+    if (!emb || !W || !pair_node || !pair_rel || !x_out || n_pairs < 0) return KGAT_ERR_INVALID_ARGUMENT;
+    if (n_pairs == 0) return KGAT_OK;
+    int64_t blocks = (n_pairs + 3) / 4;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    switch (d) {
+        case 32: pair_project_kernel<1><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(emb, W, pair_node, pair_rel, n_pairs, x_out); break;
+        case 64: pair_project_kernel<2><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(emb, W, pair_node, pair_rel, n_pairs, x_out); break;
+        case 128: pair_project_kernel<4><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(emb, W, pair_node, pair_rel, n_pairs, x_out); break;
+        default: return KGAT_ERR_UNSUPPORTED;
+    }
+    return check_launch();
+}
+
+int kgat_att_edge_scores_kgat(const float* x_head, const int32_t* head_pair, const float* x_tail, const int32_t* tail_pair, const float* rel_emb,
+                              const int32_t* edge_rel, int64_t n_edges, int32_t d, float* score_out, void* stream) {
+    if (!x_head || !head_pair || !x_tail || !tail_pair || !rel_emb || !edge_rel || !score_out || n_edges < 0 || d <= 0) return KGAT_ERR_INVALID_ARGUMENT;
+    if (n_edges == 0) return KGAT_OK;
+    const unsigned blocks = (unsigned)((n_edges * 32 + 127) / 128);
+    edge_scores_kgat_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(x_head, head_pair, x_tail, tail_pair, rel_emb, edge_rel, n_edges, d, score_out);
+    return check_launch();
 }
 
 int kgat_att_pair_scores(const float* emb, const float* W, int32_t d, const int32_t* pair_tail, const int32_t* pair_rel, int64_t n_pairs,

@@ -42,7 +42,8 @@ class _AdamSlot:
             steps.add(int(st["step"]))
         if len(steps) != 1:
             raise RuntimeError("TrainEngine needs all parameters of a phase to share one Adam step count")
-        self.step_dev = torch.full((1,), steps.pop(), dtype=torch.int64, device=dev)
+        self._host_step = steps.pop()
+        self.step_dev = torch.full((1,), self._host_step, dtype=torch.int64, device=dev)
         self.hyper = torch.empty(8, dtype=f32, device=dev)
         self.exp_avg = [opt.state[p]["exp_avg"] for p in self.params]
         self.exp_avg_sq = [opt.state[p]["exp_avg_sq"] for p in self.params]
@@ -51,7 +52,25 @@ class _AdamSlot:
         ops.adam_advance(self.step_dev, self.lr, self.b1, self.b2, self.eps, self.hyper)
         ops.adam_apply([p.data for p in self.params], grads, self.exp_avg, self.exp_avg_sq, self.hyper, row_slot0=row_slot0)
 
+    def resync(self) -> bool:
+        """Pick up what happened to the optimiser between engine epochs (API steps advance the host-side step count; load_state_dict
+        replaces the moment tensors).  Returns True when captured graphs that bake the moment pointers in must be dropped."""
+        steps = {int(self.opt.state[p]["step"]) for p in self.params}
+        if len(steps) != 1:
+            raise RuntimeError("TrainEngine needs all parameters of a phase to share one Adam step count")
+        step = steps.pop()
+        if step != self._host_step:
+            self.step_dev.fill_(step)
+            self._host_step = step
+        moved = any(self.opt.state[p]["exp_avg"].data_ptr() != m.data_ptr() or self.opt.state[p]["exp_avg_sq"].data_ptr() != v.data_ptr()
+                    for p, m, v in zip(self.params, self.exp_avg, self.exp_avg_sq))
+        if moved:
+            self.exp_avg = [self.opt.state[p]["exp_avg"] for p in self.params]
+            self.exp_avg_sq = [self.opt.state[p]["exp_avg_sq"] for p in self.params]
+        return moved
+
     def sync_host(self, n_steps: int):
+        self._host_step += n_steps
         for p in self.params:
             self.opt.state[p]["step"] += n_steps
             torch.autograd.graph.increment_version(p)
@@ -271,6 +290,8 @@ class TrainEngine:
         n_cf = int(src.cf.shape[0] if resident else src.n_cf) if n_cf is None else n_cf
         n_kg = int(src.kg.shape[0] if resident else src.n_kg) if n_kg is None else n_kg
         h2d = d2h = 0
+        if self.cf_adam.resync() | self.kg_adam.resync():  # steps taken / state replaced through the model API since the last epoch
+            self._graphs.clear()
         self.cf_loss_sum.zero_()
         self.kg_loss_sum.zero_()
         cf_host = kg_host = 0.0

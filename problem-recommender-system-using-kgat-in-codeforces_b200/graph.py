@@ -207,7 +207,7 @@ class EdgeIndex:
         row_ptr, col_idx = ops.decode_sorted_keys(uniq, n, n)
         # per-relation degrees (bincount inside the relation batch, model.py:310-311)
         rbits = max(1, (n_rel_ids * n - 1).bit_length())
-        _, g_h, p_h, _ = ops.group_by_key((rels * n + heads).contiguous(), key_bits=rbits)
+        _, g_h, p_h, uniq_rh = ops.group_by_key((rels * n + heads).contiguous(), key_bits=rbits)
         deg_h = (p_h[1:] - p_h[:-1])[g_h.long()].to(torch.int32)
         _, g_t, p_t, uniq_rt = ops.group_by_key((rels * n + tails).contiguous(), key_bits=rbits)
         deg_t = (p_t[1:] - p_t[:-1])[g_t.long()].to(torch.int32)
@@ -219,6 +219,12 @@ class EdgeIndex:
         self.pair_tail = (uniq_rt % n).to(torch.int32).contiguous()
         self.pair_of_edge = g_t[o].contiguous()  # slot-sorted edge position -> pair id
         self.n_pairs = int(uniq_rt.numel())
+        # the same for the heads, and the relation of every edge (canonical-KGAT score mode needs x_h = e_h W_r and e_r too)
+        self.head_pair_rel = (uniq_rh // n).to(torch.int32).contiguous()
+        self.head_pair_node = (uniq_rh % n).to(torch.int32).contiguous()
+        self.head_pair_of_edge = g_h[o].contiguous()
+        self.edge_rel = rels[o].to(torch.int32).contiguous()
+        self.edge_mult = mult[o].contiguous() if need_mult else None
         # the refreshed attentive matrix lives in this structure
         vals = torch.zeros(col_idx.numel(), dtype=torch.float32, device=dev)
         self.graph = AttentiveGraph(n, row_ptr, col_idx, vals, chunk)

@@ -36,6 +36,12 @@ class InteractionCSR:
             pairs = pairs[order]
             counts = np.bincount(pairs[:, 0], minlength=user_num)
             flat = pairs[:, 1]
+        # the reference derives hits and denominators from a binary item mask (metrics_calculator.py:112-122): an item listed twice for a
+        # user counts once
+        users_all = np.repeat(np.arange(user_num, dtype=np.int64), counts)
+        keys = np.unique(users_all * item_num + flat.astype(np.int64))
+        counts = np.bincount(keys // item_num, minlength=user_num).astype(np.int64)
+        flat = keys % item_num
         self.user_num, self.item_num = user_num, item_num
         self.ptr_host = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
         self.items = torch.from_numpy(flat.astype(np.int32)).to(device)

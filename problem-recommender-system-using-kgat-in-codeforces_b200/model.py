@@ -124,6 +124,10 @@ class KGAT(nn.Module):
         # Amazon-book shape.  False = the reference's literal full-graph propagation per batch.
         self.cf_pruning = True
         self._frontiers: dict = {}
+        # Edge score of the attention refresh: "reference" = what the reference computes (value path of its multi-head attention +
+        # LayerNorm + tanh-sum, degree-weighted: SURVEY.md Q1, the parity target); "kgat" = the KGAT paper's
+        # pi(h, r, t) = (W_r e_t)^T tanh(W_r e_h + e_r) that north_star names, followed by the same duplicate merge + row softmax.
+        self.score_mode = "reference"
 
     # ------------------------------------------------------------------------------------------
     # plumbing
@@ -376,7 +380,18 @@ class KGAT(nn.Module):
         graph = idx.graph
         vals = graph.vals  # refreshed in place: pointers captured by CUDA graphs / the COO view stay valid
         p = mha.dropout_p if self.training else 0.0
-        if p == 0.0:
+        if self.score_mode == "kgat":
+            rel = self._relation_embedding.weight.detach()
+            x_t = ops.att_pair_project(emb, w, idx.pair_tail, idx.pair_rel)
+            x_h = ops.att_pair_project(emb, w, idx.head_pair_node, idx.head_pair_rel)
+            edge_score = ops.att_edge_scores_kgat(x_h, idx.head_pair_of_edge, x_t, idx.pair_of_edge, rel, idx.edge_rel)
+            ones = getattr(idx, "_unit_weight", None)
+            if ones is None:
+                ones = idx._unit_weight = torch.ones_like(idx.edge_weight) if idx.edge_mult is None else idx.edge_mult.to(torch.float32)
+            ops.att_row_softmax(graph.row_ptr, idx.slot_ptr, ones, vals, edge_score=edge_score)
+        elif self.score_mode != "reference":
+            raise ValueError(f"unknown score_mode {self.score_mode!r} (\"reference\" or \"kgat\")")
+        elif p == 0.0:
             _, score = ops.att_pair_scores(emb, w, idx.pair_tail, idx.pair_rel, params, mha.head_num, mha.ln_eps)
             ops.att_row_softmax(graph.row_ptr, idx.slot_ptr, idx.edge_weight, vals, pair_score=score, pair_of_edge=idx.pair_of_edge)
         else:

@@ -547,6 +547,26 @@ def att_pair_scores(emb, W, pair_tail, pair_rel, mha_params, n_heads=8, eps=1e-5
     return v_out, s_out
 
 
+def att_pair_project(emb, W, pair_node, pair_rel):
+    """x[p] = emb[pair_node[p]] @ W[pair_rel[p]] for unique (node, relation) pairs (canonical-KGAT score mode)."""
+    lib = _lib.load()
+    n_pairs, d = pair_node.numel(), emb.shape[1]
+    out = torch.empty(n_pairs, d, dtype=f32, device=emb.device)
+    check(lib.kgat_att_pair_project(_ptr(emb, f32), _ptr(W, f32), d, _ptr(pair_node, i32), _ptr(pair_rel, i32), n_pairs, _ptr(out, f32), _stream()),
+          f"att_pair_project(d={d})")
+    return out
+
+
+def att_edge_scores_kgat(x_head, head_pair, x_tail, tail_pair, rel_emb, edge_rel):
+    """score[e] = <x_tail[tail_pair[e]], tanh(x_head[head_pair[e]] + rel_emb[edge_rel[e]])>  -- the KGAT paper's pi(h, r, t)."""
+    lib = _lib.load()
+    n_edges, d = head_pair.numel(), x_head.shape[1]
+    out = torch.empty(n_edges, dtype=f32, device=x_head.device)
+    check(lib.kgat_att_edge_scores_kgat(_ptr(x_head, f32), _ptr(head_pair, i32), _ptr(x_tail, f32), _ptr(tail_pair, i32), _ptr(rel_emb, f32),
+                                        _ptr(edge_rel, i32), n_edges, d, _ptr(out, f32), _stream()), "att_edge_scores_kgat")
+    return out
+
+
 def att_edge_scores_dropout(pair_v, pair_of_edge, mha_params, dropout_p, head_bits=None, seed=0, offset=0, n_heads=8, eps=1e-5, seed_dev=None):
     lib = _lib.load()
     n_edges = pair_of_edge.numel()

@@ -86,6 +86,15 @@ def golden_pre():
     return Golden("preprocess_tiny.npz")
 
 
+def elem_err(a, b, floor_frac: float = 1e-3) -> float:
+    """Per-element relative error with an absolute floor: max |a - b| / (|b| + floor_frac * max|b|).  Unlike ``rel_err`` (normwise) a
+    small entry that is wrong by a large factor shows; the floor keeps entries that are pure cancellation noise from dominating."""
+    a = torch.as_tensor(a, dtype=torch.float64).flatten().cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).flatten().cpu()
+    floor = floor_frac * max(float(b.abs().max()), 1e-30)
+    return float(((a - b).abs() / (b.abs() + floor)).max())
+
+
 def rel_err(a, b) -> float:
     a = torch.as_tensor(a, dtype=torch.float64).flatten().cpu()
     b = torch.as_tensor(b, dtype=torch.float64).flatten().cpu()

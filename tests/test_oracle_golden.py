@@ -225,3 +225,23 @@ def test_samplers_replay_reference_rng_stream(golden_pre):
     for i in range(3):
         b = O.sample_kg_batch(rng, kd, n_nodes, 16)
         np.testing.assert_array_equal(np.stack(b), g[f"kg_batch{i}"])
+
+
+def test_canonical_kgat_attention_oracle_on_a_hand_case():
+    """oracle.attention_refresh_kgat restates the paper's pi(h, r, t) = (W_r e_t)^T tanh(W_r e_h + e_r): check it against the formula
+    written out by hand on a 3-node graph, incl. a duplicate (h, t) under two relations (summed before the softmax)."""
+    torch.manual_seed(0)
+    n, d, r = 3, 4, 2
+    p = {"_user_entity_embedding.weight": torch.randn(n, d), "_relation_embedding.weight": torch.randn(r, d), "_trans_matrix": torch.randn(r, d, d)}
+    heads, rels, tails = [0, 0, 0, 1], [0, 1, 0, 1], [1, 1, 2, 2]
+    rows, cols, vals = O.attention_refresh_kgat(p, heads, rels, tails, [0, 1], n)
+
+    def pi(h, rr, t):
+        e, w, er = p["_user_entity_embedding.weight"], p["_trans_matrix"][rr], p["_relation_embedding.weight"][rr]
+        return float(((e[t] @ w) * torch.tanh(e[h] @ w + er)).sum())
+
+    s01, s02 = pi(0, 0, 1) + pi(0, 1, 1), pi(0, 0, 2)
+    m = max(s01, s02)
+    z = np.exp(s01 - m) + np.exp(s02 - m)
+    assert rows.tolist() == [0, 0, 1] and cols.tolist() == [1, 2, 2]
+    np.testing.assert_allclose(vals.numpy(), [np.exp(s01 - m) / z, np.exp(s02 - m) / z, 1.0], rtol=1e-5)
