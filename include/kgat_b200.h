@@ -32,7 +32,7 @@ extern "C" {
 #define KGAT_ERR_UNSUPPORTED (-3)
 #define KGAT_ERR_WORKSPACE (-4)
 
-#define KGAT_ABI_VERSION 4
+#define KGAT_ABI_VERSION 3
 #define KGAT_MAX_LAYERS 8   /* embedding table + up to 7 propagation layers */
 #define KGAT_MAX_TENSORS 24 /* tensors per multi-tensor Adam launch */
 #define KGAT_MAX_PEERS 31   /* other ranks of a row-sharded propagation */
@@ -107,33 +107,25 @@ int kgat_spmm_csr_masked(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_r
                          int64_t ldy, const float* Z, int64_t ldz, int32_t d, float* partials, const uint32_t* row_mask,
                          const uint32_t* edge_mask, void* stream);
 
-/* Persistent SpMM over a work-item LIST: Y[r] = sum_k A[r, k] X[k] (+ Z[r]) for the tasks named by `items` (int32 x 4 each:
- * {row, begin, end, partial_slot}; row < 0 = skip).  Two forms:
- *   - n_rows_dev == NULL: items = the plan's own task array, n_items_static of them (every row is written; with an
- *     edge_mask only the edges whose column is in the bitmap are summed and Z is added only for rows in it);
- *   - n_rows_dev != NULL: items = kgat_frontier_items' output for a needed-row list, n_fixed + *n_rows_dev of them (only the
- *     listed rows are written; n_items_static is ignored).
- * The warps walk the list with a static stride, fetching the descriptor two items and the first 32 (col, val) pairs one
- * item ahead of the task being gathered.  edge_mask nullable; n_mask_bits = number of nodes it covers.  d in {16,32,64,128}.
- * Replaces torch.sparse.mm at aggregator.py:54 for the rows a TRAIN_CF batch needs (model.py:188-191). */
-int kgat_spmm_csr_rows(const int32_t* items, int64_t n_items_static, int64_t n_fixed, const int32_t* n_rows_dev,
+/* Persistent variant over a needed-row LIST (one warp strides over work items; no CTA is launched for a dead row):
+ * work = the plan's first n_heavy_tasks tasks (the chunks of the heavy rows; filtered by row_mask, required then) followed
+ * by rows[0 .. *n_rows_dev) where a light row owns the single task n_heavy_tasks + light_rank[row] (light_rank[row] < 0
+ * marks a heavy row); rows == NULL runs every task (dense output, e.g. the embedding gradient) and only masks edges.
+ * edge_mask as above (staged in shared memory when n_mask_bits / 8 <= 32 KB).  d in {16, 32, 64, 128}. */
+int kgat_spmm_csr_rows(const int32_t* tasks, int64_t n_tasks, int64_t n_heavy_tasks, const int32_t* light_rank,
                        int32_t* heavy_rows, int64_t n_heavy, const int32_t* col_idx, const float* vals, const float* X,
                        int64_t n_cols, int64_t ldx, float* Y, int64_t ldy, const float* Z, int64_t ldz, int32_t d,
-                       float* partials, const uint32_t* edge_mask, int64_t n_mask_bits, void* stream);
+                       float* partials, const int32_t* rows, const int32_t* n_rows_dev, const uint32_t* row_mask,
+                       const uint32_t* edge_mask, int64_t n_mask_bits, void* stream);
 
-/* items[0 .. n_heavy_tasks + *n_rows_dev) for a needed-row list: the first n_heavy_tasks entries are the plan's chunk tasks
- * of its heavy rows (row = -1 unless the row is in row_mask), then one entry per listed row (its single task through
- * light_rank; -1 for a listed heavy row, whose chunks were taken above).  items: int32 x 4 x (n_heavy_tasks + max_rows). */
-int kgat_frontier_items(const int32_t* tasks, int64_t n_heavy_tasks, const int32_t* light_rank, const int32_t* rows,
-                        const int32_t* n_rows_dev, int64_t max_rows, const uint32_t* row_mask, int32_t* items, void* stream);
-
-/* Transposed product as a scatter over a needed-row list:  Y[c] += A[r, c] * G[r] for the listed rows r and their edges,
- * and Y[r] += Z[r] (Z nullable) -- 128-bit vector reductions, so Y's destination rows must be zero on entry
- * (kgat_frontier_zero_rows) and the fp32 summation order is not fixed.  items / n_fixed (= n_heavy_tasks): the list's
- * kgat_frontier_items for the plan of A (not of its transpose); tasks: that plan's task array.  d in {16, 32, 64, 128}. */
-int kgat_spmm_scatter_rows(const int32_t* items, const int32_t* tasks, int64_t n_fixed, const int32_t* n_rows_dev,
-                           int64_t max_rows, const int32_t* col_idx, const float* vals, const float* G, int64_t ldg,
-                           const float* Z, int64_t ldz, float* Y, int64_t ldy, int32_t d, void* stream);
+/* Transposed product as a scatter over a needed-row list:  Y[c] += A[r, c] * G[r] for the *n_rows_dev listed rows r and
+ * their edges, and Y[r] += Z[r] (Z nullable) -- 128-bit vector reductions, so Y's destination rows must be zero on entry
+ * (kgat_frontier_zero_rows) and the fp32 summation order is not fixed.  tasks / n_heavy_tasks / light_rank / row_mask: the
+ * plan of A (not of its transpose) and the list's bitmap, as in kgat_spmm_csr_rows.  d in {16, 32, 64, 128}. */
+int kgat_spmm_scatter_rows(const int32_t* tasks, int64_t n_heavy_tasks, const int32_t* light_rank, const int32_t* rows,
+                           const int32_t* n_rows_dev, int64_t max_rows, const uint32_t* row_mask, const int32_t* col_idx,
+                           const float* vals, const float* G, int64_t ldg, const float* Z, int64_t ldz, float* Y, int64_t ldy,
+                           int32_t d, void* stream);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Needed-row frontier of a TRAIN_CF step: exact pruning of model.py:188 (the full propagation   */

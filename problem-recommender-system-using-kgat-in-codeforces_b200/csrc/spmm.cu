@@ -68,25 +68,12 @@ __device__ __forceinline__ void finish_heavy_row(int slot, float* __restrict__ p
 // shared-memory copy) drops the edges whose source row holds no valid data -- the surviving edges are compacted in the
 // staging slab, so the hot loop is unchanged -- and gates the addend Z the same way (Z[row] counts only when row is in
 // `edge_mask`).  Row masking (skipping the tasks of rows nobody reads) is done by the callers.
-// the (col, val) pair of this lane for the first 32 edges of a task (tail lanes: a valid address, weight 0)
-__device__ __forceinline__ void spmm_first_batch(const int4 t, const int32_t* __restrict__ col_idx, const float* __restrict__ vals, int lane,
-                                                 int& c, float& v) {
-    c = 0;
-    v = 0.f;
-    if (t.y < t.z) {
-        const int k = t.y + lane;
-        c = ld_stream_i32(col_idx + min(k, t.z - 1));
-        v = k < t.z ? ld_stream_f32(vals + k) : 0.f;
-    }
-}
-
-template <int D, int U, bool WIDE, bool MASKED, bool PREFETCHED = false>
+template <int D, int U, bool WIDE, bool MASKED>
 __device__ __forceinline__ void spmm_do_task(const int4 t, int2* __restrict__ eb, const int32_t* __restrict__ col_idx,
                                              const float* __restrict__ vals, const float* __restrict__ X, int64_t ldx,
                                              float* __restrict__ Y, int64_t ldy, const float* __restrict__ Z, int64_t ldz,
                                              float* __restrict__ partials, int4* __restrict__ heavy, int n_heavy,
-                                             const uint32_t* __restrict__ edge_mask, const uint32_t* __restrict__ edge_mask_global,
-                                             int c0 = 0, float v0 = 0.f) {
+                                             const uint32_t* __restrict__ edge_mask, const uint32_t* __restrict__ edge_mask_global) {
     constexpr int LPE = D / 4;        // lanes per edge
     constexpr int EPW = 32 / LPE;     // edges per warp step
     constexpr int EPI = EPW * U;      // edges per unrolled iteration (divides 32)
@@ -101,9 +88,13 @@ __device__ __forceinline__ void spmm_do_task(const int4 t, int2* __restrict__ eb
 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int base = t.y;
-    int c = c0;
-    float v = v0;
-    if (!PREFETCHED) spmm_first_batch(t, col_idx, vals, lane, c, v);
+    int c = 0;
+    float v = 0.f;
+    if (base < t.z) {
+        const int k = base + lane;
+        c = ld_stream_i32(col_idx + min(k, t.z - 1));
+        v = k < t.z ? ld_stream_f32(vals + k) : 0.f;
+    }
     while (base < t.z) {
         int cnt;
         if (MASKED && edge_mask != nullptr) {
@@ -184,23 +175,22 @@ __global__ void __launch_bounds__(128) spmm_task_kernel(const int4* __restrict__
                                      edge_mask);
 }
 
-// Persistent launch over a work-item LIST (frontier.cu: kgat_frontier_items resolves a needed-row list into the plan's tasks once per
-// level; for the dense-output backward the list is simply the plan's task array): item i is a task {row, begin, end, partial_slot}, or
-// row < 0 for "nothing to do" (a heavy-row chunk whose row is outside the level).  No warp is launched for a row outside the
-// frontier -- the grid-per-task kernel spends ~30 us on 40 k empty CTAs when 3 % of the rows are live -- and the edge bitmap is staged
-// in shared memory once per CTA when it fits, so the per-edge test is an LDS.
-// A task is ~30 edges at the Amazon-book shape, so a warp's time used to be one dependent chain per task (descriptor -> (col, val) ->
-// gathers -> reduce, ~2,000 cycles of which the gathers are half; ncu: lts__throughput 32-44 %, warps active 55 %).  The loop is
-// therefore software-pipelined over the warp's items: the descriptor is fetched two items ahead and the first 32 (col, val) pairs one
-// item ahead, both in flight while the current task gathers.
+// Persistent launch over a needed-row list (frontier.cu): the warps of a fixed grid stride over
+//   [0, n_heavy_tasks)            the chunk tasks of the heavy rows (first in the plan), filtered by `row_mask`, then
+//   rows[0 .. *n_rows_dev)        the listed rows: a light row owns exactly one task, n_heavy_tasks + light_rank[row]
+// (rows == NULL: every task of the plan -- the dense-output backward, which only masks edges).  No warp is launched for
+// a row outside the frontier -- the grid-per-task kernel spends ~30 us on 40 k empty CTAs when 3 % of the rows are live --
+// and the edge bitmap is staged in shared memory once per CTA when it fits, so the per-edge test is an LDS.
 constexpr int kRowsThreads = 256;
-template <int D, int U, bool WIDE, int CTAS>
-__global__ void __launch_bounds__(kRowsThreads, CTAS) spmm_rows_kernel(const int4* __restrict__ items, int n_static, int n_fixed,
-                                                                   const int32_t* __restrict__ n_rows_dev, const int32_t* __restrict__ col_idx,
-                                                                   const float* __restrict__ vals, const float* __restrict__ X, int64_t ldx,
-                                                                   float* __restrict__ Y, int64_t ldy, const float* __restrict__ Z, int64_t ldz,
-                                                                   float* __restrict__ partials, int4* __restrict__ heavy, int n_heavy,
-                                                                   const uint32_t* __restrict__ edge_mask, int mask_words_smem) {
+template <int D, int U, bool WIDE>
+__global__ void __launch_bounds__(kRowsThreads, 5) spmm_rows_kernel(const int4* __restrict__ tasks, int n_tasks, int n_heavy_tasks,
+                                                                const int32_t* __restrict__ light_rank, const int32_t* __restrict__ rows,
+                                                                const int32_t* __restrict__ n_rows_dev, const int32_t* __restrict__ col_idx,
+                                                                const float* __restrict__ vals, const float* __restrict__ X, int64_t ldx,
+                                                                float* __restrict__ Y, int64_t ldy, const float* __restrict__ Z, int64_t ldz,
+                                                                float* __restrict__ partials, int4* __restrict__ heavy, int n_heavy,
+                                                                const uint32_t* __restrict__ row_mask, const uint32_t* __restrict__ edge_mask,
+                                                                int mask_words_smem) {
     extern __shared__ __align__(16) uint32_t smem_mask[];
     __shared__ int2 ebuf[kRowsThreads / 32][32];
     const uint32_t* emask = edge_mask;
@@ -209,53 +199,26 @@ __global__ void __launch_bounds__(kRowsThreads, CTAS) spmm_rows_kernel(const int
         __syncthreads();
         emask = smem_mask;
     }
-    const int lane = threadIdx.x & 31;
     const int n_warps = (gridDim.x * kRowsThreads) >> 5;
-    const int total = n_rows_dev != nullptr ? n_fixed + n_rows_dev[0] : n_static;
-    const int4 dead = make_int4(-1, 0, 0, -1);
-    int i = (blockIdx.x * kRowsThreads + threadIdx.x) >> 5;
-    int4 t = i < total ? __ldg(items + i) : dead;
-    int4 t1 = i + n_warps < total ? __ldg(items + i + n_warps) : dead;
-    int c, c1;
-    float v, v1;
-    spmm_first_batch(t.x >= 0 ? t : dead, col_idx, vals, lane, c, v);
-    for (; i < total; i += n_warps) {
-        const int4 t2 = i + 2 * n_warps < total ? __ldg(items + i + 2 * n_warps) : dead;  // descriptor two items ahead
-        spmm_first_batch(t1.x >= 0 ? t1 : dead, col_idx, vals, lane, c1, v1);             // first (col, val) batch one item ahead
-        if (t.x >= 0) {
-            if (edge_mask != nullptr)
-                spmm_do_task<D, U, WIDE, true, true>(t, ebuf[threadIdx.x >> 5], col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, heavy, n_heavy,
-                                                     emask, edge_mask, c, v);
-            else
-                spmm_do_task<D, U, WIDE, false, true>(t, ebuf[threadIdx.x >> 5], col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, heavy, n_heavy,
-                                                      nullptr, nullptr, c, v);
-        }
-        t = t1;
-        c = c1;
-        v = v1;
-        t1 = t2;
-    }
-}
-
-// items[i] for i in [0, n_heavy_tasks + *n_rows_dev): the plan's task of work item i of a needed-row list -- the first n_heavy_tasks
-// items are the chunk tasks of the heavy rows (dead unless their row is in `row_mask`), the others the listed rows (a light row owns the
-// single task n_heavy_tasks + light_rank[row]; a listed heavy row is dead here, its chunks were taken above).
-__global__ void __launch_bounds__(256) frontier_items_kernel(const int4* __restrict__ tasks, int n_heavy_tasks,
-                                                             const int32_t* __restrict__ light_rank, const int32_t* __restrict__ rows,
-                                                             const int32_t* __restrict__ n_rows_dev, const uint32_t* __restrict__ row_mask,
-                                                             int4* __restrict__ items) {
-    const int total = n_heavy_tasks + n_rows_dev[0];
-    const int stride = gridDim.x * blockDim.x;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int total = rows != nullptr ? n_heavy_tasks + n_rows_dev[0] : n_tasks;
+    for (int i = (blockIdx.x * kRowsThreads + threadIdx.x) >> 5; i < total; i += n_warps) {
         int4 t;
-        if (i < n_heavy_tasks) {
+        if (rows == nullptr) {
             t = __ldg(tasks + i);
-            if (!((__ldg(row_mask + (t.x >> 5)) >> (t.x & 31)) & 1u)) t.x = -1;
+        } else if (i < n_heavy_tasks) {
+            t = __ldg(tasks + i);
+            if (row_mask != nullptr && !((__ldg(row_mask + (t.x >> 5)) >> (t.x & 31)) & 1u)) continue;
         } else {
             const int lr = __ldg(light_rank + __ldg(rows + (i - n_heavy_tasks)));
-            t = lr >= 0 ? __ldg(tasks + n_heavy_tasks + lr) : make_int4(-1, 0, 0, -1);
+            if (lr < 0) continue;  // a heavy row: its chunks were taken above
+            t = __ldg(tasks + n_heavy_tasks + lr);
         }
-        items[i] = t;
+        if (edge_mask != nullptr)
+            spmm_do_task<D, U, WIDE, true>(t, ebuf[threadIdx.x >> 5], col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, heavy, n_heavy, emask,
+                                           edge_mask);
+        else
+            spmm_do_task<D, U, WIDE, false>(t, ebuf[threadIdx.x >> 5], col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, heavy, n_heavy, nullptr,
+                                            nullptr);
     }
 }
 
@@ -270,21 +233,30 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
 }
 
 template <int D>
-__global__ void __launch_bounds__(256) spmm_scatter_rows_kernel(const int4* __restrict__ items, const int4* __restrict__ tasks, int n_fixed,
-                                                               const int32_t* __restrict__ n_rows_dev, const int32_t* __restrict__ col_idx,
-                                                               const float* __restrict__ vals, const float* __restrict__ G, int64_t ldg,
-                                                               const float* __restrict__ Z, int64_t ldz, float* __restrict__ Y, int64_t ldy) {
+__global__ void __launch_bounds__(256) spmm_scatter_rows_kernel(const int4* __restrict__ tasks, int n_heavy_tasks,
+                                                               const int32_t* __restrict__ light_rank, const int32_t* __restrict__ rows,
+                                                               const int32_t* __restrict__ n_rows_dev, const uint32_t* __restrict__ row_mask,
+                                                               const int32_t* __restrict__ col_idx, const float* __restrict__ vals,
+                                                               const float* __restrict__ G, int64_t ldg, const float* __restrict__ Z,
+                                                               int64_t ldz, float* __restrict__ Y, int64_t ldy) {
     constexpr int LPE = D / 4;     // lanes per edge
     constexpr int EPW = 32 / LPE;  // edges per warp step
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPE, slot = lane / LPE;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    const int total = n_fixed + n_rows_dev[0];
+    const int total = n_heavy_tasks + n_rows_dev[0];
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < total; i += n_warps) {
-        const int4 t = __ldg(items + i);
-        if (t.x < 0) continue;
-        // the task that also carries the row's direct term Z[r]: a light row's only task, or a heavy row's first chunk
-        const bool first_chunk = t.w < 0 || i == 0 || __ldg(tasks + i - 1).x != t.x;
+        int4 t;
+        bool first_chunk = true;  // the task that also carries the row's direct term Z[r]
+        if (i < n_heavy_tasks) {
+            t = __ldg(tasks + i);
+            if (!((__ldg(row_mask + (t.x >> 5)) >> (t.x & 31)) & 1u)) continue;
+            first_chunk = (i == 0) || (__ldg(tasks + i - 1).x != t.x);
+        } else {
+            const int lr = __ldg(light_rank + __ldg(rows + (i - n_heavy_tasks)));
+            if (lr < 0) continue;
+            t = __ldg(tasks + n_heavy_tasks + lr);
+        }
         const float4 g = ldg4(G + (int64_t)t.x * ldg + sub * 4);
         if (Z != nullptr && first_chunk && slot == 0) {
             const float4 z = ldg4(Z + (int64_t)t.x * ldz + sub * 4);
@@ -448,52 +420,37 @@ extern "C" int kgat_spmm_csr_masked(const int32_t* tasks, int64_t n_tasks, int32
                        stream_);
 }
 
-extern "C" int kgat_frontier_items(const int32_t* tasks, int64_t n_heavy_tasks, const int32_t* light_rank, const int32_t* rows,
-                                   const int32_t* n_rows_dev, int64_t max_rows, const uint32_t* row_mask, int32_t* items, void* stream_) {
-    if (!tasks || !light_rank || !rows || !n_rows_dev || !items || max_rows <= 0 || n_heavy_tasks < 0 || n_heavy_tasks >= ((int64_t)1 << 30) ||
-        (n_heavy_tasks > 0 && !row_mask))
-        return KGAT_ERR_INVALID_ARGUMENT;
-    int64_t ctas = (max_rows + n_heavy_tasks + 255) / 256;
-    const int64_t cap = (int64_t)sm_count() * 8;
-    if (ctas > cap) ctas = cap;
-    frontier_items_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream_>>>(reinterpret_cast<const int4*>(tasks), (int)n_heavy_tasks, light_rank, rows,
-                                                                            n_rows_dev, row_mask, reinterpret_cast<int4*>(items));
-    return check_launch();
-}
-
-extern "C" int kgat_spmm_csr_rows(const int32_t* items, int64_t n_items_static, int64_t n_fixed, const int32_t* n_rows_dev, int32_t* heavy_rows,
-                                  int64_t n_heavy, const int32_t* col_idx, const float* vals, const float* X, int64_t n_cols, int64_t ldx, float* Y,
-                                  int64_t ldy, const float* Z, int64_t ldz, int32_t d, float* partials, const uint32_t* edge_mask,
+extern "C" int kgat_spmm_csr_rows(const int32_t* tasks, int64_t n_tasks, int64_t n_heavy_tasks, const int32_t* light_rank,
+                                  int32_t* heavy_rows, int64_t n_heavy, const int32_t* col_idx, const float* vals, const float* X,
+                                  int64_t n_cols, int64_t ldx, float* Y, int64_t ldy, const float* Z, int64_t ldz, int32_t d, float* partials,
+                                  const int32_t* rows, const int32_t* n_rows_dev, const uint32_t* row_mask, const uint32_t* edge_mask,
                                   int64_t n_mask_bits, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!items || n_items_static < 0 || n_fixed < 0 || n_heavy < 0 || n_items_static >= ((int64_t)1 << 31) || n_fixed >= ((int64_t)1 << 30))
-        return KGAT_ERR_INVALID_ARGUMENT;
+    if (n_tasks < 0 || n_heavy < 0 || n_heavy_tasks < 0 || n_heavy_tasks > n_tasks || n_tasks >= ((int64_t)1 << 31)) return KGAT_ERR_INVALID_ARGUMENT;
     if ((ldx & 3) || (ldy & 3) || (Z && (ldz & 3))) return KGAT_ERR_INVALID_ARGUMENT;
     if (n_heavy > 0 && partials == nullptr) return KGAT_ERR_INVALID_ARGUMENT;
-    if (n_rows_dev == nullptr && n_items_static == 0) return KGAT_OK;
+    if ((rows == nullptr) != (n_rows_dev == nullptr) || (rows != nullptr && light_rank == nullptr)) return KGAT_ERR_INVALID_ARGUMENT;
+    if (rows != nullptr && n_heavy_tasks > 0 && row_mask == nullptr) return KGAT_ERR_INVALID_ARGUMENT;
+    if (n_tasks == 0) return KGAT_OK;
     if (n_cols <= 0) return KGAT_ERR_INVALID_ARGUMENT;
     if (d != 16 && d != 32 && d != 64 && d != 128) return KGAT_ERR_UNSUPPORTED;
     const bool use_wide = n_cols * ldx * 4 >= ((int64_t)1 << 32);
     int mask_words = 0;
     if (edge_mask != nullptr) {
         const int64_t words = (n_mask_bits + 31) / 32;
-        if (words > 0 && words * 4 <= 32 * 1024) mask_words = (int)words;  // 1 M nodes: a 32 KB bitmap per CTA still leaves 5 CTAs / SM
+        if (words > 0 && words * 4 <= 32 * 1024) mask_words = (int)words;  // 1 M nodes: a 32 KB bitmap per CTA still leaves 6 CTAs / SM
     }
     const size_t smem = (size_t)mask_words * 4;
-    // 5 CTAs / SM = 51 registers (a few spilled by the prefetch stage) and 40 warps; 4 = 64 registers, 32 warps.  KGAT_SPMM_CTAS picks.
-    static const int ctas_per_sm = [] {
-        const char* e = getenv("KGAT_SPMM_CTAS");
-        return e && atoi(e) == 4 ? 4 : 5;
-    }();
+    const int ctas_per_sm = 5;  // 44-46 registers x 256 threads; 5 x (32 KB bitmap + 2 KB slabs) of shared memory fit as well
     const unsigned blocks = (unsigned)(sm_count() * ctas_per_sm);
-    const int4* it4 = reinterpret_cast<const int4*>(items);
+    const int4* t4 = reinterpret_cast<const int4*>(tasks);
     int4* h4 = reinterpret_cast<int4*>(heavy_rows);
-#define KGAT_ROWS_ARGS it4, (int)n_items_static, (int)n_fixed, n_rows_dev, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, h4, (int)n_heavy, edge_mask, mask_words
+#define KGAT_ROWS_ARGS t4, (int)n_tasks, (int)n_heavy_tasks, light_rank, rows, n_rows_dev, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, h4, \
+                       (int)n_heavy, row_mask, edge_mask, mask_words
 #define KGAT_ROWS_LAUNCH(DD, UU)                                                                                  \
     do {                                                                                                          \
-        if (use_wide) spmm_rows_kernel<DD, UU, true, 5><<<blocks, kRowsThreads, smem, stream>>>(KGAT_ROWS_ARGS);   \
-        else if (ctas_per_sm == 4) spmm_rows_kernel<DD, UU, false, 4><<<blocks, kRowsThreads, smem, stream>>>(KGAT_ROWS_ARGS); \
-        else spmm_rows_kernel<DD, UU, false, 5><<<blocks, kRowsThreads, smem, stream>>>(KGAT_ROWS_ARGS);           \
+        if (use_wide) spmm_rows_kernel<DD, UU, true><<<blocks, kRowsThreads, smem, stream>>>(KGAT_ROWS_ARGS);      \
+        else spmm_rows_kernel<DD, UU, false><<<blocks, kRowsThreads, smem, stream>>>(KGAT_ROWS_ARGS);              \
     } while (0)
     switch (d) {
         case 16: KGAT_ROWS_LAUNCH(16, 2); break;
@@ -509,20 +466,21 @@ extern "C" int kgat_spmm_csr_rows(const int32_t* items, int64_t n_items_static, 
     return check_launch();
 }
 
-extern "C" int kgat_spmm_scatter_rows(const int32_t* items, const int32_t* tasks, int64_t n_fixed, const int32_t* n_rows_dev, int64_t max_rows,
-                                      const int32_t* col_idx, const float* vals, const float* G, int64_t ldg, const float* Z, int64_t ldz, float* Y,
-                                      int64_t ldy, int32_t d, void* stream_) {
+extern "C" int kgat_spmm_scatter_rows(const int32_t* tasks, int64_t n_heavy_tasks, const int32_t* light_rank, const int32_t* rows,
+                                      const int32_t* n_rows_dev, int64_t max_rows, const uint32_t* row_mask, const int32_t* col_idx,
+                                      const float* vals, const float* G, int64_t ldg, const float* Z, int64_t ldz, float* Y, int64_t ldy,
+                                      int32_t d, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!items || !tasks || !n_rows_dev || !col_idx || !vals || !G || !Y || max_rows <= 0 || n_fixed < 0 || n_fixed >= ((int64_t)1 << 30) ||
-        (ldg & 3) || (ldy & 3) || (Z && (ldz & 3)))
+    if (!tasks || !light_rank || !rows || !n_rows_dev || !col_idx || !vals || !G || !Y || max_rows <= 0 || n_heavy_tasks < 0 ||
+        n_heavy_tasks >= ((int64_t)1 << 30) || (n_heavy_tasks > 0 && !row_mask) || (ldg & 3) || (ldy & 3) || (Z && (ldz & 3)))
         return KGAT_ERR_INVALID_ARGUMENT;
-    int64_t ctas = (max_rows + n_fixed + 7) / 8;
+    int64_t ctas = (max_rows + n_heavy_tasks + 7) / 8;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (ctas > cap) ctas = cap;
-    const int4* it4 = reinterpret_cast<const int4*>(items);
     const int4* t4 = reinterpret_cast<const int4*>(tasks);
-#define KGAT_SCATTER(DD) \
-    spmm_scatter_rows_kernel<DD><<<(unsigned)ctas, 256, 0, stream>>>(it4, t4, (int)n_fixed, n_rows_dev, col_idx, vals, G, ldg, Z, ldz, Y, ldy)
+#define KGAT_SCATTER(DD)                                                                                                               \
+    spmm_scatter_rows_kernel<DD><<<(unsigned)ctas, 256, 0, stream>>>(t4, (int)n_heavy_tasks, light_rank, rows, n_rows_dev, row_mask, col_idx, \
+                                                                     vals, G, ldg, Z, ldz, Y, ldy)
     switch (d) {
         case 16: KGAT_SCATTER(16); break;
         case 32: KGAT_SCATTER(32); break;

@@ -40,8 +40,6 @@ class Frontier:
         self.caps = [self.n] * (self.n_layers - 1) + [min(self.n, int(max_ids))]
         self.row_lists = [torch.zeros(c, dtype=torch.int32, device=dev) for c in self.caps]
         self.counts = torch.zeros(self.n_layers, dtype=torch.int32, device=dev)
-        # each level's list resolved into the work items of A's SpMM plan (forward of the level, scatter backward out of it)
-        self.item_lists = [torch.zeros(graph.plan.n_partials + c, 4, dtype=torch.int32, device=dev) for c in self.caps]
         self.scratch = torch.zeros(ops.frontier_scratch_ints(self.n), dtype=torch.int32, device=dev)
         self.bad_ids = torch.zeros(1, dtype=torch.int32, device=dev)  # ids outside [0, n) seen so far (skipped)
         # backward of the upper (sparse) layers: scatter the edges of the few source rows (fp32 vector reductions) instead of
@@ -55,9 +53,6 @@ class Frontier:
 
     def rows(self, level: int) -> torch.Tensor:
         return self.row_lists[level - 1]
-
-    def items(self, level: int) -> torch.Tensor:
-        return self.item_lists[level - 1]
 
     def count(self, level: int) -> torch.Tensor:
         return self.counts[level - 1 : level]
@@ -75,8 +70,6 @@ class Frontier:
         for level in range(top - 1, 0, -1):
             ops.frontier_expand(g.plan, g.col_idx, self.rows(level + 1), self.count(level + 1), self.cap(level + 1), self.mask(level + 1), self.flags)
             ops.frontier_list(self.flags, self.mask(level), self.n, self.scratch, self.rows(level), self.count(level))
-        for level in range(1, top + 1):
-            ops.frontier_items(g.plan, self.rows(level), self.count(level), self.cap(level), self.mask(level), out=self.items(level))
         return self
 
     def check_ids(self) -> None:

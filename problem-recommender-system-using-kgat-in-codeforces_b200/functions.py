@@ -79,7 +79,7 @@ def propagate_forward(graph: AttentiveGraph, e0: torch.Tensor, layers, drop: Dro
             side = graph.matmul(x, out=_buf(n, x.shape[1], device=dev), row_mask=frontier.mask(1), tag="_L1")
         else:
             side = graph.matmul(x, out=_buf(n, x.shape[1], device=dev), row_mask=frontier.mask(l + 1), rows=frontier.rows(l + 1),
-                                n_rows_dev=frontier.count(l + 1), tag=f"_L{l + 1}", items=frontier.items(l + 1))
+                                n_rows_dev=frontier.count(l + 1), tag=f"_L{l + 1}")
         out = _buf(n, d_out, device=dev)
         inv = _buf(n, device=dev) if save else None
         flags = _buf(n, d_out, dtype=torch.uint8, device=dev) if save else None
@@ -141,7 +141,7 @@ def propagate_backward(graph: AttentiveGraph, st: PropState, layers, g_last: tor
             g_prev = _buf(n, d_in, device=dev)
             ops.frontier_zero_rows(g_prev, frontier.rows(l - 1), frontier.count(l - 1), frontier.cap(l - 1))
             ops.spmm_scatter_rows(graph.plan, graph.col_idx, graph.vals, g_s, g_prev, frontier.rows(l), frontier.count(l), frontier.cap(l),
-                                  frontier.mask(l), addend=g_e, tag=f"_L{l}", items=frontier.items(l))
+                                  frontier.mask(l), addend=g_e, tag=f"_L{l}")
         else:
             below = {"row_mask": frontier.mask(l - 1), "rows": frontier.rows(l - 1), "n_rows_dev": frontier.count(l - 1)} if l > 1 else {}
             g_prev = graph.matmul_t(g_s, out=_buf(n, d_in, device=dev), addend=g_e, edge_mask=frontier.mask(l), tag=f"_L{l}", **below)

@@ -147,21 +147,21 @@ class AttentiveGraph:
 
     # -- ops ----------------------------------------------------------------------------------
     def matmul(self, x: torch.Tensor, out: torch.Tensor | None = None, addend: torch.Tensor | None = None, row_mask=None, edge_mask=None,
-               rows=None, n_rows_dev=None, tag: str = "", items=None):
+               rows=None, n_rows_dev=None, tag: str = ""):
         """out = A @ x (+ addend)   -- reference aggregator.py:54.  ``row_mask`` / ``edge_mask`` / ``rows``: a frontier level's
         bitmap(s) and row list (ops.spmm)."""
         if out is None:
             out = torch.empty(self.n, x.shape[1], dtype=torch.float32, device=x.device)
         return ops.spmm(self.plan, self.col_idx, self.vals, x, out, addend, self.partials(x.shape[1]), row_mask=row_mask, edge_mask=edge_mask,
-                        rows=rows, n_rows_dev=n_rows_dev, tag=tag, items=items)
+                        rows=rows, n_rows_dev=n_rows_dev, tag=tag)
 
     def matmul_t(self, x: torch.Tensor, out: torch.Tensor | None = None, addend: torch.Tensor | None = None, row_mask=None, edge_mask=None,
-                 rows=None, n_rows_dev=None, tag: str = "", items=None):
+                 rows=None, n_rows_dev=None, tag: str = ""):
         """out = A^T @ x (+ addend)   -- autograd backward of aggregator.py:54"""
         if out is None:
             out = torch.empty(self.n, x.shape[1], dtype=torch.float32, device=x.device)
         return ops.spmm(self.t_plan, self.t_idx, self.t_vals, x, out, addend, self.partials(x.shape[1]), row_mask=row_mask, edge_mask=edge_mask,
-                        rows=rows, n_rows_dev=n_rows_dev, tag=tag, items=items)
+                        rows=rows, n_rows_dev=n_rows_dev, tag=tag)
 
     # -- the reference-facing view --------------------------------------------------------------
     def indices64(self) -> torch.Tensor:

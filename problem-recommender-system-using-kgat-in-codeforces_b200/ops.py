@@ -194,12 +194,11 @@ def _spmm_name(plan, col_idx, vals, x, out, addend=None, partials=None, row_mask
 @_timed(_spmm_name)
 def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.Tensor | None = None, partials=None,
          row_mask: torch.Tensor | None = None, edge_mask: torch.Tensor | None = None, rows: torch.Tensor | None = None,
-         n_rows_dev: torch.Tensor | None = None, tag: str = "", items: torch.Tensor | None = None):
+         n_rows_dev: torch.Tensor | None = None, tag: str = ""):
     """out = A @ x (+ addend); ``plan`` is a graph.SpmmPlan.  ``row_mask`` / ``edge_mask``: node bitmaps of a
     ``frontier.Frontier`` level (only the rows in ``row_mask`` are computed; edges / addend rows outside ``edge_mask`` are
     dropped).  With the level's row list (``rows``, ``n_rows_dev``; needs ``row_mask`` too) or with an ``edge_mask`` alone the
-    persistent row-list kernel runs; a ``row_mask`` without a list uses the grid-per-task kernel.  ``items``: the list already
-    resolved into the plan's tasks (``frontier_items``; resolved here when absent)."""
+    persistent row-list kernel runs; a ``row_mask`` without a list uses the grid-per-task kernel."""
     lib = _lib.load()
     d = x.shape[1]
     if plan.n_heavy > 0:
@@ -218,19 +217,15 @@ def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.
         for m in (row_mask, edge_mask):
             if m is not None and m.numel() * 32 < n_bits:
                 raise KgatLibraryError("spmm: node bitmap too small")
-        if rows is not None:
-            if row_mask is None or n_rows_dev is None or plan.light_rank is None:
-                raise KgatLibraryError("spmm: a row list needs its bitmap, its device-side count and a plan with light_rank")
-            if items is None:  # callers that keep a Frontier pass its per-level list; a one-off list is resolved here
-                items = frontier_items(plan, rows, n_rows_dev, rows.numel(), row_mask)
-            elif items.numel() < 4 * (plan.n_partials + 1):
-                raise KgatLibraryError("spmm: work-item list too small")
-            listed = (_ptr(items, i32), 0, plan.n_partials, _ptr(n_rows_dev, i32))
-        else:
-            listed = (_ptr(plan.tasks, i32), plan.n_tasks, 0, None)
+        if rows is not None and (row_mask is None or n_rows_dev is None or plan.light_rank is None):
+            raise KgatLibraryError("spmm: a row list needs its bitmap, its device-side count and a plan with light_rank")
         check(
-            lib.kgat_spmm_csr_rows(*listed, _ptr(plan.heavy, i32) if plan.n_heavy else None, plan.n_heavy, *args[4:],
-                                   _ptr(edge_mask, i32) if edge_mask is not None else None, n_bits, _stream()),
+            lib.kgat_spmm_csr_rows(
+                _ptr(plan.tasks, i32), plan.n_tasks, plan.n_partials, _ptr(plan.light_rank, i32) if plan.light_rank is not None else None,
+                _ptr(plan.heavy, i32) if plan.n_heavy else None, plan.n_heavy, *args[4:],
+                _ptr(rows, i32) if rows is not None else None, _ptr(n_rows_dev, i32) if rows is not None else None,
+                _ptr(row_mask, i32) if row_mask is not None else None, _ptr(edge_mask, i32) if edge_mask is not None else None, n_bits, _stream(),
+            ),
             "spmm_csr_rows",
         )
     elif row_mask is None and edge_mask is None:
@@ -247,38 +242,19 @@ def spmm(plan, col_idx, vals, x: torch.Tensor, out: torch.Tensor, addend: torch.
 
 @_timed(lambda plan, col_idx, vals, g, out, *a, **k: f"spmmT_d{g.shape[1]}_scatter{k.get('tag', '')}")
 def spmm_scatter_rows(plan, col_idx, vals, g: torch.Tensor, out: torch.Tensor, rows, n_rows_dev, max_rows: int, row_mask, addend=None,
-                      tag: str = "", items: torch.Tensor | None = None):
+                      tag: str = ""):
     """out[c] += A[r, c] * g[r] over the listed rows r (and out[r] += addend[r]); ``plan`` / ``col_idx`` / ``vals`` of A itself.
-    The destination rows of ``out`` must have been zeroed (frontier_zero_rows).  ``items`` as in ``spmm``."""
+    The destination rows of ``out`` must have been zeroed (frontier_zero_rows)."""
     lib = _lib.load()
     d = g.shape[1]
-    if items is None:
-        items = frontier_items(plan, rows, n_rows_dev, max_rows, row_mask)
     check(
         lib.kgat_spmm_scatter_rows(
-            _ptr(items, i32), _ptr(plan.tasks, i32), plan.n_partials, _ptr(n_rows_dev, i32), int(max_rows),
-            _ptr(col_idx, i32), _ptr(vals, f32), _ptr(g, f32, "g", True), g.stride(0),
+            _ptr(plan.tasks, i32), plan.n_partials, _ptr(plan.light_rank, i32), _ptr(rows, i32), _ptr(n_rows_dev, i32), int(max_rows),
+            _ptr(row_mask, i32), _ptr(col_idx, i32), _ptr(vals, f32), _ptr(g, f32, "g", True), g.stride(0),
             _ptr(addend, f32, "addend", True) if addend is not None else None, addend.stride(0) if addend is not None else 0,
             _ptr(out, f32, "out", True), out.stride(0), d, _stream(),
         ),
         "spmm_scatter_rows",
-    )
-    return out
-
-
-def frontier_items(plan, rows, n_rows_dev, max_rows: int, row_mask, out: torch.Tensor | None = None) -> torch.Tensor:
-    """The needed-row list ``rows[: *n_rows_dev]`` resolved into work items of ``plan`` (int32 [n_heavy_tasks + max_rows, 4]) for the
-    row-list SpMM / scatter kernels."""
-    lib = _lib.load()
-    need = plan.n_partials + int(max_rows)
-    if out is None:
-        out = torch.empty(need, 4, dtype=torch.int32, device=rows.device)
-    elif out.numel() < 4 * need:
-        raise KgatLibraryError("frontier_items: output too small")
-    check(
-        lib.kgat_frontier_items(_ptr(plan.tasks, i32), plan.n_partials, _ptr(plan.light_rank, i32), _ptr(rows, i32), _ptr(n_rows_dev, i32),
-                                int(max_rows), _ptr(row_mask, i32) if row_mask is not None else None, _ptr(out, i32), _stream()),
-        "frontier_items",
     )
     return out
 

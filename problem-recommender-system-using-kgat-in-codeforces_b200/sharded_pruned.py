@@ -232,8 +232,7 @@ class RangeShardedEngine:
             w1, b1, w2, b2 = self.layers[l]
             lvl = l + 1
             x = tables[-1]
-            side = g.matmul(x, out=_buf(n, x.shape[1], device=dev), row_mask=f.mask(lvl), rows=f.rows(lvl), n_rows_dev=f.count(lvl), tag=f"_L{lvl}",
-                            items=f.items(lvl))
+            side = g.matmul(x, out=_buf(n, x.shape[1], device=dev), row_mask=f.mask(lvl), rows=f.rows(lvl), n_rows_dev=f.count(lvl), tag=f"_L{lvl}")
             out = _buf(n, self.dims[lvl], device=dev)
             inv, flags = _buf(n, device=dev), _buf(n, self.dims[lvl], dtype=torch.uint8, device=dev)
             ops.biagg_forward(x, side, w1, b1, w2, b2, out, inv, flags, dropout_p=ps[l], seed=seed, offset=lvl << 40, seed_dev=self.step_dev,
@@ -271,7 +270,7 @@ class RangeShardedEngine:
             pgrads[l - 1] = gw
             g_prev = _buf(n, d_in, device=dev)
             ops.frontier_zero_rows(g_prev, f.rows(l - 1), f.count(l - 1), f.cap(l - 1))
-            ops.spmm_scatter_rows(g.plan, g.col_idx, g.vals, g_s, g_prev, f.rows(l), f.count(l), f.cap(l), f.mask(l), addend=g_e, tag=f"_L{l}", items=f.items(l))
+            ops.spmm_scatter_rows(g.plan, g.col_idx, g.vals, g_s, g_prev, f.rows(l), f.count(l), f.cap(l), f.mask(l), addend=g_e, tag=f"_L{l}")
             inject(l - 1, g_prev)
             grad = g_prev
         # ---- first layer backward, my rows of level 1
