@@ -352,22 +352,24 @@ __global__ void __launch_bounds__(Cfg<DIN, DOUT>::NT) biagg_bwd_kernel(
 }
 
 // Sum the per-CTA partial parameter gradients in a fixed order (deterministic).  A block owns 32 output
-// elements; its 8 warps each add a strided eighth of the CTAs, then the 8 sub-sums are added in warp order.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int n_ctas, int din, int dout,
-                                                              float* __restrict__ gW1, float* __restrict__ gb1,
-                                                              float* __restrict__ gW2, float* __restrict__ gb2, int accumulate) {
-    __shared__ float sub[8][32];
+// elements; its 32 warps each add a strided 32nd of the CTAs (296 persistent CTAs: a chain of <= 10 loads per warp -- with 8 warps
+// the 37-deep chains made this a 8-12 us kernel), then the 32 sub-sums are added in warp order.
+constexpr int kReduceParts = 32;
+__global__ void __launch_bounds__(32 * kReduceParts) reduce_partials_kernel(const float* __restrict__ partials, int n_ctas, int din, int dout,
+                                                                           float* __restrict__ gW1, float* __restrict__ gb1,
+                                                                           float* __restrict__ gW2, float* __restrict__ gb2, int accumulate) {
+    __shared__ float sub[kReduceParts][32];
     const int total = 2 * din * dout + 2 * dout;
     const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + lane;
     float s = 0.f;
     if (i < total)
-        for (int c = part; c < n_ctas; c += 8) s += partials[(int64_t)c * total + i];
+        for (int c = part; c < n_ctas; c += kReduceParts) s += partials[(int64_t)c * total + i];
     sub[part][lane] = s;
     __syncthreads();
     if (part != 0 || i >= total) return;
 #pragma unroll
-    for (int q = 1; q < 8; ++q) s += sub[q][lane];
+    for (int q = 1; q < kReduceParts; ++q) s += sub[q][lane];
     float* dst;
     if (i < din * dout) dst = gW1 + i;
     else if (i < 2 * din * dout) dst = gW2 + (i - din * dout);
@@ -575,7 +577,7 @@ int kgat_biagg_reduce_param_grads(const float* partials, int32_t n_ctas, int32_t
                                   float* gW2, float* gb2, int32_t accumulate, void* stream) {
     if (n_ctas <= 0 || d_in <= 0 || d_out <= 0) return KGAT_ERR_INVALID_ARGUMENT;
     const int total = 2 * d_in * d_out + 2 * d_out;
-    reduce_partials_kernel<<<(total + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partials, n_ctas, d_in, d_out, gW1, gb1, gW2, gb2,
+    reduce_partials_kernel<<<(total + 31) / 32, 32 * kReduceParts, 0, (cudaStream_t)stream>>>(partials, n_ctas, d_in, d_out, gW1, gb1, gW2, gb2,
                                                                                accumulate);
     return check_launch();
 }
