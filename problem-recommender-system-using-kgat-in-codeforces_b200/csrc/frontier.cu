@@ -40,6 +40,12 @@ __global__ void frontier_mark_kernel(const int64_t* __restrict__ ids, int64_t n_
 // flags[r] = flags[c] = 1 for every listed row r and every column c of A[r, :].  Work items are the SpMM plan's tasks
 // (<= chunk edges each, graph.py), enumerated like the row-list SpMM does: the chunk tasks of the heavy rows first
 // (filtered by the level's bitmap), then one task per listed light row -- so a hub row does not serialise on one warp.
+__device__ __forceinline__ uint32_t ld_flag_l1(const uint8_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.ca.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 __global__ void __launch_bounds__(128) frontier_expand_kernel(const int4* __restrict__ tasks, int n_heavy_tasks,
                                                               const int32_t* __restrict__ light_rank, const int32_t* __restrict__ col_idx,
                                                               const int32_t* __restrict__ rows, const int32_t* __restrict__ cnt_dev,
@@ -69,9 +75,11 @@ __global__ void __launch_bounds__(128) frontier_expand_kernel(const int4* __rest
                 const int k = base + q * 32 + lane;
                 c[q] = k < t.z ? __ldg(col_idx + k) : -1;
             }
-            // test before set: hub columns are hit thousands of times (a stale 0 only costs a redundant store of 1)
+            // test before set: hub columns are hit thousands of times (a stale 0 only costs a redundant store of 1).  The test is
+            // an L1-cached load on purpose: read through L2 (ld.cg) the few hub bytes are one hot sector for every SM and the kernel
+            // took 56-75 us; from L1 each SM misses once per hub and stores at most about once.
 #pragma unroll
-            for (int q = 0; q < 8; ++q) seen[q] = c[q] >= 0 ? (uint32_t)__ldcg(flags + c[q]) : 1u;
+            for (int q = 0; q < 8; ++q) seen[q] = c[q] >= 0 ? (uint32_t)ld_flag_l1(flags + c[q]) : 1u;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
                 if (!seen[q]) flags[c[q]] = 1;
