@@ -32,7 +32,7 @@ extern "C" {
 #define KGAT_ERR_UNSUPPORTED (-3)
 #define KGAT_ERR_WORKSPACE (-4)
 
-#define KGAT_ABI_VERSION 3
+#define KGAT_ABI_VERSION 4
 #define KGAT_MAX_LAYERS 8   /* embedding table + up to 7 propagation layers */
 #define KGAT_MAX_TENSORS 24 /* tensors per multi-tensor Adam launch */
 #define KGAT_MAX_PEERS 31   /* other ranks of a row-sharded propagation */
@@ -141,10 +141,11 @@ int kgat_frontier_mark_ids(const int64_t* ids64, int64_t n_ids, int64_t n_nodes,
                            void* stream);
 /* flags[r] = flags[c] = 1 for the *count_dev rows r listed in `rows` (their bitmap: level_bitmap) and every column c of
  * A[r, :].  Work items are the SpMM plan's tasks (kgat_spmm_csr_rows: the first n_heavy_tasks chunk tasks filtered by
- * level_bitmap, then the listed light rows through light_rank), so hub rows are spread over many warps. */
+ * level_bitmap, then the listed light rows through light_rank), so hub rows are spread over many warps.  n_nodes = the
+ * number of rows / columns of A (while a bitmap of them fits in shared memory the columns are deduplicated per SM first). */
 int kgat_frontier_expand(const int32_t* tasks, int64_t n_heavy_tasks, const int32_t* light_rank, const int32_t* col_idx,
                          const int32_t* rows, const int32_t* count_dev, int64_t max_rows, const uint32_t* level_bitmap,
-                         uint8_t* flags, void* stream);
+                         uint8_t* flags, int64_t n_nodes, void* stream);
 /* bitmap <- flags (every word written; flags cleared); rows[0 .. *count_dev) = ascending node ids of the set bits;
  * scratch: kgat_frontier_scratch_ints(n_nodes) int32 */
 int64_t kgat_frontier_scratch_ints(int64_t n_nodes);

@@ -13,7 +13,7 @@ from pathlib import Path
 
 KGAT_MAX_LAYERS = 8
 KGAT_MAX_TENSORS = 24
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("KGAT_B200_LIB", _PKG_DIR / "lib" / "libkgat_b200.so"))
@@ -84,7 +84,7 @@ SIGNATURES: dict[str, tuple] = {
     "kgat_spmm_csr_rows": (_I32, [_P, _I64, _I64, _P, _P, _I64, _P, _P, _P, _I64, _I64, _P, _I64, _P, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P]),
     "kgat_spmm_scatter_rows": (_I32, [_P, _I64, _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _P, _I64, _P, _I64, _I32, _P]),
     "kgat_frontier_mark_ids": (_I32, [_P, _I64, _I64, _P, _P, _P]),
-    "kgat_frontier_expand": (_I32, [_P, _I64, _P, _P, _P, _P, _I64, _P, _P, _P]),
+    "kgat_frontier_expand": (_I32, [_P, _I64, _P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
     "kgat_frontier_scratch_ints": (_I64, [_I64]),
     "kgat_frontier_list": (_I32, [_P, _P, _I64, _P, _P, _P, _P]),
     "kgat_frontier_segment": (_I32, [_P, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P]),

@@ -11,6 +11,8 @@
 // Membership is collected in a BYTE-per-node flag array with plain stores (idempotent, so no atomics: 700 k edge
 // visits at the Amazon-book shape would otherwise serialise on the ~160 cache lines of a 20 KB bitmap -- measured
 // 98 us with atomicOr, see profiles/) and folded into the bitmap by the listing pass, which also clears the flags.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace kgat {
@@ -40,12 +42,10 @@ __global__ void frontier_mark_kernel(const int64_t* __restrict__ ids, int64_t n_
 // flags[r] = flags[c] = 1 for every listed row r and every column c of A[r, :].  Work items are the SpMM plan's tasks
 // (<= chunk edges each, graph.py), enumerated like the row-list SpMM does: the chunk tasks of the heavy rows first
 // (filtered by the level's bitmap), then one task per listed light row -- so a hub row does not serialise on one warp.
-__device__ __forceinline__ uint32_t ld_flag_l1(const uint8_t* p) {
-    uint32_t v;
-    asm volatile("ld.global.ca.u8 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-
+// Measured at the Amazon-book shape (tools/prof_frontier.py, ~35 k source rows; profiles/r2_frontier_variants.txt): testing a flag
+// before setting it costs more than it saves -- the loads of a byte other SMs are storing to are slower than the redundant stores
+// (test through L2, 32 edges at a time: 87 us; 256 at a time: 113 us; test through L1: 148 us; store without a test: 57 us; the
+// shared-memory kernel below: 45 us).  This kernel is the fallback for graphs whose node bitmap does not fit in shared memory.
 __global__ void __launch_bounds__(128) frontier_expand_kernel(const int4* __restrict__ tasks, int n_heavy_tasks,
                                                               const int32_t* __restrict__ light_rank, const int32_t* __restrict__ col_idx,
                                                               const int32_t* __restrict__ rows, const int32_t* __restrict__ cnt_dev,
@@ -64,25 +64,60 @@ __global__ void __launch_bounds__(128) frontier_expand_kernel(const int4* __rest
             t = __ldg(tasks + n_heavy_tasks + lr);
         }
         if (lane == 0) flags[t.x] = 1;
-        // A task is <= 256 edges and a warp owns only a few tasks, so the kernel's time is the dependent chain
-        // col_idx (HBM stream) -> flag byte (L2) -> store per 32 edges (measured 56 us for ~10^6 edges when walked 32 at a time).
-        // Eight column loads, then eight flag tests, are issued back to back instead: one round trip of each kind per 256 edges.
         for (int base = t.y; base < t.z; base += 256) {
             int c[8];
-            uint32_t seen[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int k = base + q * 32 + lane;
                 c[q] = k < t.z ? __ldg(col_idx + k) : -1;
             }
-            // test before set: hub columns are hit thousands of times (a stale 0 only costs a redundant store of 1).  The test is
-            // an L1-cached load on purpose: read through L2 (ld.cg) the few hub bytes are one hot sector for every SM and the kernel
-            // took 56-75 us; from L1 each SM misses once per hub and stores at most about once.
-#pragma unroll
-            for (int q = 0; q < 8; ++q) seen[q] = c[q] >= 0 ? (uint32_t)ld_flag_l1(flags + c[q]) : 1u;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-                if (!seen[q]) flags[c[q]] = 1;
+                if (c[q] >= 0) flags[c[q]] = 1;
+        }
+    }
+}
+
+// Default: one persistent 1024-thread CTA per SM keeps a bitmap of the WHOLE node range in shared memory (n_nodes / 8 bytes); an edge's
+// column goes to the global flag array only the first time this CTA sees it, so a hub column costs <= one global store per SM.
+__global__ void __launch_bounds__(1024) frontier_expand_smem_kernel(const int4* __restrict__ tasks, int n_heavy_tasks,
+                                                                    const int32_t* __restrict__ light_rank, const int32_t* __restrict__ col_idx,
+                                                                    const int32_t* __restrict__ rows, const int32_t* __restrict__ cnt_dev,
+                                                                    const uint32_t* __restrict__ level_mask, uint8_t* __restrict__ flags,
+                                                                    int n_words) {
+    extern __shared__ __align__(16) uint32_t seen_bits[];
+    for (int w = threadIdx.x; w < n_words; w += 1024) seen_bits[w] = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int n_warps = (gridDim.x * 1024) >> 5;
+    const int total = n_heavy_tasks + cnt_dev[0];
+    // consecutive items to consecutive CTAs (not warps): the chunks of one hub row then meet different shared bitmaps, its columns
+    // (mostly other hubs) are deduplicated against what the CTA's other 31 warps have already seen
+    for (int i = blockIdx.x + gridDim.x * (threadIdx.x >> 5); i < total; i += n_warps) {
+        int4 t;
+        if (i < n_heavy_tasks) {
+            t = __ldg(tasks + i);
+            if (!((__ldg(level_mask + (t.x >> 5)) >> (t.x & 31)) & 1u)) continue;
+        } else {
+            const int lr = __ldg(light_rank + __ldg(rows + (i - n_heavy_tasks)));
+            if (lr < 0) continue;
+            t = __ldg(tasks + n_heavy_tasks + lr);
+        }
+        if (lane == 0) flags[t.x] = 1;
+        for (int base = t.y; base < t.z; base += 256) {
+            int c[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k = base + q * 32 + lane;
+                c[q] = k < t.z ? __ldg(col_idx + k) : -1;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (c[q] < 0) continue;
+                const uint32_t bit = 1u << (c[q] & 31);
+                if (seen_bits[c[q] >> 5] & bit) continue;
+                if (!(atomicOr(seen_bits + (c[q] >> 5), bit) & bit)) flags[c[q]] = 1;
+            }
         }
     }
 }
@@ -236,15 +271,33 @@ int kgat_frontier_mark_ids(const int64_t* ids64, int64_t n_ids, int64_t n_nodes,
 
 int kgat_frontier_expand(const int32_t* tasks, int64_t n_heavy_tasks, const int32_t* light_rank, const int32_t* col_idx,
                          const int32_t* rows, const int32_t* count_dev, int64_t max_rows, const uint32_t* level_bitmap, uint8_t* flags,
-                         void* stream) {
-    if (!tasks || !light_rank || !col_idx || !rows || !count_dev || !flags || max_rows <= 0 || n_heavy_tasks < 0 ||
+                         int64_t n_nodes, void* stream) {
+    if (!tasks || !light_rank || !col_idx || !rows || !count_dev || !flags || max_rows <= 0 || n_heavy_tasks < 0 || n_nodes <= 0 ||
         (n_heavy_tasks > 0 && !level_bitmap) || n_heavy_tasks >= ((int64_t)1 << 30))
         return KGAT_ERR_INVALID_ARGUMENT;
     int64_t ctas = (max_rows + n_heavy_tasks + 3) / 4;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (ctas > cap) ctas = cap;
-    frontier_expand_kernel<<<(unsigned)ctas, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int4*>(tasks), (int)n_heavy_tasks, light_rank,
-                                                                             col_idx, rows, count_dev, level_bitmap, flags);
+    static const bool plain = [] {  // KGAT_EXPAND_PLAIN=1: the global-store kernel even when the bitmap fits (A/B, tools/prof_frontier.py)
+        const char* e = getenv("KGAT_EXPAND_PLAIN");
+        return e && atoi(e) == 1;
+    }();
+    const int4* t4 = reinterpret_cast<const int4*>(tasks);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_words = (n_nodes + 31) / 32;
+    if (!plain && n_words * 4 <= 200 * 1024) {
+        static bool configured = false;
+        if (!configured) {
+            KGAT_CUDA_TRY(cudaFuncSetAttribute(frontier_expand_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured = true;
+        }
+        int64_t big = (max_rows + n_heavy_tasks + 31) / 32;
+        if (big > sm_count()) big = sm_count();
+        frontier_expand_smem_kernel<<<(unsigned)big, 1024, (size_t)n_words * 4, st>>>(t4, (int)n_heavy_tasks, light_rank, col_idx, rows, count_dev,
+                                                                                     level_bitmap, flags, (int)n_words);
+        return check_launch();
+    }
+    frontier_expand_kernel<<<(unsigned)ctas, 128, 0, st>>>(t4, (int)n_heavy_tasks, light_rank, col_idx, rows, count_dev, level_bitmap, flags);
     return check_launch();
 }
 

@@ -281,7 +281,8 @@ def frontier_expand(plan, col_idx, rows, count_dev, max_rows: int, level_bitmap,
     """flags[r] = flags[c] = 1 for the listed rows r and the columns c of their CSR rows; ``plan``: the graph's SpmmPlan."""
     lib = _lib.load()
     check(lib.kgat_frontier_expand(_ptr(plan.tasks, i32), plan.n_partials, _ptr(plan.light_rank, i32), _ptr(col_idx, i32), _ptr(rows, i32),
-                                   _ptr(count_dev, i32), int(max_rows), _ptr(level_bitmap, i32), _ptr(flags, u8), _stream()), "frontier_expand")
+                                   _ptr(count_dev, i32), int(max_rows), _ptr(level_bitmap, i32), _ptr(flags, u8), plan.light_rank.numel(),
+                                   _stream()), "frontier_expand")
 
 
 def frontier_list(flags, bitmap, n_nodes: int, scratch, rows, count_dev):
