@@ -32,7 +32,7 @@ extern "C" {
 #define KGAT_ERR_UNSUPPORTED (-3)
 #define KGAT_ERR_WORKSPACE (-4)
 
-#define KGAT_ABI_VERSION 4
+#define KGAT_ABI_VERSION 5
 #define KGAT_MAX_LAYERS 8   /* embedding table + up to 7 propagation layers */
 #define KGAT_MAX_TENSORS 24 /* tensors per multi-tensor Adam launch */
 #define KGAT_MAX_PEERS 31   /* other ranks of a row-sharded propagation */
@@ -390,6 +390,31 @@ int kgat_adam_sparse_rows(float* param, float* grad, float* exp_avg, float* exp_
                           int32_t n_ids, int32_t d, const int64_t* cur_step_dev, const int64_t* s0_dev, const float* hyper_dev, void* stream);
 int kgat_adam_lazy_flush(float* param, float* exp_avg, float* exp_avg_sq, int32_t* row_step, int64_t n_rows, int32_t d,
                          const int64_t* cur_step_dev, const int64_t* s0_dev, const float* table, const float* hyper_dev, void* stream);
+
+/* Rolling-window exact Adam for the KG phase (the epoch engine's default; replaces the per-step dense sweep of
+ * torch.optim.Adam over the N x d embedding table, model.py:414-419, with bit-identical results).  The table is cut
+ * into `window` contiguous slices; phase step j replays the zero-gradient updates of slice (j - 1) mod window up to
+ * step j - 1, so no row lags more than window + 1 steps and a step moves 1/window of the optimiser state through HBM.
+ *   kgat_adam_rolling_prepare  before the forward: claims the batch's compact gradient rows (as kgat_transr_claim_rows),
+ *                              zeroes g_rows and the two optional buffers zero_a / zero_b (n_a / n_b floats, multiples of
+ *                              4), and brings every batch row up to the steps done so far (cur_step_dev - s0_dev);
+ *   kgat_transr_step_claimed   kgat_transr_step minus its claim launch;
+ *   kgat_adam_rolling_apply    after kgat_adam_advance: claimed rows take their gradient (step j) and free their slot,
+ *                              the tensors of `dense` (may be NULL) take a plain Adam step, the slice is replayed;
+ *   kgat_adam_lazy_flush       end of the phase.
+ * row_step / s0_dev / table / hyper_dev as for the lazy scheme above. */
+int kgat_adam_rolling_prepare(const int64_t* heads, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, int32_t d,
+                              int32_t* row_slot, float* g_rows, float* zero_a, int64_t n_a, float* zero_b, int64_t n_b, float* param,
+                              float* exp_avg, float* exp_avg_sq, int32_t* row_step, const int64_t* cur_step_dev, const int64_t* s0_dev,
+                              const float* table, const float* hyper_dev, void* stream);
+int kgat_transr_step_claimed(const float* emb, const float* rel_emb, const float* W, int32_t d, int32_t k, const int64_t* heads,
+                             const int64_t* rels, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, float reg, float* loss,
+                             float* loss_sum, float* margin, const int32_t* row_slot, float* g_rows, float* g_rel_emb, float* g_W,
+                             void* stream);
+int kgat_adam_rolling_apply(const int64_t* heads, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, int32_t d,
+                            int32_t* row_slot, const float* g_rows, float* param, float* exp_avg, float* exp_avg_sq, int32_t* row_step,
+                            int64_t n_rows, int32_t window, const kgat_adam_tensors_t* dense, const int64_t* cur_step_dev,
+                            const int64_t* s0_dev, const float* table, const float* hyper_dev, void* stream);
 
 /* dst[0..elems) = src[(counter_dev[0] % n_batches) * elems + ...]: selects the current step's pre-sampled
  * id batch from a device-resident epoch array (counter = an optimiser step counter) so that a captured

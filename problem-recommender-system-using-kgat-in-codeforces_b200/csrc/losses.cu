@@ -484,6 +484,22 @@ int kgat_transr_step(const float* emb, const float* rel_emb, const float* W, int
     return check_launch();
 }
 
+/* kgat_transr_step without its first launch: the compact rows were claimed and the gradient buffers zeroed by the caller
+ * (kgat_adam_rolling_prepare does both while it brings the batch rows up to date) */
+int kgat_transr_step_claimed(const float* emb, const float* rel_emb, const float* W, int32_t d, int32_t k, const int64_t* heads,
+                             const int64_t* rels, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, float reg, float* loss,
+                             float* loss_sum, float* margin, const int32_t* row_slot, float* g_rows, float* g_rel_emb, float* g_W,
+                             void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (batch <= 0 || d <= 0 || !row_slot || !g_rows || !g_rel_emb || !g_W || !loss || !margin) return KGAT_ERR_INVALID_ARGUMENT;
+    const unsigned blocks = (unsigned)batch;
+    KGAT_TRANSR_DISPATCH((transr_bwd_kernel<DM, KM, true><<<blocks, 128, 0, stream>>>(emb, rel_emb, W, heads, rels, pos_tails, neg_tails,
+                                                                                     batch, reg, margin, nullptr, g_rows, g_rel_emb, g_W,
+                                                                                     row_slot)));
+    loss_reduce_kernel<<<1, 256, 0, stream>>>(margin, batch, reg, loss, loss_sum);
+    return check_launch();
+}
+
 int kgat_transr_claim_rows(const int64_t* heads, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, int32_t d,
                            int32_t* row_slot, float* g_rows, void* stream_) {
     if (batch <= 0 || d <= 0 || (d & 3) || !row_slot || !g_rows) return KGAT_ERR_INVALID_ARGUMENT;

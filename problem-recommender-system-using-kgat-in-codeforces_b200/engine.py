@@ -13,6 +13,8 @@ un-captured equivalent through the public model API (the two are tested to agree
 
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib, ops
@@ -86,7 +88,8 @@ class _AdamSlot:
 
 
 class TrainEngine:
-    def __init__(self, model: KGAT, cf_batch: int = CF_BATCH, kg_batch: int = KG_BATCH, use_graphs: bool = True, lazy_kg_adam: bool = False):
+    def __init__(self, model: KGAT, cf_batch: int = CF_BATCH, kg_batch: int = KG_BATCH, use_graphs: bool = True, lazy_kg_adam: bool = False,
+                 kg_adam: str | None = None, kg_window: int = 32):
         if not hasattr(model, "_cf_optimizer"):
             raise RuntimeError("call model.build_optimizer(...) before creating a TrainEngine")
         self.model = model
@@ -118,7 +121,19 @@ class TrainEngine:
         # be replayed once, and the replay (IEEE sqrt + division per element-step, serial per row) is
         # latency-bound, whereas the dense sweep streams at 81-91 % of HBM peak.  Kept as a documented negative
         # result and for graphs where only a vanishing fraction of the rows is ever touched.
-        self.lazy_kg_adam = lazy_kg_adam
+        # KG-phase Adam over the embedding table (all three are bit-identical, tested):
+        #   "rolling" (default)  bounded deferral: a rotating 1/kg_window slice of the table is replayed per step (csrc/adam.cu)
+        #   "dense"              the per-step 245 MB sweep (what torch.optim.Adam does)
+        #   "lazy"               unbounded deferral (the negative result above)
+        if kg_adam is None:
+            kg_adam = "lazy" if lazy_kg_adam else os.environ.get("KGAT_KG_ADAM", "rolling")
+        if kg_adam not in ("rolling", "dense", "lazy"):
+            raise ValueError(f"kg_adam must be 'rolling', 'dense' or 'lazy', got {kg_adam!r}")
+        self.kg_adam_mode = kg_adam
+        self.lazy_kg_adam = kg_adam == "lazy"
+        self.kg_window = int(kg_window)
+        if self.kg_window < 1:
+            raise ValueError("kg_window must be >= 1")
         self.kg_row_step = torch.zeros(emb.shape[0], dtype=torch.int32, device=dev)
         self.kg_s0 = torch.zeros(1, dtype=torch.int64, device=dev)
         self.kg_table = None
@@ -185,6 +200,16 @@ class TrainEngine:
             ops.adam_apply([p.data for p in ad.params[1:]], self.kg_grads[1:], ad.exp_avg[1:], ad.exp_avg_sq[1:], ad.hyper)
             for ids in (h, tails):
                 ops.adam_sparse_rows(emb, self.kg_grads[0], ad.exp_avg[0], ad.exp_avg_sq[0], self.kg_row_step, ids, ad.step_dev, self.kg_s0, ad.hyper)
+        elif self.kg_adam_mode == "rolling":
+            ops.adam_rolling_prepare(h, pt, nt, self.kg_row_slot, self.kg_grad_rows, self.kg_grads[1], self.kg_grads[2], emb, ad.exp_avg[0],
+                                     ad.exp_avg_sq[0], self.kg_row_step, ad.step_dev, self.kg_s0, self.kg_table, ad.hyper)
+            ops.transr_step_claimed(emb, rel, w, h, r, pt, nt, reg, self.kg_loss, self.kg_loss_sum, self.kg_scratch, self.kg_row_slot,
+                                    self.kg_grad_rows, self.kg_grads[1], self.kg_grads[2])
+            ops.adam_advance(ad.step_dev, ad.lr, ad.b1, ad.b2, ad.eps, ad.hyper)
+            ops.adam_rolling_apply(h, pt, nt, self.kg_row_slot, self.kg_grad_rows, emb, ad.exp_avg[0], ad.exp_avg_sq[0], self.kg_row_step,
+                                   self.kg_window, [p.data for p in ad.params[1:]], self.kg_grads[1:], ad.exp_avg[1:], ad.exp_avg_sq[1:],
+                                   ad.step_dev, self.kg_s0, self.kg_table, ad.hyper)
+            return
         else:
             ops.transr_step(emb, rel, w, h, r, pt, nt, reg, self.kg_loss, self.kg_loss_sum, self.kg_scratch, self.kg_row_slot,
                             self.kg_grad_rows, self.kg_grads[1], self.kg_grads[2])
@@ -193,13 +218,14 @@ class TrainEngine:
         self.kg_loss_sum.add_(self.kg_loss)
 
     def _kg_phase_begin(self, n_kg: int):
-        """Lazy Adam bookkeeping: phase origin = current optimiser step, per-step bias-correction table."""
-        if not self.lazy_kg_adam or n_kg == 0:
+        """Lazy / rolling Adam bookkeeping: phase origin = current optimiser step, per-step bias-correction table."""
+        if self.kg_adam_mode == "dense" or n_kg == 0:
             return
         ad = self.kg_adam
         self.kg_s0.copy_(ad.step_dev)
         self.kg_row_step.zero_()
-        self.kg_grads[0].zero_()
+        if self.lazy_kg_adam:
+            self.kg_grads[0].zero_()
         need = 2 * (n_kg + 2)  # +2: the capture warm-up may run one extra (undone) step
         if self.kg_table is None or self.kg_table.numel() < need:
             self.kg_table = torch.empty(max(need, 2 * 16384), dtype=f32, device=self.dev)
@@ -209,7 +235,7 @@ class TrainEngine:
         ops.adam_set_hyper(1, ad.lr, ad.b1, ad.b2, ad.eps, ad.hyper)  # constants (1-b1, b2, 1-b2, eps) for the first catch-up
 
     def _kg_phase_end(self, n_kg: int):
-        if not self.lazy_kg_adam or n_kg == 0:
+        if self.kg_adam_mode == "dense" or n_kg == 0:
             return
         ad = self.kg_adam
         emb = self.kg_params[0].detach()

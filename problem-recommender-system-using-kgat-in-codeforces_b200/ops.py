@@ -694,6 +694,57 @@ def adam_apply(params, grads, exp_avgs, exp_avg_sqs, hyper: torch.Tensor, peer_p
         check(lib.kgat_adam_apply(C.byref(t), _ptr(hyper, f32), _stream()), "adam_apply")
 
 
+@_timed("adam_rolling_prepare")
+def adam_rolling_prepare(heads, pos_t, neg_t, row_slot, g_rows, zero_a, zero_b, param, exp_avg, exp_avg_sq, row_step, cur_step_dev, s0, table, hyper):
+    """Rolling-window KG Adam, before the forward: claim compact gradient rows, zero ``g_rows`` / ``zero_a`` / ``zero_b``, bring
+    the batch rows of ``param`` up to the steps done so far."""
+    lib = _lib.load()
+    if g_rows.numel() < 3 * heads.numel() * param.shape[1]:
+        raise KgatLibraryError("adam_rolling_prepare: g_rows needs 3 * batch * d floats")
+    check(lib.kgat_adam_rolling_prepare(_ptr(heads, i64), _ptr(pos_t, i64), _ptr(neg_t, i64), heads.numel(), param.shape[1], _ptr(row_slot, i32),
+                                        _ptr(g_rows, f32), _ptr(zero_a, f32) if zero_a is not None else None, zero_a.numel() if zero_a is not None else 0,
+                                        _ptr(zero_b, f32) if zero_b is not None else None, zero_b.numel() if zero_b is not None else 0,
+                                        _ptr(param, f32), _ptr(exp_avg, f32), _ptr(exp_avg_sq, f32), _ptr(row_step, i32), _ptr(cur_step_dev, i64),
+                                        _ptr(s0, i64), _ptr(table, f32), _ptr(hyper, f32), _stream()), "adam_rolling_prepare")
+
+
+@_timed("transr_step_claimed")
+def transr_step_claimed(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, loss, loss_sum, scratch, row_slot, g_rows, g_rel, g_W):
+    """``transr_step`` for rows claimed (and buffers zeroed) by ``adam_rolling_prepare``."""
+    lib = _lib.load()
+    if g_rows.numel() < 3 * heads.numel() * emb.shape[1] or scratch.numel() < 2 * heads.numel():
+        raise KgatLibraryError("transr_step_claimed: g_rows needs 3 * batch * d floats, scratch 2 * batch")
+    check(lib.kgat_transr_step_claimed(_ptr(emb, f32), _ptr(rel_emb, f32), _ptr(W, f32), emb.shape[1], rel_emb.shape[1], _ptr(heads, i64),
+                                       _ptr(rels, i64), _ptr(pos_t, i64), _ptr(neg_t, i64), heads.numel(), float(reg), _ptr(loss, f32),
+                                       _ptr(loss_sum, f32) if loss_sum is not None else None, _ptr(scratch, f32), _ptr(row_slot, i32),
+                                       _ptr(g_rows, f32), _ptr(g_rel, f32), _ptr(g_W, f32), _stream()), "transr_step_claimed")
+
+
+@_timed("adam_rolling_apply")
+def adam_rolling_apply(heads, pos_t, neg_t, row_slot, g_rows, param, exp_avg, exp_avg_sq, row_step, window, dense_params, dense_grads,
+                       dense_exp_avgs, dense_exp_avg_sqs, cur_step_dev, s0, table, hyper):
+    """Rolling-window KG Adam, after ``adam_advance``: claimed rows take their gradient, the small dense tensors a plain step, and the
+    window's current slice of ``param`` is replayed (zero-gradient updates) to the previous step."""
+    lib = _lib.load()
+    n = len(dense_params)
+    if n > _lib.KGAT_MAX_TENSORS:
+        raise KgatLibraryError("adam_rolling_apply: too many dense tensors")
+    t = AdamTensorsT()
+    t.n_tensors = n
+    for j in range(n):
+        if dense_grads[j].numel() != dense_params[j].numel():
+            raise KgatLibraryError("adam_rolling_apply: gradient / parameter size mismatch")
+        t.param[j] = _ptr(dense_params[j], f32, "param")
+        t.grad[j] = _ptr(dense_grads[j], f32, "grad")
+        t.exp_avg[j] = _ptr(dense_exp_avgs[j], f32, "exp_avg")
+        t.exp_avg_sq[j] = _ptr(dense_exp_avg_sqs[j], f32, "exp_avg_sq")
+        t.numel[j] = dense_params[j].numel()
+    check(lib.kgat_adam_rolling_apply(_ptr(heads, i64), _ptr(pos_t, i64), _ptr(neg_t, i64), heads.numel(), param.shape[1], _ptr(row_slot, i32),
+                                      _ptr(g_rows, f32), _ptr(param, f32), _ptr(exp_avg, f32), _ptr(exp_avg_sq, f32), _ptr(row_step, i32),
+                                      param.shape[0], int(window), C.byref(t), _ptr(cur_step_dev, i64), _ptr(s0, i64), _ptr(table, f32),
+                                      _ptr(hyper, f32), _stream()), "adam_rolling_apply")
+
+
 def adam_hyper_table(s0_dev: torch.Tensor, n_steps: int, lr, beta1, beta2, table: torch.Tensor):
     lib = _lib.load()
     if table.numel() < 2 * n_steps:
