@@ -32,7 +32,7 @@ extern "C" {
 #define KGAT_ERR_UNSUPPORTED (-3)
 #define KGAT_ERR_WORKSPACE (-4)
 
-#define KGAT_ABI_VERSION 5
+#define KGAT_ABI_VERSION 6
 #define KGAT_MAX_LAYERS 8   /* embedding table + up to 7 propagation layers */
 #define KGAT_MAX_TENSORS 24 /* tensors per multi-tensor Adam launch */
 #define KGAT_MAX_PEERS 31   /* other ranks of a row-sharded propagation */
@@ -402,25 +402,37 @@ int kgat_adam_lazy_flush(float* param, float* exp_avg, float* exp_avg_sq, int32_
  *   kgat_adam_rolling_apply    after kgat_adam_advance: claimed rows take their gradient (step j) and free their slot,
  *                              the tensors of `dense` (may be NULL) take a plain Adam step, the slice is replayed;
  *   kgat_adam_lazy_flush       end of the phase.
- * row_step / s0_dev / table / hyper_dev as for the lazy scheme above. */
+ * row_step / s0_dev / table / hyper_dev as for the lazy scheme above.  `advanced` = 1 when the step counter was already
+ * advanced for this step (kgat_step_begin_i64), so the steps done are one fewer.  `parts`: bit 0 = claimed rows + dense tensors,
+ * bit 1 = slice replay; the two parts touch disjoint rows (ownership through atomicMax on row_step) and may run as concurrent
+ * launches on two streams once the prepare launch has finished. */
 int kgat_adam_rolling_prepare(const int64_t* heads, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, int32_t d,
                               int32_t* row_slot, float* g_rows, float* zero_a, int64_t n_a, float* zero_b, int64_t n_b, float* param,
-                              float* exp_avg, float* exp_avg_sq, int32_t* row_step, const int64_t* cur_step_dev, const int64_t* s0_dev,
-                              const float* table, const float* hyper_dev, void* stream);
+                              float* exp_avg, float* exp_avg_sq, int32_t* row_step, const int64_t* cur_step_dev, int32_t advanced,
+                              const int64_t* s0_dev, const float* table, const float* hyper_dev, void* stream);
 int kgat_transr_step_claimed(const float* emb, const float* rel_emb, const float* W, int32_t d, int32_t k, const int64_t* heads,
                              const int64_t* rels, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, float reg, float* loss,
                              float* loss_sum, float* margin, const int32_t* row_slot, float* g_rows, float* g_rel_emb, float* g_W,
                              void* stream);
 int kgat_adam_rolling_apply(const int64_t* heads, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, int32_t d,
                             int32_t* row_slot, const float* g_rows, float* param, float* exp_avg, float* exp_avg_sq, int32_t* row_step,
-                            int64_t n_rows, int32_t window, const kgat_adam_tensors_t* dense, const int64_t* cur_step_dev,
+                            int64_t n_rows, int32_t window, const kgat_adam_tensors_t* dense, int32_t parts, const int64_t* cur_step_dev,
                             const int64_t* s0_dev, const float* table, const float* hyper_dev, void* stream);
+
+/* Device self-test of the Adam arithmetic core: for i < n computes q = m[i] / (sqrt(v[i]) * inv_sqrt_bc2 + eps) by the kernels'
+ * branch-free sequences (with their fallback) and by the IEEE builtins; counts[0] += results whose bits differ, counts[1] +=
+ * elements that stayed on the fast sequences.  counts: 2 int32, zeroed by the caller. */
+int kgat_selftest_adam_arith(const float* m, const float* v, int64_t n, float inv_sqrt_bc2, float eps, int32_t* counts, void* stream);
 
 /* dst[0..elems) = src[(counter_dev[0] % n_batches) * elems + ...]: selects the current step's pre-sampled
  * id batch from a device-resident epoch array (counter = an optimiser step counter) so that a captured
  * CUDA graph of a training step replays through the whole epoch without host work. */
 int kgat_select_batch_i64(const int64_t* src, int64_t n_batches, int64_t elems, const int64_t* counter_dev, int64_t* dst,
                           void* stream);
+/* kgat_select_batch_i64 followed by kgat_adam_advance on the same counter, in one single-CTA launch: the batch of step
+ * counter % n_batches is selected, then the counter is incremented and hyper_dev written for the new step. */
+int kgat_step_begin_i64(const int64_t* src, int64_t n_batches, int64_t elems, int64_t* step_dev, int64_t* dst, double lr, double beta1,
+                        double beta2, double eps, float* hyper_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------- */
 /* P5: batch samplers on the device       reference preprocess.py:328-415 (CF), 417-530 (KG)   */

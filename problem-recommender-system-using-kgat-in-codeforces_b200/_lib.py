@@ -13,7 +13,7 @@ from pathlib import Path
 
 KGAT_MAX_LAYERS = 8
 KGAT_MAX_TENSORS = 24
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("KGAT_B200_LIB", _PKG_DIR / "lib" / "libkgat_b200.so"))
@@ -123,9 +123,11 @@ SIGNATURES: dict[str, tuple] = {
     "kgat_adam_lazy_catchup": (_I32, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P]),
     "kgat_adam_sparse_rows": (_I32, [_P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P]),
     "kgat_adam_lazy_flush": (_I32, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P]),
-    "kgat_adam_rolling_prepare": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "kgat_adam_rolling_prepare": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
+    "kgat_step_begin_i64": (_I32, [_P, _I64, _I64, _P, _P, _D, _D, _D, _D, _P, _P]),
     "kgat_transr_step_claimed": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P, _P, _I32, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "kgat_adam_rolling_apply": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, C.POINTER(AdamTensorsT), _P, _P, _P, _P, _P]),
+    "kgat_adam_rolling_apply": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, C.POINTER(AdamTensorsT), _I32, _P, _P, _P, _P, _P]),
+    "kgat_selftest_adam_arith": (_I32, [_P, _P, _I64, _F, _F, _P, _P]),
     "kgat_fill_f32": (_I32, [_P, _I64, _F, _P]),
     "kgat_select_batch_i64": (_I32, [_P, _I64, _I64, _P, _P, _P]),
     "kgat_sample_cf_batch": (_I32, [_P, _P, _P, _I32, _I32, _I32, _U64, _P, _P, _P]),
@@ -157,7 +159,7 @@ KERNELS_PER_CALL = {
     "kgat_adam_advance": 1, "kgat_adam_set_hyper": 1, "kgat_adam_apply": 1, "kgat_adam_hyper_table": 1, "kgat_adam_lazy_catchup": 1, "kgat_adam_sparse_rows": 1,
     "kgat_adam_lazy_flush": 1, "kgat_fill_f32": 1, "kgat_select_batch_i64": 1, "kgat_sample_cf_batch": 1, "kgat_sample_kg_batch": 1,
     "kgat_peer_push": 1, "kgat_peer_push_rows": 1, "kgat_publish_loss": 1, "kgat_zero_rows_i64": 1, "kgat_transr_rows_to_dense": 1, "kgat_transr_release_rows": 1, "kgat_peer_signal_wait": 1, "kgat_transr_claim_rows": 1, "kgat_transr_step": 3,
-    "kgat_adam_rolling_prepare": 1, "kgat_transr_step_claimed": 2, "kgat_adam_rolling_apply": 1,
+    "kgat_adam_rolling_prepare": 1, "kgat_transr_step_claimed": 2, "kgat_adam_rolling_apply": 1, "kgat_selftest_adam_arith": 1, "kgat_step_begin_i64": 1,
 }
 
 

@@ -98,6 +98,29 @@ __global__ void select_batch_kernel(const int64_t* __restrict__ src, int64_t n_b
         dst[i] = src[b * elems + i];
 }
 
+// select_batch + kgat_adam_advance in one single-CTA launch (the first node of a captured KG step): every thread reads the
+// counter, the batch is copied, and only then is the counter advanced and the step's Adam scalars written
+__global__ void __launch_bounds__(1024) step_begin_kernel(const int64_t* __restrict__ src, int64_t n_batches, int64_t elems,
+                                                          int64_t* __restrict__ step, int64_t* __restrict__ dst, double lr, double b1,
+                                                          double b2, double eps, float* __restrict__ hyper) {
+    const int64_t s_old = step[0];
+    const int64_t b = s_old % n_batches;
+    for (int64_t i = threadIdx.x; i < elems; i += blockDim.x) dst[i] = src[b * elems + i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int64_t s = s_old + 1;
+        step[0] = s;
+        const double bc1 = 1.0 - pow(b1, (double)s);
+        const double bc2 = 1.0 - pow(b2, (double)s);
+        hyper[0] = (float)(1.0 - b1);
+        hyper[1] = (float)b2;
+        hyper[2] = (float)(1.0 - b2);
+        hyper[3] = (float)(lr / bc1);
+        hyper[4] = (float)(1.0 / sqrt(bc2));
+        hyper[5] = (float)eps;
+    }
+}
+
 inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 inline unsigned blocks_for(int64_t n, int threads = 256) { return (unsigned)((n + threads - 1) / threads); }
 
@@ -221,6 +244,13 @@ int kgat_select_batch_i64(const int64_t* src, int64_t n_batches, int64_t elems, 
     if (n_batches <= 0 || elems <= 0 || !counter_dev) return KGAT_ERR_INVALID_ARGUMENT;
     select_batch_kernel<<<(unsigned)((elems + 255) / 256 < 64 ? (elems + 255) / 256 : 64), 256, 0, (cudaStream_t)stream>>>(
         src, n_batches, elems, counter_dev, dst);
+    return check_launch();
+}
+
+int kgat_step_begin_i64(const int64_t* src, int64_t n_batches, int64_t elems, int64_t* step_dev, int64_t* dst, double lr, double beta1,
+                        double beta2, double eps, float* hyper_dev, void* stream) {
+    if (!src || n_batches <= 0 || elems <= 0 || !step_dev || !dst || !hyper_dev) return KGAT_ERR_INVALID_ARGUMENT;
+    step_begin_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(src, n_batches, elems, step_dev, dst, lr, beta1, beta2, eps, hyper_dev);
     return check_launch();
 }
 

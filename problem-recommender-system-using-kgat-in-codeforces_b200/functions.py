@@ -287,6 +287,7 @@ class GraphedStep:
         self.grads = None
         self.adam_grads = None  # optional: the gradient tensors the fused optimiser replay reads instead of `grads` ...
         self.adam_row_slot0 = None  # ... with compact rows for the first parameter (ops.adam_apply row_slot0)
+        self.adam_rolling = None  # ... or the rolling-window update of optim.DeferredRows: dict(deferred, ids, row_slot)
         self._adam = {}
         self._lib = _lib.load()
         # the captured graph bakes in the addresses of every buffer the bodies' closures own (needed-row frontier, static
@@ -313,6 +314,8 @@ class GraphedStep:
         self._exec = self.graph.raw_cuda_graph_exec()
         self._ids_ptr = self.ids.data_ptr()
         self._ids_bytes = self.ids.numel() * 8
+        self._batch, self._row_bytes = batch, batch * 8
+        self._dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
         self._grad_key = tuple(g.data_ptr() for g in self.grads)
         self._param_ids = tuple(id(p) for p in self.params)
 
@@ -324,17 +327,17 @@ class GraphedStep:
             pg = p.grad
             if pg is not None and (pg is g or pg.data_ptr() == g.data_ptr()):
                 p.grad = pg.clone()  # an un-applied gradient still aliases our buffer (accumulation): keep its value
-        b = self.ids.shape[1]
+        # consecutive int64 rows of one [n_ids, B] block (device, or host: pinned or not, cudaMemcpyAsync stages pageable memory
+        # before it returns) travel in the same C call as the launch
         first = ids[0]
-        stream = torch.cuda.current_stream().cuda_stream
-        one_block = first.numel() == b and first.dtype == torch.int64 and first.is_contiguous()
-        if one_block:
-            base = first.data_ptr()
-            for i, t in enumerate(ids):
-                if t.data_ptr() != base + i * b * 8 or t.dtype != torch.int64 or not t.is_contiguous() or t.numel() != b:
-                    one_block = False
-                    break
-            one_block = one_block and (first.is_cuda or first.is_pinned())
+        base = first.data_ptr()
+        stride = self._row_bytes
+        one_block = True
+        for i, t in enumerate(ids):
+            if t.data_ptr() != base + i * stride or t.numel() != self._batch:
+                one_block = False
+                break
+        stream = torch._C._cuda_getCurrentRawStream(self._dev_index)
         if one_block:
             rc = self._lib.kgat_step_submit(self._ids_ptr, base, self._ids_bytes, self._exec, stream)
         else:
@@ -376,7 +379,7 @@ class GraphedStep:
             if p.grad is not g:
                 return False
         plan = opt.fast_plan(self.params, self.adam_grads if self.adam_grads is not None else self.grads, self._grad_key,
-                             row_slot0=self.adam_row_slot0)
+                             row_slot0=self.adam_row_slot0, rolling=self.adam_rolling)
         if plan is None:
             return False
         opt.fast_replay(plan, self.params)

@@ -36,7 +36,7 @@ from .functions import (CFLossFunction, DropoutSpec, GraphedStep, KGLossFunction
                         propagate_backward, propagate_forward)
 from .graph import AttentiveGraph, EdgeIndex
 from .multi_head_attention import MultiHeadAttention
-from .optim import FusedAdam
+from .optim import DeferredRows, FusedAdam
 
 
 @dataclass
@@ -59,6 +59,23 @@ class KGATMode(IntEnum):
     PREDICT = 3
 
 
+class _EntityEmbedding(nn.Embedding):
+    """``nn.Embedding`` whose ``weight`` attribute first settles any deferred optimiser work on it (optim.DeferredRows): inside
+    a run of TRAIN_KG steps the table's rows lag a bounded number of zero-gradient Adam updates behind; whoever looks at the
+    parameter -- other modes, checkpoints, user code -- triggers the catch-up and sees exactly the reference's values.  The
+    KG step itself reads ``_parameters["weight"]``.  Same state_dict keys, same repr, same init RNG consumption."""
+
+    def __getattr__(self, name: str):
+        if name == "weight":
+            hook = self.__dict__.get("_kgat_settle")
+            if hook is not None:
+                hook()
+        return super().__getattr__(name)
+
+    def _get_name(self) -> str:
+        return "Embedding"
+
+
 class KGAT(nn.Module):
     def __init__(self, args: KGATArgs) -> None:
         super().__init__()
@@ -74,7 +91,7 @@ class KGAT(nn.Module):
         self._kg_embedding_dim = args.kg_embedding_dim
         n = self._user_num + self._entity_num
 
-        self._user_entity_embedding = nn.Embedding(num_embeddings=n, embedding_dim=self._cf_embedding_dim)
+        self._user_entity_embedding = _EntityEmbedding(num_embeddings=n, embedding_dim=self._cf_embedding_dim)
         self._relation_embedding = nn.Embedding(num_embeddings=self._relation_num, embedding_dim=self._kg_embedding_dim)
         self._trans_matrix = nn.Parameter(data=torch.Tensor(self._relation_num, self._cf_embedding_dim, self._kg_embedding_dim))
         nn.init.xavier_uniform_(tensor=self._user_entity_embedding.weight)
@@ -128,6 +145,11 @@ class KGAT(nn.Module):
         # LayerNorm + tanh-sum, degree-weighted: SURVEY.md Q1, the parity target); "kgat" = the KGAT paper's
         # pi(h, r, t) = (W_r e_t)^T tanh(W_r e_h + e_r) that north_star names, followed by the same duplicate merge + row softmax.
         self.score_mode = "reference"
+        # KG phase through this API: update the batch's rows and a rotating 1 / kg_window slice of the entity table per step
+        # instead of sweeping all N rows (bit-identical once settled; see optim.DeferredRows).  False = per-step sweep.
+        self.kg_deferred_adam = True
+        self.kg_window = 16
+        self._user_entity_embedding.__dict__["_kgat_settle"] = self._settle
 
     # ------------------------------------------------------------------------------------------
     # plumbing
@@ -136,8 +158,30 @@ class KGAT(nn.Module):
     def node_num(self) -> int:
         return self._user_num + self._entity_num
 
+    def _settle(self) -> None:
+        """Bring every row of the entity table up to the KG optimiser's step count (no-op unless a deferred phase is open)."""
+        opt = self.__dict__.get("_kg_optimizer")
+        if opt is not None and opt.deferred is not None and opt.deferred.active:
+            opt.deferred.flush()
+
+    def _emb_raw(self) -> torch.nn.Parameter:
+        """The entity table without settling deferred rows (the KG step's own accesses)."""
+        return self._user_entity_embedding._parameters["weight"]
+
+    def state_dict(self, *a, **k):
+        self._settle()
+        return super().state_dict(*a, **k)
+
+    def train(self, mode: bool = True):
+        self._settle()
+        return super().train(mode)
+
+    def named_parameters(self, *a, **k):
+        self._settle()
+        return super().named_parameters(*a, **k)
+
     def _device(self) -> torch.device:
-        dev = self._user_entity_embedding.weight.device
+        dev = self._emb_raw().device
         if dev.type != "cuda":
             raise KgatLibraryError(
                 "kgat_b200.KGAT runs on a CUDA device only (call .to('cuda')); there is no CPU / PyTorch fallback"
@@ -154,11 +198,13 @@ class KGAT(nn.Module):
         return [agg.kernel_params() for agg in self._aggregator_layers]
 
     def _apply(self, fn, *a, **k):
+        self._settle()
         out = super()._apply(fn, *a, **k)
         self._invalidate()
         return out
 
     def load_state_dict(self, *a, **k):
+        self._settle()
         out = super().load_state_dict(*a, **k)
         self._invalidate()
         return out
@@ -258,7 +304,9 @@ class KGAT(nn.Module):
         (copied by the step's own launch call), pass through untouched; anything else goes through ``_ids``."""
         out = []
         for t in tensors:
-            if isinstance(t, torch.Tensor) and t.dtype == torch.int64 and t.is_contiguous() and (t.is_cuda or t.is_pinned()):
+            # host tensors need not be pinned: the step's copy (cudaMemcpyAsync in kgat_step_submit / Tensor.copy_) stages pageable
+            # memory before it returns; is_pinned() alone costs ~1 us per tensor
+            if type(t) is torch.Tensor and t.dtype is torch.int64 and t.is_contiguous():
                 out.append(t)
             else:
                 out.append(self._ids(t))
@@ -312,9 +360,21 @@ class KGAT(nn.Module):
 
     def _calc_kg_loss(self, heads, relations, positive_tails, negative_tails) -> torch.Tensor:
         self._device()
-        params = [self._user_entity_embedding.weight, self._relation_embedding.weight, self._trans_matrix]
+        params = [self._emb_raw(), self._relation_embedding.weight, self._trans_matrix]
         if self._use_api_graphs(params):
             ids = self._ids_fast((heads, relations, positive_tails, negative_tails))
+            opt = self.__dict__.get("_kg_optimizer")
+            deferred = None
+            if self.kg_deferred_adam and opt is not None and params[0].shape[1] % 64 == 0:
+                deferred = opt.deferred
+                if deferred is None or deferred.param is not params[0] or deferred.window != self.kg_window:
+                    if deferred is not None:
+                        deferred.flush()
+                    deferred = opt.deferred = DeferredRows(opt, params[0], window=self.kg_window)
+                if not deferred.active and not (deferred.usable() and len({int(opt.state[p]["step"]) if opt.state[p] else 0 for p in params}) == 1):
+                    deferred = None  # no optimiser state yet (first step): the per-step sweep creates it
+            if deferred is None:
+                self._settle()
 
             def make_bodies():
                 reg = float(self._regularization_params[1])
@@ -330,21 +390,36 @@ class KGAT(nn.Module):
                 row_slot = torch.full((emb.shape[0],), -1, dtype=torch.int32, device=emb.device)
                 g_rows = torch.zeros(3 * b, emb.shape[1], dtype=torch.float32, device=emb.device)
                 prev_ids = torch.zeros(4, b, dtype=torch.int64, device=emb.device)
+                d = deferred
+                if d is not None:
+                    exp_avg, exp_avg_sq = d.state_tensors()
 
                 def body_fwd(st):
                     ops.transr_release_rows(g_dense, prev_ids.view(-1), row_slot)  # the previous batch's rows and slot claims
-                    ops.transr_step(emb, rel, w, st.ids[0], st.ids[1], st.ids[2], st.ids[3], reg, st.loss, None, st.scratch, row_slot, g_rows,
-                                    g_rel, g_w)
+                    if d is None:
+                        ops.transr_step(emb, rel, w, st.ids[0], st.ids[1], st.ids[2], st.ids[3], reg, st.loss, None, st.scratch, row_slot,
+                                        g_rows, g_rel, g_w)
+                    else:  # rows this batch reads first take the zero-gradient updates they were spared (csrc/adam.cu, rolling window)
+                        ops.adam_rolling_prepare(st.ids[0], st.ids[2], st.ids[3], row_slot, g_rows, g_rel, g_w, emb, exp_avg, exp_avg_sq,
+                                                 d.row_step, d.step_dev, d.s0, d.table, d.hyper)
+                        ops.transr_step_claimed(emb, rel, w, st.ids[0], st.ids[1], st.ids[2], st.ids[3], reg, st.loss, None, st.scratch,
+                                                row_slot, g_rows, g_rel, g_w)
 
                 def body_bwd(st):
                     ops.transr_rows_to_dense(g_rows, row_slot, st.ids[0], st.ids[2], st.ids[3], g_dense)
                     prev_ids.copy_(st.ids)
                     st.adam_grads, st.adam_row_slot0 = [g_rows, g_rel, g_w], row_slot
+                    if d is not None:
+                        st.adam_rolling = dict(deferred=d, ids=(st.ids[0], st.ids[2], st.ids[3]), row_slot=row_slot)
                     return [g_dense, g_rel, g_w]
                 return body_fwd, body_bwd
 
-            step = self._api_step("kg", ids[0].numel(), params, None, 4, make_bodies)
+            key = None if deferred is None else (id(deferred), deferred.state_tensors()[0].data_ptr())
+            if deferred is not None:
+                deferred.ensure_phase()
+            step = self._api_step("kg", ids[0].numel(), params, key, 4, make_bodies)
             return step.submit(ids)
+        self._settle()
         return KGLossFunction.apply(
             self._ids(heads), self._ids(relations), self._ids(positive_tails), self._ids(negative_tails),
             float(self._regularization_params[1]), self._user_entity_embedding.weight, self._relation_embedding.weight,
@@ -457,12 +532,15 @@ class KGAT(nn.Module):
     def forward(self, *args: Any, mode: KGATMode) -> torch.Tensor | None:  # noqa: ANN401
         match mode:
             case KGATMode.TRAIN_CF:
+                self._settle()
                 return self._calc_cf_loss(*args)
             case KGATMode.TRAIN_KG:
                 return self._calc_kg_loss(*args)
             case KGATMode.UPDATE_ATTENTION:
+                self._settle()
                 self._update_attention(*args)
                 return None
             case KGATMode.PREDICT:
+                self._settle()
                 return self._calc_score(*args)
         raise ValueError(f"unknown mode {mode!r}")

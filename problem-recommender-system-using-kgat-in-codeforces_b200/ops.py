@@ -19,7 +19,9 @@ f32, i32, i64, u8 = torch.float32, torch.int32, torch.int64, torch.uint8
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of torch's current stream on the current device (two C calls; ``torch.cuda.current_stream()`` builds a Stream
+    object through several layers of Python and costs ~10 us, more than some of the launches it serves)."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 class KernelTimer:
@@ -173,6 +175,17 @@ def select_batch(src: torch.Tensor, counter_dev: torch.Tensor, dst: torch.Tensor
         raise KgatLibraryError("select_batch: dst size mismatch")
     check(lib.kgat_select_batch_i64(_ptr(src, i64), n_batches, elems, _ptr(counter_dev, i64), _ptr(dst, i64), _stream()), "select_batch")
     return dst
+
+
+def step_begin(src: torch.Tensor, step_dev: torch.Tensor, dst: torch.Tensor, lr, beta1, beta2, eps, hyper: torch.Tensor):
+    """``select_batch`` + ``adam_advance`` on the same counter in one launch: dst = src[step % n_batches], then step += 1 and
+    ``hyper`` holds the new step's Adam scalars."""
+    lib = _lib.load()
+    elems = src[0].numel()
+    if dst.numel() != elems:
+        raise KgatLibraryError("step_begin: dst size mismatch")
+    check(lib.kgat_step_begin_i64(_ptr(src, i64), src.shape[0], elems, _ptr(step_dev, i64), _ptr(dst, i64), float(lr), float(beta1), float(beta2),
+                                  float(eps), _ptr(hyper, f32), _stream()), "step_begin")
 
 
 def fill_(t: torch.Tensor, value: float = 0.0):
@@ -695,7 +708,8 @@ def adam_apply(params, grads, exp_avgs, exp_avg_sqs, hyper: torch.Tensor, peer_p
 
 
 @_timed("adam_rolling_prepare")
-def adam_rolling_prepare(heads, pos_t, neg_t, row_slot, g_rows, zero_a, zero_b, param, exp_avg, exp_avg_sq, row_step, cur_step_dev, s0, table, hyper):
+def adam_rolling_prepare(heads, pos_t, neg_t, row_slot, g_rows, zero_a, zero_b, param, exp_avg, exp_avg_sq, row_step, cur_step_dev, s0, table, hyper,
+                         advanced: bool = False):
     """Rolling-window KG Adam, before the forward: claim compact gradient rows, zero ``g_rows`` / ``zero_a`` / ``zero_b``, bring
     the batch rows of ``param`` up to the steps done so far."""
     lib = _lib.load()
@@ -705,7 +719,7 @@ def adam_rolling_prepare(heads, pos_t, neg_t, row_slot, g_rows, zero_a, zero_b, 
                                         _ptr(g_rows, f32), _ptr(zero_a, f32) if zero_a is not None else None, zero_a.numel() if zero_a is not None else 0,
                                         _ptr(zero_b, f32) if zero_b is not None else None, zero_b.numel() if zero_b is not None else 0,
                                         _ptr(param, f32), _ptr(exp_avg, f32), _ptr(exp_avg_sq, f32), _ptr(row_step, i32), _ptr(cur_step_dev, i64),
-                                        _ptr(s0, i64), _ptr(table, f32), _ptr(hyper, f32), _stream()), "adam_rolling_prepare")
+                                        int(bool(advanced)), _ptr(s0, i64), _ptr(table, f32), _ptr(hyper, f32), _stream()), "adam_rolling_prepare")
 
 
 @_timed("transr_step_claimed")
@@ -722,7 +736,7 @@ def transr_step_claimed(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, loss, l
 
 @_timed("adam_rolling_apply")
 def adam_rolling_apply(heads, pos_t, neg_t, row_slot, g_rows, param, exp_avg, exp_avg_sq, row_step, window, dense_params, dense_grads,
-                       dense_exp_avgs, dense_exp_avg_sqs, cur_step_dev, s0, table, hyper):
+                       dense_exp_avgs, dense_exp_avg_sqs, cur_step_dev, s0, table, hyper, parts: int = 3):
     """Rolling-window KG Adam, after ``adam_advance``: claimed rows take their gradient, the small dense tensors a plain step, and the
     window's current slice of ``param`` is replayed (zero-gradient updates) to the previous step."""
     lib = _lib.load()
@@ -741,8 +755,18 @@ def adam_rolling_apply(heads, pos_t, neg_t, row_slot, g_rows, param, exp_avg, ex
         t.numel[j] = dense_params[j].numel()
     check(lib.kgat_adam_rolling_apply(_ptr(heads, i64), _ptr(pos_t, i64), _ptr(neg_t, i64), heads.numel(), param.shape[1], _ptr(row_slot, i32),
                                       _ptr(g_rows, f32), _ptr(param, f32), _ptr(exp_avg, f32), _ptr(exp_avg_sq, f32), _ptr(row_step, i32),
-                                      param.shape[0], int(window), C.byref(t), _ptr(cur_step_dev, i64), _ptr(s0, i64), _ptr(table, f32),
+                                      param.shape[0], int(window), C.byref(t), int(parts), _ptr(cur_step_dev, i64), _ptr(s0, i64), _ptr(table, f32),
                                       _ptr(hyper, f32), _stream()), "adam_rolling_apply")
+
+
+def selftest_adam_arith(m, v, inv_sqrt_bc2: float, eps: float):
+    """(mismatches vs the IEEE builtins, elements on the fast sequences) for q = m / (sqrt(v) * inv_sqrt_bc2 + eps)."""
+    lib = _lib.load()
+    counts = torch.zeros(2, dtype=torch.int32, device=m.device)
+    check(lib.kgat_selftest_adam_arith(_ptr(m, f32), _ptr(v, f32), m.numel(), float(inv_sqrt_bc2), float(eps), _ptr(counts, i32), _stream()),
+          "selftest_adam_arith")
+    c = counts.tolist()
+    return c[0], c[1]
 
 
 def adam_hyper_table(s0_dev: torch.Tensor, n_steps: int, lr, beta1, beta2, table: torch.Tensor):

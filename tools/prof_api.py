@@ -34,13 +34,13 @@ for _ in range(2):
 torch.cuda.synchronize()
 for name, kw in (("kg", dict(n_cf=0, n_kg=args.kg)), ("cf", dict(n_cf=args.cf, n_kg=0))):
     t0 = time.perf_counter()
-    run_epoch(model, data, refresh=False, **kw)
+    run_epoch(model, data, refresh=False, read_loss_every_step=True, **kw)
     torch.cuda.synchronize()
     n = args.kg if name == "kg" else args.cf
     print(f"{name}: {1e6 * (time.perf_counter() - t0) / n:.1f} us/step wall (unprofiled)")
     pr = cProfile.Profile()
     pr.enable()
-    run_epoch(model, data, refresh=False, **kw)
+    run_epoch(model, data, refresh=False, read_loss_every_step=True, **kw)
     torch.cuda.synchronize()
     pr.disable()
     pstats.Stats(pr).sort_stats("tottime").print_stats(args.top)
