@@ -32,7 +32,7 @@ extern "C" {
 #define KGAT_ERR_UNSUPPORTED (-3)
 #define KGAT_ERR_WORKSPACE (-4)
 
-#define KGAT_ABI_VERSION 6
+#define KGAT_ABI_VERSION 7
 #define KGAT_MAX_LAYERS 8   /* embedding table + up to 7 propagation layers */
 #define KGAT_MAX_TENSORS 24 /* tensors per multi-tensor Adam launch */
 #define KGAT_MAX_PEERS 31   /* other ranks of a row-sharded propagation */
@@ -234,9 +234,9 @@ typedef struct {
 
 /* loss[0] = -mean(logsigmoid(pos - neg)) + reg * (mean|u|^2/2 + mean|p|^2/2 + mean|n|^2/2);
  * margin: scratch of 2*batch floats: [pos_b - neg_b (saved for the backward)][per-sample l2 term].
- * ids are used as given (no user offset). */
+ * ids are used as given (no user offset).  loss_sum (may be NULL): loss_sum[0] += loss[0] in the same launch. */
 int kgat_bpr_forward(const kgat_tables_t* tables, const int64_t* users, const int64_t* pos, const int64_t* neg,
-                     int32_t batch, float reg, float* loss, float* margin, void* stream);
+                     int32_t batch, float reg, float* loss, float* loss_sum, float* margin, void* stream);
 /* Scatter-adds d loss / d table rows into grad tables (atomicAdd; tables[l] may be NULL to skip a
  * layer).  g_loss: device scalar (upstream gradient). */
 int kgat_bpr_backward(const kgat_tables_t* tables, const kgat_grad_tables_t* grads, const int64_t* users,

@@ -13,7 +13,7 @@ from pathlib import Path
 
 KGAT_MAX_LAYERS = 8
 KGAT_MAX_TENSORS = 24
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("KGAT_B200_LIB", _PKG_DIR / "lib" / "libkgat_b200.so"))
@@ -99,7 +99,7 @@ SIGNATURES: dict[str, tuple] = {
     "kgat_zero_rows_i64": (_I32, [_P, _I64, _I64, _I32, _P, _I64, _P]),
     "kgat_transr_rows_to_dense": (_I32, [_P, _P, _P, _P, _P, _I32, _I32, _P, _I64, _P]),
     "kgat_transr_release_rows": (_I32, [_P, _I64, _I64, _I32, _P, _I64, _P, _P]),
-    "kgat_bpr_forward": (_I32, [C.POINTER(TablesT), _P, _P, _P, _I32, _F, _P, _P, _P]),
+    "kgat_bpr_forward": (_I32, [C.POINTER(TablesT), _P, _P, _P, _I32, _F, _P, _P, _P, _P]),
     "kgat_bpr_backward": (_I32, [C.POINTER(TablesT), C.POINTER(TablesT), _P, _P, _P, _I32, _F, _P, _P, _P]),
     "kgat_transr_forward": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P, _P, _I32, _F, _P, _P, _P]),
     "kgat_transr_backward": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P, _P, _I32, _F, _P, _P, _P, _P, _P, _P, _P]),

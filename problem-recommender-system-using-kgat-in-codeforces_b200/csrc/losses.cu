@@ -406,14 +406,14 @@ int kgat_zero_rows_i64(float* T, int64_t n_rows, int64_t ld, int32_t d, const in
 }
 
 int kgat_bpr_forward(const kgat_tables_t* tables, const int64_t* users, const int64_t* pos, const int64_t* neg, int32_t batch,
-                     float reg, float* loss, float* margin, void* stream_) {
+                     float reg, float* loss, float* loss_sum, float* margin, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     Tables T;
     int rc = pack_tables(tables, &T);
     if (rc != KGAT_OK) return rc;
     if (batch <= 0) return KGAT_ERR_INVALID_ARGUMENT;
     bpr_fwd_kernel<<<(batch * 32 + 255) / 256, 256, 0, stream>>>(T, users, pos, neg, batch, margin);
-    loss_reduce_kernel<<<1, 256, 0, stream>>>(margin, batch, reg, loss);
+    loss_reduce_kernel<<<1, 256, 0, stream>>>(margin, batch, reg, loss, loss_sum);
     return check_launch();
 }
 

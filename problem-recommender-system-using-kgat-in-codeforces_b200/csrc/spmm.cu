@@ -182,8 +182,8 @@ __global__ void __launch_bounds__(128) spmm_task_kernel(const int4* __restrict__
 // a row outside the frontier -- the grid-per-task kernel spends ~30 us on 40 k empty CTAs when 3 % of the rows are live --
 // and the edge bitmap is staged in shared memory once per CTA when it fits, so the per-edge test is an LDS.
 constexpr int kRowsThreads = 256;
-template <int D, int U, bool WIDE>
-__global__ void __launch_bounds__(kRowsThreads, 5) spmm_rows_kernel(const int4* __restrict__ tasks, int n_tasks, int n_heavy_tasks,
+template <int D, int U, bool WIDE, bool MASKED, int CTAS>
+__global__ void __launch_bounds__(kRowsThreads, CTAS) spmm_rows_kernel(const int4* __restrict__ tasks, int n_tasks, int n_heavy_tasks,
                                                                 const int32_t* __restrict__ light_rank, const int32_t* __restrict__ rows,
                                                                 const int32_t* __restrict__ n_rows_dev, const int32_t* __restrict__ col_idx,
                                                                 const float* __restrict__ vals, const float* __restrict__ X, int64_t ldx,
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kRowsThreads, 5) spmm_rows_kernel(const int4* 
     extern __shared__ __align__(16) uint32_t smem_mask[];
     __shared__ int2 ebuf[kRowsThreads / 32][32];
     const uint32_t* emask = edge_mask;
-    if (edge_mask != nullptr && mask_words_smem > 0) {
+    if (MASKED && mask_words_smem > 0) {
         for (int i = threadIdx.x; i < mask_words_smem; i += kRowsThreads) smem_mask[i] = __ldg(edge_mask + i);
         __syncthreads();
         emask = smem_mask;
@@ -213,12 +213,8 @@ __global__ void __launch_bounds__(kRowsThreads, 5) spmm_rows_kernel(const int4* 
             if (lr < 0) continue;  // a heavy row: its chunks were taken above
             t = __ldg(tasks + n_heavy_tasks + lr);
         }
-        if (edge_mask != nullptr)
-            spmm_do_task<D, U, WIDE, true>(t, ebuf[threadIdx.x >> 5], col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, heavy, n_heavy, emask,
-                                           edge_mask);
-        else
-            spmm_do_task<D, U, WIDE, false>(t, ebuf[threadIdx.x >> 5], col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, heavy, n_heavy, nullptr,
-                                            nullptr);
+        spmm_do_task<D, U, WIDE, MASKED>(t, ebuf[threadIdx.x >> 5], col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, heavy, n_heavy,
+                                         MASKED ? emask : nullptr, MASKED ? edge_mask : nullptr);
     }
 }
 
@@ -345,14 +341,28 @@ __global__ void __launch_bounds__(128) spmm_heavy_reduce_kernel(const int4* __re
 
 using namespace kgat;
 
-// loads in flight per lane for d = 64 (KGAT_SPMM_U = 4 | 8; A/B switch for the profiling runs)
-static int spmm_unroll64() {
-    static int u = 0;
-    if (u == 0) {
-        const char* e = getenv("KGAT_SPMM_U");
-        u = (e != nullptr && atoi(e) == 8) ? 8 : 4;
+// CTAs per SM of the unmasked row-list kernel (KGAT_SPMM_CTAS = 5 | 6; A/B switch)
+static int spmm_plain_ctas() {
+    static int c = 0;
+    if (c == 0) {
+        const char* e = getenv("KGAT_SPMM_CTAS");
+        c = (e != nullptr && atoi(e) == 6) ? 6 : 5;  // 6 CTAs (40 registers) spills and measured 2 % slower
     }
-    return u;
+    return c;
+}
+
+// loads in flight per lane for d = 64 (KGAT_SPMM_U = 4 | 8 forces one depth everywhere; A/B switch for the profiling runs).
+// Default: 8 for the edge-masked instance (backward over all rows: 126 -> 122 us), 4 for the plain ones -- the staged batch is
+// padded to a whole unrolled step (2 x depth edges) with zero-weight gathers, which on ~30-edge rows costs the plain forward
+// instance more than the deeper queue buys (102 -> 125 us at depth 8).
+static int spmm_unroll64(bool edge_masked) {
+    static int u = -1;
+    if (u < 0) {
+        const char* e = getenv("KGAT_SPMM_U");
+        u = e != nullptr ? atoi(e) : 0;
+    }
+    if (u == 4 || u == 8) return u;
+    return edge_masked ? 8 : 4;
 }
 
 static int spmm_launch(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_rows, int64_t n_heavy, const int32_t* col_idx,
@@ -387,7 +397,7 @@ static int spmm_launch(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_row
         case 16: KGAT_SPMM_LAUNCH(16, 2); break;
         case 32: KGAT_SPMM_LAUNCH(32, 4); break;
         case 64:
-            if (spmm_unroll64() == 8) KGAT_SPMM_LAUNCH(64, 8);
+            if (spmm_unroll64(edge_mask != nullptr) == 8) KGAT_SPMM_LAUNCH(64, 8);
             else KGAT_SPMM_LAUNCH(64, 4);
             break;
         case 128: KGAT_SPMM_LAUNCH(128, 4); break;
@@ -441,22 +451,32 @@ extern "C" int kgat_spmm_csr_rows(const int32_t* tasks, int64_t n_tasks, int64_t
         if (words > 0 && words * 4 <= 32 * 1024) mask_words = (int)words;  // 1 M nodes: a 32 KB bitmap per CTA still leaves 6 CTAs / SM
     }
     const size_t smem = (size_t)mask_words * 4;
-    const int ctas_per_sm = 5;  // 44-46 registers x 256 threads; 5 x (32 KB bitmap + 2 KB slabs) of shared memory fit as well
-    const unsigned blocks = (unsigned)(sm_count() * ctas_per_sm);
+    // edge-masked (backward) instance: 48 registers x 256 threads -> 5 CTAs / SM (5 x (32 KB bitmap + 2 KB slabs) of shared memory
+    // fit as well); the unmasked (forward) instance is compiled on its own and runs kCtasPlain CTAs / SM
+    const bool em = edge_mask != nullptr;
+    const unsigned blocks = (unsigned)(sm_count() * (em ? 5 : spmm_plain_ctas()));
     const int4* t4 = reinterpret_cast<const int4*>(tasks);
     int4* h4 = reinterpret_cast<int4*>(heavy_rows);
 #define KGAT_ROWS_ARGS t4, (int)n_tasks, (int)n_heavy_tasks, light_rank, rows, n_rows_dev, col_idx, vals, X, ldx, Y, ldy, Z, ldz, partials, h4, \
                        (int)n_heavy, row_mask, edge_mask, mask_words
-#define KGAT_ROWS_LAUNCH(DD, UU)                                                                                  \
-    do {                                                                                                          \
-        if (use_wide) spmm_rows_kernel<DD, UU, true><<<blocks, kRowsThreads, smem, stream>>>(KGAT_ROWS_ARGS);      \
-        else spmm_rows_kernel<DD, UU, false><<<blocks, kRowsThreads, smem, stream>>>(KGAT_ROWS_ARGS);              \
+#define KGAT_ROWS_LAUNCH(DD, UU)                                                                                           \
+    do {                                                                                                                   \
+        if (em) {                                                                                                          \
+            if (use_wide) spmm_rows_kernel<DD, UU, true, true, 5><<<blocks, kRowsThreads, smem, stream>>>(KGAT_ROWS_ARGS);  \
+            else spmm_rows_kernel<DD, UU, false, true, 5><<<blocks, kRowsThreads, smem, stream>>>(KGAT_ROWS_ARGS);          \
+        } else if (spmm_plain_ctas() == 6) {                                                                               \
+            if (use_wide) spmm_rows_kernel<DD, UU, true, false, 6><<<blocks, kRowsThreads, smem, stream>>>(KGAT_ROWS_ARGS); \
+            else spmm_rows_kernel<DD, UU, false, false, 6><<<blocks, kRowsThreads, smem, stream>>>(KGAT_ROWS_ARGS);         \
+        } else {                                                                                                           \
+            if (use_wide) spmm_rows_kernel<DD, UU, true, false, 5><<<blocks, kRowsThreads, smem, stream>>>(KGAT_ROWS_ARGS); \
+            else spmm_rows_kernel<DD, UU, false, false, 5><<<blocks, kRowsThreads, smem, stream>>>(KGAT_ROWS_ARGS);         \
+        }                                                                                                                  \
     } while (0)
     switch (d) {
         case 16: KGAT_ROWS_LAUNCH(16, 2); break;
         case 32: KGAT_ROWS_LAUNCH(32, 4); break;
         case 64:
-            if (spmm_unroll64() == 8) KGAT_ROWS_LAUNCH(64, 8);
+            if (spmm_unroll64(em) == 8) KGAT_ROWS_LAUNCH(64, 8);
             else KGAT_ROWS_LAUNCH(64, 4);
             break;
         default: KGAT_ROWS_LAUNCH(128, 4); break;

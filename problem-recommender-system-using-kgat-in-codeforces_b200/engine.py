@@ -50,8 +50,9 @@ class _AdamSlot:
         self.exp_avg = [opt.state[p]["exp_avg"] for p in self.params]
         self.exp_avg_sq = [opt.state[p]["exp_avg_sq"] for p in self.params]
 
-    def apply(self, grads, row_slot0=None):
-        ops.adam_advance(self.step_dev, self.lr, self.b1, self.b2, self.eps, self.hyper)
+    def apply(self, grads, row_slot0=None, advance: bool = True):
+        if advance:  # (False: the step counter and scalars were advanced with the batch selection, ops.step_begin)
+            ops.adam_advance(self.step_dev, self.lr, self.b1, self.b2, self.eps, self.hyper)
         ops.adam_apply([p.data for p in self.params], grads, self.exp_avg, self.exp_avg_sq, self.hyper, row_slot0=row_slot0)
 
     def resync(self) -> bool:
@@ -151,10 +152,13 @@ class TrainEngine:
     # ------------------------------------------------------------------------------------------
     def _cf_body(self, select: bool):
         m = self.model
+        begun = False
         if select and self.device_sampler is not None:
             self.device_sampler.cf_batch(self.cf_adam.step_dev, self.cf_ids)
-        elif select:
-            ops.select_batch(self._resident.cf, self.cf_adam.step_dev, self.cf_ids.view(-1))
+        elif select:  # batch selection + the optimiser's step counter / scalars in one launch
+            ad = self.cf_adam
+            ops.step_begin(self._resident.cf, ad.step_dev, self.cf_ids.view(-1), ad.lr, ad.b1, ad.b2, ad.eps, ad.hyper)
+            begun = True
         u, p, n = self.cf_ids[0], self.cf_ids[1], self.cf_ids[2]
         graph = m._graph()
         layers = [tuple(t.detach() for t in grp) for grp in m._layers()]
@@ -167,7 +171,7 @@ class TrainEngine:
             frontier.build([self.cf_ids.view(-1)])
         st = propagate_forward(graph, m._user_entity_embedding.weight.detach(), layers, drop, save=True, frontier=frontier)
         reg = float(m._regularization_params[0])
-        ops.bpr_forward(st.tables, u, p, n, reg, self.cf_loss, self.cf_scratch)
+        ops.bpr_forward(st.tables, u, p, n, reg, self.cf_loss, self.cf_scratch, loss_sum=self.cf_loss_sum)
         n_tab = len(st.tables)
 
         def inject(l, buf):
@@ -178,8 +182,7 @@ class TrainEngine:
         g_last = last_table_grad(st, frontier)
         inject(n_tab - 1, g_last)
         g_e0, pgrads = propagate_backward(graph, st, layers, g_last, inject, frontier=frontier)
-        self.cf_adam.apply([g_e0] + [t for grp in pgrads for t in grp])
-        self.cf_loss_sum.add_(self.cf_loss)
+        self.cf_adam.apply([g_e0] + [t for grp in pgrads for t in grp], advance=not begun)
 
     def _kg_body(self, select: bool):
         m = self.model

@@ -425,7 +425,7 @@ def zero_rows_(table: torch.Tensor, ids: torch.Tensor):
 
 
 @_timed("bpr_fwd")
-def bpr_forward(tables, users, pos, neg, reg, loss, scratch):
+def bpr_forward(tables, users, pos, neg, reg, loss, scratch, loss_sum=None):
     lib = _lib.load()
     b = users.numel()
     if scratch.numel() < 2 * b:
@@ -433,7 +433,7 @@ def bpr_forward(tables, users, pos, neg, reg, loss, scratch):
     t = _tables(tables)
     check(
         lib.kgat_bpr_forward(C.byref(t), _ptr(users, i64, "users"), _ptr(pos, i64, "pos"), _ptr(neg, i64, "neg"), b, float(reg),
-                             _ptr(loss, f32), _ptr(scratch, f32), _stream()),
+                             _ptr(loss, f32), _ptr(loss_sum, f32) if loss_sum is not None else None, _ptr(scratch, f32), _stream()),
         "bpr_forward",
     )
 
