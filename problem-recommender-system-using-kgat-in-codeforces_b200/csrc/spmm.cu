@@ -351,18 +351,16 @@ static int spmm_plain_ctas() {
     return c;
 }
 
-// loads in flight per lane for d = 64 (KGAT_SPMM_U = 4 | 8 forces one depth everywhere; A/B switch for the profiling runs).
-// Default: 8 for the edge-masked instance (backward over all rows: 126 -> 122 us), 4 for the plain ones -- the staged batch is
-// padded to a whole unrolled step (2 x depth edges) with zero-weight gathers, which on ~30-edge rows costs the plain forward
-// instance more than the deeper queue buys (102 -> 125 us at depth 8).
-static int spmm_unroll64(bool edge_masked) {
-    static int u = -1;
-    if (u < 0) {
+// loads in flight per lane for d = 64 (KGAT_SPMM_U = 4 | 8; A/B switch for the profiling runs).  Measured on captured CF steps
+// (tools/prof_cf.py, same box): depth 8 everywhere 647 us, depth 8 for the edge-masked instance only 658 us, depth 4 everywhere
+// 663 us.  (Per-kernel eager timings suggested the opposite for the plain forward instance; the captured step is what counts.)
+static int spmm_unroll64(bool /*edge_masked*/) {
+    static int u = 0;
+    if (u == 0) {
         const char* e = getenv("KGAT_SPMM_U");
-        u = e != nullptr ? atoi(e) : 0;
+        u = (e != nullptr && atoi(e) == 4) ? 4 : 8;
     }
-    if (u == 4 || u == 8) return u;
-    return edge_masked ? 8 : 4;
+    return u;
 }
 
 static int spmm_launch(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_rows, int64_t n_heavy, const int32_t* col_idx,
