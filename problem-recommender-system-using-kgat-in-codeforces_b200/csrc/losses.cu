@@ -127,9 +127,37 @@ int pack_tables(const kgat_tables_t* t, Tables* out) {
 // ---------------------------------------------------------------------------------------------
 // TransR:  x = e W_r  (row-vector convention).  One CTA of 4 warps per sample: the kernels are latency
 // bound (512 samples, a 64-step dependent mat-vec each), so the rows j of W_r are split over the 4 warps
-// and the partial projections are combined through shared memory.  Lane owns output columns lane + 32 m.
+// and the partial projections are combined through shared memory.  Lane owns the KM consecutive output columns from KM * lane (ld_cols / red_cols).
 // ---------------------------------------------------------------------------------------------
 constexpr int kTrWarps = 4;
+
+// A lane owns the KM CONSECUTIVE output columns [KM lane, KM lane + KM): its slice of a row of W_r / e_r is one 4 KM-byte load
+// and its slice of a gradient row ONE vector reduction (red.global.add.v2/.v4.f32) -- the W_r gradient is 2.1 M scalar float
+// atomics per 512-sample batch otherwise, which is what bounds the kernel.
+template <int KM>
+__device__ __forceinline__ void ld_cols(const float* __restrict__ p, int lane, float (&x)[KM]) {
+    if constexpr (KM == 1) {
+        x[0] = __ldg(p + lane);
+    } else if constexpr (KM == 2) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(p) + lane);
+        x[0] = v.x; x[1] = v.y;
+    } else {
+        static_assert(KM == 4, "KM is 1, 2 or 4");
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p) + lane);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    }
+}
+template <int KM>
+__device__ __forceinline__ void red_cols(float* __restrict__ p, int lane, const float (&x)[KM]) {
+    if constexpr (KM == 1) {
+        atomicAdd(p + lane, x[0]);
+    } else if constexpr (KM == 2) {
+        asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p + 2 * lane), "f"(x[0]), "f"(x[1]) : "memory");
+    } else {
+        asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + 4 * lane), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3])
+                     : "memory");
+    }
+}
 
 // partial projections of (e_h, e_p, e_n) over this warp's rows [j0, j0 + JW) of W_r
 template <int D, int KM>
@@ -152,13 +180,13 @@ __device__ __forceinline__ void transr_partial(const float* __restrict__ Wr, con
         const float a = __shfl_sync(kFull, eh, jj);
         const float b = __shfl_sync(kFull, ep, jj);
         const float c = __shfl_sync(kFull, en, jj);
-        const float* wrow = Wr + (j0 + jj) * K + lane;
+        float w[KM];
+        ld_cols<KM>(Wr + (j0 + jj) * K, lane, w);
 #pragma unroll
         for (int m = 0; m < KM; ++m) {
-            const float w = __ldg(wrow + 32 * m);
-            xh[m] = fmaf(a, w, xh[m]);
-            xp[m] = fmaf(b, w, xp[m]);
-            xn[m] = fmaf(c, w, xn[m]);
+            xh[m] = fmaf(a, w[m], xh[m]);
+            xp[m] = fmaf(b, w[m], xp[m]);
+            xn[m] = fmaf(c, w[m], xn[m]);
         }
     }
 }
@@ -204,14 +232,15 @@ __global__ void __launch_bounds__(128) transr_fwd_kernel(const float* __restrict
     transr_combine<KM>(part, warp, lane, xh, xp, xn);
     if (warp != 0) return;
     float ps = 0.f, ns = 0.f, l2 = 0.f;
+    float er[KM];
+    ld_cols<KM>(rel_emb + r * K, lane, er);
 #pragma unroll
     for (int m = 0; m < KM; ++m) {
-        const float er = __ldg(rel_emb + r * K + lane + 32 * m);
-        const float dp = xh[m] + er - xp[m];
-        const float dn = xh[m] + er - xn[m];
+        const float dp = xh[m] + er[m] - xp[m];
+        const float dn = xh[m] + er[m] - xn[m];
         ps = fmaf(dp, dp, ps);
         ns = fmaf(dn, dn, ns);
-        l2 += xh[m] * xh[m] + er * er + xp[m] * xp[m] + xn[m] * xn[m];
+        l2 += xh[m] * xh[m] + er[m] * er[m] + xp[m] * xp[m] + xn[m] * xn[m];
     }
     ps = warp_sum(ps);
     ns = warp_sum(ns);
@@ -244,17 +273,18 @@ __global__ void __launch_bounds__(128) transr_bwd_kernel(const float* __restrict
     transr_partial<D, KM>(Wr, emb, h, p, n, warp, lane, eh, ep, en, xh, xp, xn);
     transr_combine<KM>(part, warp, lane, xh, xp, xn);
 
+    float er[KM];
+    ld_cols<KM>(rel_emb + r * K, lane, er);
     float margin;
     if (FUSED) {
         float ps = 0.f, ns = 0.f, l2 = 0.f;
 #pragma unroll
         for (int m = 0; m < KM; ++m) {
-            const float er = __ldg(rel_emb + r * K + lane + 32 * m);
-            const float dp = xh[m] + er - xp[m];
-            const float dn = xh[m] + er - xn[m];
+            const float dp = xh[m] + er[m] - xp[m];
+            const float dn = xh[m] + er[m] - xn[m];
             ps = fmaf(dp, dp, ps);
             ns = fmaf(dn, dn, ns);
-            l2 += xh[m] * xh[m] + er * er + xp[m] * xp[m] + xn[m] * xn[m];
+            l2 += xh[m] * xh[m] + er[m] * er[m] + xp[m] * xp[m] + xn[m] * xn[m];
         }
         ps = warp_sum(ps);
         ns = warp_sum(ns);
@@ -270,19 +300,19 @@ __global__ void __launch_bounds__(128) transr_bwd_kernel(const float* __restrict
     const float g = (FUSED ? 1.f : g_loss[0]) / (float)batch;
     const float s2 = 2.f * sigmoidf_(-margin) * g;  // loss = -logsigmoid(ns - ps)
     const float lam = reg * g;
-    float gxh[KM], gxp[KM], gxn[KM];
+    float gxh[KM], gxp[KM], gxn[KM], ger[KM];
 #pragma unroll
     for (int m = 0; m < KM; ++m) {
-        const float er = __ldg(rel_emb + r * K + lane + 32 * m);
-        const float dp = xh[m] + er - xp[m];
-        const float dn = xh[m] + er - xn[m];
+        const float dp = xh[m] + er[m] - xp[m];
+        const float dn = xh[m] + er[m] - xn[m];
         const float gdp = s2 * dp;   // dL/d dpos
         const float gdn = -s2 * dn;  // dL/d dneg
         gxh[m] = gdp + gdn + lam * xh[m];
         gxp[m] = -gdp + lam * xp[m];
         gxn[m] = -gdn + lam * xn[m];
-        if (warp == 0) atomicAdd(g_rel + r * K + lane + 32 * m, gdp + gdn + lam * er);
+        ger[m] = gdp + gdn + lam * er[m];
     }
+    if (warp == 0) red_cols<KM>(g_rel + r * K, lane, ger);
     // this warp's rows of W_r: d e[j] = <g_x, W_r[j, :]>, d W_r[j, :] += e[j] * g_x
     const int j0 = warp * JW;
     float* gWr = g_W + r * (int64_t)D * K;
@@ -294,14 +324,16 @@ __global__ void __launch_bounds__(128) transr_bwd_kernel(const float* __restrict
         const float bb = __shfl_sync(kFull, ep, jj);
         const float c = __shfl_sync(kFull, en, jj);
         float ph = 0.f, pp = 0.f, pn = 0.f;
+        float w[KM], gw[KM];
+        ld_cols<KM>(Wr + j * K, lane, w);
 #pragma unroll
         for (int m = 0; m < KM; ++m) {
-            const float w = __ldg(Wr + j * K + lane + 32 * m);
-            ph = fmaf(gxh[m], w, ph);
-            pp = fmaf(gxp[m], w, pp);
-            pn = fmaf(gxn[m], w, pn);
-            atomicAdd(gWr + j * K + lane + 32 * m, a * gxh[m] + bb * gxp[m] + c * gxn[m]);
+            ph = fmaf(gxh[m], w[m], ph);
+            pp = fmaf(gxp[m], w[m], pp);
+            pn = fmaf(gxn[m], w[m], pn);
+            gw[m] = a * gxh[m] + bb * gxp[m] + c * gxn[m];
         }
+        red_cols<KM>(gWr + j * K, lane, gw);
         ph = warp_sum(ph);
         pp = warp_sum(pp);
         pn = warp_sum(pn);
