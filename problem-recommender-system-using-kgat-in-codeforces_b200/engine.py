@@ -67,6 +67,11 @@ class _AdamSlot:
             self._host_step = step
         moved = any(self.opt.state[p]["exp_avg"].data_ptr() != m.data_ptr() or self.opt.state[p]["exp_avg_sq"].data_ptr() != v.data_ptr()
                     for p, m, v in zip(self.params, self.exp_avg, self.exp_avg_sq))
+        group = self.opt.param_groups[0]
+        if (group["lr"], tuple(group["betas"]), group["eps"]) != (self.lr, (self.b1, self.b2), self.eps):
+            # a scheduler / the user changed the optimiser's scalars: the captured steps bake them in as kernel arguments
+            self.lr, (self.b1, self.b2), self.eps = group["lr"], group["betas"], group["eps"]
+            moved = True
         if moved:
             self.exp_avg = [self.opt.state[p]["exp_avg"] for p in self.params]
             self.exp_avg_sq = [self.opt.state[p]["exp_avg_sq"] for p in self.params]

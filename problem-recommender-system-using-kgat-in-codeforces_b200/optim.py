@@ -32,6 +32,7 @@ class DeferredRows:
         self.active = False  # a phase is open: rows may lag behind step_dev
         self.phase_len = 0  # optimiser steps taken in the open phase
         self.host_step = -1  # optimiser step count (host) the device counter corresponds to
+        self.hyper_key = None  # (lr, betas, eps) the open phase's bias-correction table was built for
 
     def state_tensors(self):
         st = self.opt.state[self.param]
@@ -43,11 +44,13 @@ class DeferredRows:
 
     def ensure_phase(self) -> None:
         """Open a phase at the optimiser's current step (no-op while one is open, in sync and has table entries left)."""
-        if self.active and self.phase_len < self.capacity - 2:
+        group = self.opt.param_groups[0]
+        hyper_key = (group["lr"], group["betas"], group["eps"])
+        if self.active and self.phase_len < self.capacity - 2 and hyper_key == self.hyper_key:
             return  # (that the optimiser has not moved under the open phase is checked where it matters: FusedAdam.fast_plan)
         cur = int(self.opt.state[self.param]["step"])
-        self.flush()
-        group = self.opt.param_groups[0]
+        self.flush()  # (with the scalars the open phase was built for: a changed lr / betas / eps only applies from here on)
+        self.hyper_key = hyper_key
         b1, b2 = group["betas"]
         self.step_dev.fill_(cur)
         self.s0.fill_(cur)
