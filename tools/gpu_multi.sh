@@ -1,4 +1,4 @@
-# usage: bash tools/r2_run_n.sh N [check]
+# usage: bash tools/gpu_multi.sh N [check]
 N=$1
 cd /root/repo; mkdir -p gpurun_out
 if [ "$2" = "check" ]; then
