@@ -137,6 +137,7 @@ class KGAT(nn.Module):
         self.api_graphs = True
         self._api_steps: dict = {}
         self._last_step: dict = {}
+        self._kg_fast = None  # closure re-submitting the last TRAIN_KG step after re-checking everything that can change between calls
         # TRAIN_CF computes every layer only for the rows the batch can reach (frontier.py): exact, ~2x less work at the
         # Amazon-book shape.  False = the reference's literal full-graph propagation per batch.
         self.cf_pruning = True
@@ -214,6 +215,7 @@ class KGAT(nn.Module):
         self._table_cache = self._table_key = None
         self._api_steps = {}
         self._last_step = {}
+        self._kg_fast = None
         self._frontiers = {}
 
     def _frontier(self, graph: AttentiveGraph, n_ids: int, fresh: bool = False) -> Frontier | None:
@@ -285,8 +287,12 @@ class KGAT(nn.Module):
     # A5 / A6: losses
     # ------------------------------------------------------------------------------------------
     def _use_api_graphs(self, params) -> bool:
-        return (self.api_graphs and torch.is_grad_enabled() and all(p.requires_grad for p in params)
-                and self._injected_message_keep_bits is None and not torch.cuda.is_current_stream_capturing())
+        if not (self.api_graphs and self._injected_message_keep_bits is None and torch.is_grad_enabled()):
+            return False
+        for p in params:
+            if not p.requires_grad:
+                return False
+        return not torch._C._cuda_isCurrentStreamCapturing()
 
     def _api_step(self, kind: str, batch: int, params, extra_key, n_ids, make_bodies) -> GraphedStep:
         key = (kind, batch, self.training, tuple(p.data_ptr() for p in params), extra_key)
@@ -358,7 +364,47 @@ class KGAT(nn.Module):
             self._frontier(graph, u.numel() + p.numel() + n.numel()), self._user_entity_embedding.weight, *flat,
         )
 
+    def _make_kg_fast(self, step: GraphedStep, params, opt, deferred):
+        """The steady state of a KG phase: the same step object is re-submitted ~12 k times per epoch and the host is the
+        bottleneck (a KG step is ~40 us of GPU work), so everything ``_calc_kg_loss`` decides is decided once and this closure only
+        re-checks, with identity / integer comparisons, what can change between two calls.  Returns None to fall back."""
+        emb, rel, w = params
+        emb_mod, rel_mod, own = self._user_entity_embedding._parameters, self._relation_embedding._parameters, self._parameters
+        ptrs = (emb.data_ptr(), rel.data_ptr(), w.data_ptr())
+        training, want_deferred, window, batch = self.training, self.kg_deferred_adam, self.kg_window, step._batch
+        state_version = opt.state_version if opt is not None else 0
+        int64, Tensor, capturing, grad_enabled = torch.int64, torch.Tensor, torch._C._cuda_isCurrentStreamCapturing, torch.is_grad_enabled
+        last_step = self._last_step
+
+        def fast(h, r, pt, nt):
+            if not (self.api_graphs and self.training is training and self.kg_deferred_adam is want_deferred and self.kg_window == window
+                    and self._injected_message_keep_bits is None and grad_enabled()):
+                return None
+            if emb_mod["weight"] is not emb or rel_mod["weight"] is not rel or own["_trans_matrix"] is not w:
+                return None
+            if (emb.data_ptr(), rel.data_ptr(), w.data_ptr()) != ptrs or not (emb.requires_grad and rel.requires_grad and w.requires_grad):
+                return None
+            if self.__dict__.get("_kg_optimizer") is not opt or (opt is not None and (opt.deferred is not deferred or opt.state_version != state_version)):
+                return None
+            for t in (h, r, pt, nt):
+                if type(t) is not Tensor or t.dtype is not int64 or not t.is_contiguous() or t.numel() != batch:
+                    return None
+            if capturing():
+                return None
+            if deferred is not None:
+                deferred.ensure_phase()
+            last_step["kg"] = step
+            return step.submit((h, r, pt, nt))
+
+        return fast
+
     def _calc_kg_loss(self, heads, relations, positive_tails, negative_tails) -> torch.Tensor:
+        fast = self._kg_fast
+        if fast is not None:
+            loss = fast(heads, relations, positive_tails, negative_tails)
+            if loss is not None:
+                return loss
+            self._kg_fast = None
         self._device()
         params = [self._emb_raw(), self._relation_embedding.weight, self._trans_matrix]
         if self._use_api_graphs(params):
@@ -418,6 +464,8 @@ class KGAT(nn.Module):
             if deferred is not None:
                 deferred.ensure_phase()
             step = self._api_step("kg", ids[0].numel(), params, key, 4, make_bodies)
+            if deferred is not None or not self.kg_deferred_adam or opt is None:  # (otherwise the next call may be able to defer: re-decide)
+                self._kg_fast = self._make_kg_fast(step, params, opt, deferred)
             return step.submit(ids)
         self._settle()
         return KGLossFunction.apply(

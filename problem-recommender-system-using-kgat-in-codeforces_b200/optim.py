@@ -76,6 +76,7 @@ class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, use_graphs: bool = True):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self.deferred: DeferredRows | None = None  # set by the model for its KG optimiser
+        self.state_version = 0  # bumped whenever the state tensors may have been replaced (load_state_dict)
         self._hyper: dict[int, torch.Tensor] = {}
         # When the same (parameter, gradient-buffer) set shows up step after step -- the model's API fast path hands
         # autograd static gradient buffers -- the whole update (bias-correction scalars from a device step counter +
@@ -135,6 +136,7 @@ class FusedAdam(torch.optim.Optimizer):
     def load_state_dict(self, state_dict):
         self.flush_deferred()
         self._fast.clear()
+        self.state_version += 1
         return super().load_state_dict(state_dict)
 
     def fast_plan(self, ps, grads, grads_key=None, row_slot0=None, rolling=None):
@@ -210,18 +212,19 @@ class FusedAdam(torch.optim.Optimizer):
         return plan
 
     def fast_replay(self, plan, ps) -> None:
-        from . import _lib
-        from ._lib import check
-
         rc = plan["launch"](plan["exec"], torch._C._cuda_getCurrentRawStream(plan["dev_index"]))
         if rc != 0:
+            from ._lib import check
+
             check(rc, "adam graph launch")
         plan["count"] += 1
         for st in plan["states"]:
             st["step"] += 1
-        if plan["deferred"] is not None:
-            plan["deferred"].stepped()
-        torch.autograd.graph.increment_version(ps)  # the kernel wrote through raw pointers: tell autograd the data changed
+        d = plan["deferred"]
+        if d is not None:
+            d.phase_len += 1
+            d.host_step += 1
+        torch._C._increment_version(ps)  # the kernel wrote through raw pointers: tell autograd the data changed
         for p in ps:
             p.grad = None
 
