@@ -32,7 +32,7 @@ extern "C" {
 #define KGAT_ERR_UNSUPPORTED (-3)
 #define KGAT_ERR_WORKSPACE (-4)
 
-#define KGAT_ABI_VERSION 7
+#define KGAT_ABI_VERSION 8
 #define KGAT_MAX_LAYERS 8   /* embedding table + up to 7 propagation layers */
 #define KGAT_MAX_TENSORS 24 /* tensors per multi-tensor Adam launch */
 #define KGAT_MAX_PEERS 31   /* other ranks of a row-sharded propagation */
@@ -232,11 +232,21 @@ typedef struct {
     int64_t lds[KGAT_MAX_LAYERS];
 } kgat_grad_tables_t;
 
+/* Optional publication of a step's loss to the host by the kernel that reduces it (what kgat_publish_loss does as a launch of
+ * its own): ring_host_mapped[s % n_slots] = (s << 32) | float bits of the loss, with s = ++serial_dev[0]; the ring lives in
+ * mapped pinned host memory, so loss.item() is a host-side poll that does not wait for the kernels queued behind the loss. */
+typedef struct {
+    uint64_t* serial_dev;
+    uint64_t* ring_host_mapped;
+    int32_t n_slots;
+} kgat_publish_t;
+
 /* loss[0] = -mean(logsigmoid(pos - neg)) + reg * (mean|u|^2/2 + mean|p|^2/2 + mean|n|^2/2);
  * margin: scratch of 2*batch floats: [pos_b - neg_b (saved for the backward)][per-sample l2 term].
  * ids are used as given (no user offset).  loss_sum (may be NULL): loss_sum[0] += loss[0] in the same launch. */
 int kgat_bpr_forward(const kgat_tables_t* tables, const int64_t* users, const int64_t* pos, const int64_t* neg,
-                     int32_t batch, float reg, float* loss, float* loss_sum, float* margin, void* stream);
+                     int32_t batch, float reg, float* loss, float* loss_sum, float* margin, const kgat_publish_t* publish /* may be NULL */,
+                     void* stream);
 /* Scatter-adds d loss / d table rows into grad tables (atomicAdd; tables[l] may be NULL to skip a
  * layer).  g_loss: device scalar (upstream gradient). */
 int kgat_bpr_backward(const kgat_tables_t* tables, const kgat_grad_tables_t* grads, const int64_t* users,
@@ -267,7 +277,7 @@ int kgat_transr_backward(const float* emb, const float* rel_emb, const float* W,
 int kgat_transr_step(const float* emb, const float* rel_emb, const float* W, int32_t d, int32_t k, int32_t n_rel,
                      const int64_t* heads, const int64_t* rels, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch,
                      float reg, float* loss, float* loss_sum, float* margin, int32_t* row_slot, float* g_rows, float* g_rel_emb,
-                     float* g_W, void* stream);
+                     float* g_W, const kgat_publish_t* publish /* may be NULL */, void* stream);
 /* One slot per distinct node of a TransR batch: row_slot (n_nodes int32, -1 = free) gets, for every node among
  * heads / pos_tails / neg_tails, the index in [0, 3*batch) of its first claimant; g_rows (3*batch x d) is zeroed.
  * kgat_adam_apply (row_slot0) consumes the rows and frees the slots. */
@@ -413,7 +423,7 @@ int kgat_adam_rolling_prepare(const int64_t* heads, const int64_t* pos_tails, co
 int kgat_transr_step_claimed(const float* emb, const float* rel_emb, const float* W, int32_t d, int32_t k, const int64_t* heads,
                              const int64_t* rels, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, float reg, float* loss,
                              float* loss_sum, float* margin, const int32_t* row_slot, float* g_rows, float* g_rel_emb, float* g_W,
-                             void* stream);
+                             const kgat_publish_t* publish /* may be NULL */, void* stream);
 int kgat_adam_rolling_apply(const int64_t* heads, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, int32_t d,
                             int32_t* row_slot, const float* g_rows, float* param, float* exp_avg, float* exp_avg_sq, int32_t* row_step,
                             int64_t n_rows, int32_t window, const kgat_adam_tensors_t* dense, int32_t parts, const int64_t* cur_step_dev,

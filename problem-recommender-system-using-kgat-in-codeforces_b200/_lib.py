@@ -13,7 +13,7 @@ from pathlib import Path
 
 KGAT_MAX_LAYERS = 8
 KGAT_MAX_TENSORS = 24
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("KGAT_B200_LIB", _PKG_DIR / "lib" / "libkgat_b200.so"))
@@ -60,6 +60,10 @@ class AdamTensorsT(C.Structure):
     ]
 
 
+class PublishT(C.Structure):
+    _fields_ = [("serial_dev", C.c_void_p), ("ring_host_mapped", C.c_void_p), ("n_slots", C.c_int32)]
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _I32 = C.c_int32
@@ -99,12 +103,12 @@ SIGNATURES: dict[str, tuple] = {
     "kgat_zero_rows_i64": (_I32, [_P, _I64, _I64, _I32, _P, _I64, _P]),
     "kgat_transr_rows_to_dense": (_I32, [_P, _P, _P, _P, _P, _I32, _I32, _P, _I64, _P]),
     "kgat_transr_release_rows": (_I32, [_P, _I64, _I64, _I32, _P, _I64, _P, _P]),
-    "kgat_bpr_forward": (_I32, [C.POINTER(TablesT), _P, _P, _P, _I32, _F, _P, _P, _P, _P]),
+    "kgat_bpr_forward": (_I32, [C.POINTER(TablesT), _P, _P, _P, _I32, _F, _P, _P, _P, C.POINTER(PublishT), _P]),
     "kgat_bpr_backward": (_I32, [C.POINTER(TablesT), C.POINTER(TablesT), _P, _P, _P, _I32, _F, _P, _P, _P]),
     "kgat_transr_forward": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P, _P, _I32, _F, _P, _P, _P]),
     "kgat_transr_backward": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P, _P, _I32, _F, _P, _P, _P, _P, _P, _P, _P]),
     "kgat_transr_claim_rows": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P]),
-    "kgat_transr_step": (_I32, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _I32, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "kgat_transr_step": (_I32, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _I32, _F, _P, _P, _P, _P, _P, _P, _P, C.POINTER(PublishT), _P]),
     "kgat_mha_forward": (_I32, [_P, _I64, _I32, C.POINTER(MhaT), _F, _P, _U64, _U64, _P, _P]),
     "kgat_att_pair_project": (_I32, [_P, _P, _I32, _P, _P, _I64, _P, _P]),
     "kgat_att_edge_scores_kgat": (_I32, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P]),
@@ -125,7 +129,7 @@ SIGNATURES: dict[str, tuple] = {
     "kgat_adam_lazy_flush": (_I32, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P]),
     "kgat_adam_rolling_prepare": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
     "kgat_step_begin_i64": (_I32, [_P, _I64, _I64, _P, _P, _D, _D, _D, _D, _P, _P]),
-    "kgat_transr_step_claimed": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P, _P, _I32, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "kgat_transr_step_claimed": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P, _P, _I32, _F, _P, _P, _P, _P, _P, _P, _P, C.POINTER(PublishT), _P]),
     "kgat_adam_rolling_apply": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, C.POINTER(AdamTensorsT), _I32, _P, _P, _P, _P, _P]),
     "kgat_selftest_adam_arith": (_I32, [_P, _P, _I64, _F, _F, _P, _P]),
     "kgat_fill_f32": (_I32, [_P, _I64, _F, _P]),

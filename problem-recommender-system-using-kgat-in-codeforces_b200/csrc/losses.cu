@@ -8,8 +8,17 @@ namespace kgat {
 namespace {
 
 // loss = mean_b(-logsigmoid(margin_b)) + reg * mean_b(l2_b);   scratch = [margin (B)][l2 (B)]
+// `pub` (optional): the loss is also published to the host -- ring[s % n_slots] = (s << 32) | bits(loss) with s = ++serial, one
+// aligned 8-byte store into mapped pinned memory (what kgat_publish_loss does as a launch of its own)
+struct Publish {
+    unsigned long long* serial_dev;
+    volatile unsigned long long* ring_host;
+    int n_slots;
+};
+
 __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ scratch, int batch, float reg,
-                                                          float* __restrict__ loss, float* __restrict__ loss_sum = nullptr) {
+                                                          float* __restrict__ loss, float* __restrict__ loss_sum = nullptr,
+                                                          Publish pub = Publish{nullptr, nullptr, 0}) {
     __shared__ float sh_a[8], sh_b[8];
     float a = 0.f, b = 0.f;
     for (int i = threadIdx.x; i < batch; i += 256) {
@@ -32,7 +41,19 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restric
         const float l = ta / (float)batch + reg * (tb / (float)batch);
         loss[0] = l;
         if (loss_sum != nullptr) loss_sum[0] += l;
+        if (pub.serial_dev != nullptr) {
+            const unsigned long long sn = pub.serial_dev[0] + 1ull;
+            pub.serial_dev[0] = sn;
+            pub.ring_host[sn % (unsigned long long)pub.n_slots] = (sn << 32) | (unsigned long long)__float_as_uint(l);
+            __threadfence_system();
+        }
     }
+}
+
+inline Publish make_publish(const kgat_publish_t* p) {
+    if (p == nullptr || p->serial_dev == nullptr || p->ring_host_mapped == nullptr || p->n_slots <= 0) return Publish{nullptr, nullptr, 0};
+    return Publish{reinterpret_cast<unsigned long long*>(p->serial_dev), reinterpret_cast<volatile unsigned long long*>(p->ring_host_mapped),
+                   p->n_slots};
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -438,14 +459,14 @@ int kgat_zero_rows_i64(float* T, int64_t n_rows, int64_t ld, int32_t d, const in
 }
 
 int kgat_bpr_forward(const kgat_tables_t* tables, const int64_t* users, const int64_t* pos, const int64_t* neg, int32_t batch,
-                     float reg, float* loss, float* loss_sum, float* margin, void* stream_) {
+                     float reg, float* loss, float* loss_sum, float* margin, const kgat_publish_t* publish, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     Tables T;
     int rc = pack_tables(tables, &T);
     if (rc != KGAT_OK) return rc;
     if (batch <= 0) return KGAT_ERR_INVALID_ARGUMENT;
     bpr_fwd_kernel<<<(batch * 32 + 255) / 256, 256, 0, stream>>>(T, users, pos, neg, batch, margin);
-    loss_reduce_kernel<<<1, 256, 0, stream>>>(margin, batch, reg, loss, loss_sum);
+    loss_reduce_kernel<<<1, 256, 0, stream>>>(margin, batch, reg, loss, loss_sum, make_publish(publish));
     return check_launch();
 }
 
@@ -499,7 +520,8 @@ int kgat_transr_backward(const float* emb, const float* rel_emb, const float* W,
 
 int kgat_transr_step(const float* emb, const float* rel_emb, const float* W, int32_t d, int32_t k, int32_t n_rel, const int64_t* heads,
                      const int64_t* rels, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, float reg, float* loss,
-                     float* loss_sum, float* margin, int32_t* row_slot, float* g_rows, float* g_rel_emb, float* g_W, void* stream_) {
+                     float* loss_sum, float* margin, int32_t* row_slot, float* g_rows, float* g_rel_emb, float* g_W,
+                     const kgat_publish_t* publish, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (batch <= 0 || d <= 0 || (d & 3) || (k & 3) || n_rel <= 0 || !row_slot || !g_rows || !g_rel_emb || !g_W || !loss || !margin)
         return KGAT_ERR_INVALID_ARGUMENT;
@@ -512,7 +534,7 @@ int kgat_transr_step(const float* emb, const float* rel_emb, const float* W, int
     KGAT_TRANSR_DISPATCH((transr_bwd_kernel<DM, KM, true><<<blocks, 128, 0, stream>>>(emb, rel_emb, W, heads, rels, pos_tails, neg_tails,
                                                                                      batch, reg, margin, nullptr, g_rows, g_rel_emb, g_W,
                                                                                      row_slot)));
-    loss_reduce_kernel<<<1, 256, 0, stream>>>(margin, batch, reg, loss, loss_sum);
+    loss_reduce_kernel<<<1, 256, 0, stream>>>(margin, batch, reg, loss, loss_sum, make_publish(publish));
     return check_launch();
 }
 
@@ -521,14 +543,14 @@ int kgat_transr_step(const float* emb, const float* rel_emb, const float* W, int
 int kgat_transr_step_claimed(const float* emb, const float* rel_emb, const float* W, int32_t d, int32_t k, const int64_t* heads,
                              const int64_t* rels, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, float reg, float* loss,
                              float* loss_sum, float* margin, const int32_t* row_slot, float* g_rows, float* g_rel_emb, float* g_W,
-                             void* stream_) {
+                             const kgat_publish_t* publish, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (batch <= 0 || d <= 0 || !row_slot || !g_rows || !g_rel_emb || !g_W || !loss || !margin) return KGAT_ERR_INVALID_ARGUMENT;
     const unsigned blocks = (unsigned)batch;
     KGAT_TRANSR_DISPATCH((transr_bwd_kernel<DM, KM, true><<<blocks, 128, 0, stream>>>(emb, rel_emb, W, heads, rels, pos_tails, neg_tails,
                                                                                      batch, reg, margin, nullptr, g_rows, g_rel_emb, g_W,
                                                                                      row_slot)));
-    loss_reduce_kernel<<<1, 256, 0, stream>>>(margin, batch, reg, loss, loss_sum);
+    loss_reduce_kernel<<<1, 256, 0, stream>>>(margin, batch, reg, loss, loss_sum, make_publish(publish));
     return check_launch();
 }
 

@@ -294,9 +294,16 @@ class GraphedStep:
         # gradient tables, previous-batch ids ...): keep the closures -- and with them those buffers -- alive as long as the graph
         self._bodies = (body_fwd, body_bwd)
 
+        # the loss kernel of the forward body publishes (serial, loss) itself when the body passes ``publish=st.publish`` on and
+        # reports so (``st.published = True``); otherwise a one-thread launch does it
+        self.publish = ops.publish_args(self.pub_serial, self.ring)
+        self.published = False
+
         def whole(st):
+            st.published = False
             body_fwd(st)
-            ops.publish_loss(st.loss, st.pub_serial, st.ring)
+            if not st.published:
+                ops.publish_loss(st.loss, st.pub_serial, st.ring)
             return body_bwd(st)
 
         side = torch.cuda.Stream()

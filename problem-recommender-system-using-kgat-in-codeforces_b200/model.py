@@ -339,7 +339,8 @@ class KGAT(nn.Module):
                     if frontier is not None:
                         frontier.build([st.ids.view(-1)])
                     st.prop = propagate_forward(graph, params[0].detach(), layers, drop, save=True, frontier=frontier)
-                    ops.bpr_forward(st.prop.tables, st.ids[0], st.ids[1], st.ids[2], reg, st.loss, st.scratch)
+                    ops.bpr_forward(st.prop.tables, st.ids[0], st.ids[1], st.ids[2], reg, st.loss, st.scratch, publish=st.publish)
+                    st.published = True
 
                 def body_bwd(st):
                     n_tab = len(st.prop.tables)
@@ -444,12 +445,13 @@ class KGAT(nn.Module):
                     ops.transr_release_rows(g_dense, prev_ids.view(-1), row_slot)  # the previous batch's rows and slot claims
                     if d is None:
                         ops.transr_step(emb, rel, w, st.ids[0], st.ids[1], st.ids[2], st.ids[3], reg, st.loss, None, st.scratch, row_slot,
-                                        g_rows, g_rel, g_w)
+                                        g_rows, g_rel, g_w, publish=st.publish)
                     else:  # rows this batch reads first take the zero-gradient updates they were spared (csrc/adam.cu, rolling window)
                         ops.adam_rolling_prepare(st.ids[0], st.ids[2], st.ids[3], row_slot, g_rows, g_rel, g_w, emb, exp_avg, exp_avg_sq,
                                                  d.row_step, d.step_dev, d.s0, d.table, d.hyper)
                         ops.transr_step_claimed(emb, rel, w, st.ids[0], st.ids[1], st.ids[2], st.ids[3], reg, st.loss, None, st.scratch,
-                                                row_slot, g_rows, g_rel, g_w)
+                                                row_slot, g_rows, g_rel, g_w, publish=st.publish)
+                    st.published = True
 
                 def body_bwd(st):
                     ops.transr_rows_to_dense(g_rows, row_slot, st.ids[0], st.ids[2], st.ids[3], g_dense)

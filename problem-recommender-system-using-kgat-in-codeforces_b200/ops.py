@@ -425,7 +425,7 @@ def zero_rows_(table: torch.Tensor, ids: torch.Tensor):
 
 
 @_timed("bpr_fwd")
-def bpr_forward(tables, users, pos, neg, reg, loss, scratch, loss_sum=None):
+def bpr_forward(tables, users, pos, neg, reg, loss, scratch, loss_sum=None, publish=None):
     lib = _lib.load()
     b = users.numel()
     if scratch.numel() < 2 * b:
@@ -433,7 +433,8 @@ def bpr_forward(tables, users, pos, neg, reg, loss, scratch, loss_sum=None):
     t = _tables(tables)
     check(
         lib.kgat_bpr_forward(C.byref(t), _ptr(users, i64, "users"), _ptr(pos, i64, "pos"), _ptr(neg, i64, "neg"), b, float(reg),
-                             _ptr(loss, f32), _ptr(loss_sum, f32) if loss_sum is not None else None, _ptr(scratch, f32), _stream()),
+                             _ptr(loss, f32), _ptr(loss_sum, f32) if loss_sum is not None else None, _ptr(scratch, f32),
+                             C.byref(publish) if publish is not None else None, _stream()),
         "bpr_forward",
     )
 
@@ -479,7 +480,7 @@ def transr_claim_rows(heads, pos_t, neg_t, d: int, row_slot, g_rows):
 
 
 @_timed("transr_step")
-def transr_step(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, loss, loss_sum, scratch, row_slot, g_rows, g_rel, g_W):
+def transr_step(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, loss, loss_sum, scratch, row_slot, g_rows, g_rel, g_W, publish=None):
     """Claim compact gradient rows + zero the gradient buffers, TransR forward and backward in one pass, loss value
     (added to ``loss_sum`` when given): the KG half-step of the epoch engine in three launches."""
     lib = _lib.load()
@@ -488,7 +489,8 @@ def transr_step(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, loss, loss_sum,
     check(lib.kgat_transr_step(_ptr(emb, f32), _ptr(rel_emb, f32), _ptr(W, f32), emb.shape[1], rel_emb.shape[1], rel_emb.shape[0],
                                _ptr(heads, i64), _ptr(rels, i64), _ptr(pos_t, i64), _ptr(neg_t, i64), heads.numel(), float(reg),
                                _ptr(loss, f32), _ptr(loss_sum, f32) if loss_sum is not None else None, _ptr(scratch, f32),
-                               _ptr(row_slot, i32), _ptr(g_rows, f32), _ptr(g_rel, f32), _ptr(g_W, f32), _stream()), "transr_step")
+                               _ptr(row_slot, i32), _ptr(g_rows, f32), _ptr(g_rel, f32), _ptr(g_W, f32),
+                               C.byref(publish) if publish is not None else None, _stream()), "transr_step")
 
 
 def transr_rows_to_dense(g_rows, row_slot, heads, pos_t, neg_t, dense):
@@ -723,7 +725,7 @@ def adam_rolling_prepare(heads, pos_t, neg_t, row_slot, g_rows, zero_a, zero_b, 
 
 
 @_timed("transr_step_claimed")
-def transr_step_claimed(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, loss, loss_sum, scratch, row_slot, g_rows, g_rel, g_W):
+def transr_step_claimed(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, loss, loss_sum, scratch, row_slot, g_rows, g_rel, g_W, publish=None):
     """``transr_step`` for rows claimed (and buffers zeroed) by ``adam_rolling_prepare``."""
     lib = _lib.load()
     if g_rows.numel() < 3 * heads.numel() * emb.shape[1] or scratch.numel() < 2 * heads.numel():
@@ -731,7 +733,8 @@ def transr_step_claimed(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, loss, l
     check(lib.kgat_transr_step_claimed(_ptr(emb, f32), _ptr(rel_emb, f32), _ptr(W, f32), emb.shape[1], rel_emb.shape[1], _ptr(heads, i64),
                                        _ptr(rels, i64), _ptr(pos_t, i64), _ptr(neg_t, i64), heads.numel(), float(reg), _ptr(loss, f32),
                                        _ptr(loss_sum, f32) if loss_sum is not None else None, _ptr(scratch, f32), _ptr(row_slot, i32),
-                                       _ptr(g_rows, f32), _ptr(g_rel, f32), _ptr(g_W, f32), _stream()), "transr_step_claimed")
+                                       _ptr(g_rows, f32), _ptr(g_rel, f32), _ptr(g_W, f32), C.byref(publish) if publish is not None else None,
+                                       _stream()), "transr_step_claimed")
 
 
 @_timed("adam_rolling_apply")
@@ -797,6 +800,16 @@ def adam_lazy_flush(param, exp_avg, exp_avg_sq, row_step, cur_step_dev, s0, tabl
     check(lib.kgat_adam_lazy_flush(_ptr(param, f32), _ptr(exp_avg, f32), _ptr(exp_avg_sq, f32), _ptr(row_step, i32), param.shape[0],
                                    param.shape[1], _ptr(cur_step_dev, i64), _ptr(s0, i64), _ptr(table, f32), _ptr(hyper, f32), _stream()),
           "adam_lazy_flush")
+
+
+def publish_args(serial_dev: torch.Tensor, ring_pinned: torch.Tensor):
+    """kgat_publish_t for the ``publish=`` argument of bpr_forward / transr_step / transr_step_claimed (keep it alive with the
+    tensors: the loss kernel itself then writes (serial, loss) into the pinned ring, no launch of its own)."""
+    if ring_pinned.is_cuda or not ring_pinned.is_pinned() or ring_pinned.dtype != i64:
+        raise KgatLibraryError("publish_args: the ring must be a pinned int64 host tensor")
+    p = _lib.PublishT()
+    p.serial_dev, p.ring_host_mapped, p.n_slots = _ptr(serial_dev, i64), ring_pinned.data_ptr(), ring_pinned.numel()
+    return p
 
 
 def publish_loss(loss: torch.Tensor, serial_dev: torch.Tensor, ring_pinned: torch.Tensor):
