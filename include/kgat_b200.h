@@ -32,7 +32,7 @@ extern "C" {
 #define KGAT_ERR_UNSUPPORTED (-3)
 #define KGAT_ERR_WORKSPACE (-4)
 
-#define KGAT_ABI_VERSION 8
+#define KGAT_ABI_VERSION 9
 #define KGAT_MAX_LAYERS 8   /* embedding table + up to 7 propagation layers */
 #define KGAT_MAX_TENSORS 24 /* tensors per multi-tensor Adam launch */
 #define KGAT_MAX_PEERS 31   /* other ranks of a row-sharded propagation */
@@ -211,7 +211,9 @@ int kgat_zero_rows_i64(float* T, int64_t n_rows, int64_t ld, int32_t d, const in
  * ids -- what autograd hands out as embedding.weight.grad (model.py:204-261), zero outside those rows, kept valid by
  * kgat_transr_release_rows(previous batch's ids) = clear those rows and free their row_slot claims. */
 int kgat_transr_rows_to_dense(const float* g_rows, const int32_t* row_slot, const int64_t* heads, const int64_t* pos_tails,
-                              const int64_t* neg_tails, int32_t batch, int32_t d, float* dense, int64_t ld, void* stream);
+                              const int64_t* neg_tails, int32_t batch, int32_t d, float* dense, int64_t ld, int64_t* keep_heads,
+                              int64_t* keep_pos_tails, int64_t* keep_neg_tails /* optional: copies of the ids, all three or none */,
+                              void* stream);
 int kgat_transr_release_rows(float* dense, int64_t n_rows, int64_t ld, int32_t d, const int64_t* ids64, int64_t n_ids,
                              int32_t* row_slot, void* stream);
 
@@ -415,11 +417,13 @@ int kgat_adam_lazy_flush(float* param, float* exp_avg, float* exp_avg_sq, int32_
  * row_step / s0_dev / table / hyper_dev as for the lazy scheme above.  `advanced` = 1 when the step counter was already
  * advanced for this step (kgat_step_begin_i64), so the steps done are one fewer.  `parts`: bit 0 = claimed rows + dense tensors,
  * bit 1 = slice replay; the two parts touch disjoint rows (ownership through atomicMax on row_step) and may run as concurrent
- * launches on two streams once the prepare launch has finished. */
+ * launches on two streams once the prepare launch has finished.  dense (may be NULL) + prev_*: the API path's dense view of
+ * the embedding gradient (kgat_transr_rows_to_dense) still holds the previous batch's rows; the prepare launch clears them. */
 int kgat_adam_rolling_prepare(const int64_t* heads, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, int32_t d,
                               int32_t* row_slot, float* g_rows, float* zero_a, int64_t n_a, float* zero_b, int64_t n_b, float* param,
                               float* exp_avg, float* exp_avg_sq, int32_t* row_step, const int64_t* cur_step_dev, int32_t advanced,
-                              const int64_t* s0_dev, const float* table, const float* hyper_dev, void* stream);
+                              const int64_t* s0_dev, const float* table, const float* hyper_dev, const int64_t* prev_heads,
+                              const int64_t* prev_pos_tails, const int64_t* prev_neg_tails, float* dense, int64_t ld_dense, void* stream);
 int kgat_transr_step_claimed(const float* emb, const float* rel_emb, const float* W, int32_t d, int32_t k, const int64_t* heads,
                              const int64_t* rels, const int64_t* pos_tails, const int64_t* neg_tails, int32_t batch, float reg, float* loss,
                              float* loss_sum, float* margin, const int32_t* row_slot, float* g_rows, float* g_rel_emb, float* g_W,

@@ -404,11 +404,17 @@ __global__ void zero_rows_i64_kernel(float* __restrict__ T, int64_t ld, int d4, 
 // embedding gradient autograd would hand out, restricted to the <= 3B rows that are not zero
 __global__ void transr_rows_to_dense_kernel(const float4* __restrict__ g_rows, const int32_t* __restrict__ row_slot,
                                             const int64_t* __restrict__ heads, const int64_t* __restrict__ pt, const int64_t* __restrict__ nt,
-                                            int batch, int d4, float* __restrict__ dense, int64_t ld) {
+                                            int batch, int d4, float* __restrict__ dense, int64_t ld, int64_t* __restrict__ keep_h,
+                                            int64_t* __restrict__ keep_pt, int64_t* __restrict__ keep_nt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 3 * batch * d4) return;
     const int e = i / d4, q = i % d4;
     const int64_t id = e < batch ? heads[e] : (e < 2 * batch ? pt[e - batch] : nt[e - 2 * batch]);
+    if (keep_h != nullptr && q == 0) {  // remember whose rows the dense view now holds (cleared before the next batch's rows go in)
+        if (e < batch) keep_h[e] = id;
+        else if (e < 2 * batch) keep_pt[e - batch] = id;
+        else keep_nt[e - 2 * batch] = id;
+    }
     if (row_slot[id] != e) return;
     reinterpret_cast<float4*>(dense + id * ld)[q] = g_rows[(int64_t)e * d4 + q];
 }
@@ -432,12 +438,15 @@ using namespace kgat;
 extern "C" {
 
 int kgat_transr_rows_to_dense(const float* g_rows, const int32_t* row_slot, const int64_t* heads, const int64_t* pos_tails,
-                              const int64_t* neg_tails, int32_t batch, int32_t d, float* dense, int64_t ld, void* stream) {
+                              const int64_t* neg_tails, int32_t batch, int32_t d, float* dense, int64_t ld, int64_t* keep_heads,
+                              int64_t* keep_pos_tails, int64_t* keep_neg_tails, void* stream) {
+    if ((keep_heads != nullptr) != (keep_pos_tails != nullptr) || (keep_heads != nullptr) != (keep_neg_tails != nullptr)) return KGAT_ERR_INVALID_ARGUMENT;
     if (!g_rows || !row_slot || !heads || !pos_tails || !neg_tails || !dense || batch <= 0 || d <= 0 || (d & 3) || (ld & 3))
         return KGAT_ERR_INVALID_ARGUMENT;
     const int total = 3 * batch * (d / 4);
     transr_rows_to_dense_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(g_rows), row_slot, heads,
-                                                                                    pos_tails, neg_tails, batch, d / 4, dense, ld);
+                                                                                    pos_tails, neg_tails, batch, d / 4, dense, ld, keep_heads,
+                                                                                    keep_pos_tails, keep_neg_tails);
     return check_launch();
 }
 

@@ -288,6 +288,7 @@ class GraphedStep:
         self.adam_grads = None  # optional: the gradient tensors the fused optimiser replay reads instead of `grads` ...
         self.adam_row_slot0 = None  # ... with compact rows for the first parameter (ops.adam_apply row_slot0)
         self.adam_rolling = None  # ... or the rolling-window update of optim.DeferredRows: dict(deferred, ids, row_slot)
+        self.pre_submit = None  # optional host-side check run before every launch (set by the model)
         self._adam = {}
         self._lib = _lib.load()
         # the captured graph bakes in the addresses of every buffer the bodies' closures own (needed-row frontier, static
@@ -336,6 +337,8 @@ class GraphedStep:
                 p.grad = pg.clone()  # an un-applied gradient still aliases our buffer (accumulation): keep its value
         # consecutive int64 rows of one [n_ids, B] block (device, or host: pinned or not, cudaMemcpyAsync stages pageable memory
         # before it returns) travel in the same C call as the launch
+        if self.pre_submit is not None:
+            self.pre_submit(self)
         first = ids[0]
         base = first.data_ptr()
         stride = self._row_bytes

@@ -300,8 +300,9 @@ class KGAT(nn.Module):
         if step is None:
             if len(self._api_steps) > 8:
                 self._api_steps.clear()
-            body_fwd, body_bwd = make_bodies()
-            step = self._api_steps[key] = GraphedStep(params, batch, n_ids, body_fwd, body_bwd)
+            bodies = make_bodies()
+            step = self._api_steps[key] = GraphedStep(params, batch, n_ids, bodies[0], bodies[1])
+            step.pre_submit = bodies[2] if len(bodies) > 2 else None
         self._last_step[kind] = step
         return step
 
@@ -441,26 +442,41 @@ class KGAT(nn.Module):
                 if d is not None:
                     exp_avg, exp_avg_sq = d.state_tensors()
 
+                keep = (prev_ids[0], prev_ids[2], prev_ids[3])  # whose rows the dense view holds (row 1, the relations, stays unused)
+
                 def body_fwd(st):
-                    ops.transr_release_rows(g_dense, prev_ids.view(-1), row_slot)  # the previous batch's rows and slot claims
                     if d is None:
+                        ops.transr_release_rows(g_dense, prev_ids.view(-1), row_slot)  # the previous batch's rows and slot claims
                         ops.transr_step(emb, rel, w, st.ids[0], st.ids[1], st.ids[2], st.ids[3], reg, st.loss, None, st.scratch, row_slot,
                                         g_rows, g_rel, g_w, publish=st.publish)
-                    else:  # rows this batch reads first take the zero-gradient updates they were spared (csrc/adam.cu, rolling window)
+                    else:
+                        # rows this batch reads first take the zero-gradient updates they were spared (csrc/adam.cu, rolling window); the
+                        # same launch claims the compact gradient rows, zeroes the gradient buffers and clears the previous batch's rows
+                        # of the dense view.  (The previous batch's slot claims were consumed by the rolling update; ``pre_submit``
+                        # below covers the steps where it did not run.)
                         ops.adam_rolling_prepare(st.ids[0], st.ids[2], st.ids[3], row_slot, g_rows, g_rel, g_w, emb, exp_avg, exp_avg_sq,
-                                                 d.row_step, d.step_dev, d.s0, d.table, d.hyper)
+                                                 d.row_step, d.step_dev, d.s0, d.table, d.hyper, prev_ids=keep, dense=g_dense)
                         ops.transr_step_claimed(emb, rel, w, st.ids[0], st.ids[1], st.ids[2], st.ids[3], reg, st.loss, None, st.scratch,
                                                 row_slot, g_rows, g_rel, g_w, publish=st.publish)
                     st.published = True
 
                 def body_bwd(st):
-                    ops.transr_rows_to_dense(g_rows, row_slot, st.ids[0], st.ids[2], st.ids[3], g_dense)
-                    prev_ids.copy_(st.ids)
-                    st.adam_grads, st.adam_row_slot0 = [g_rows, g_rel, g_w], row_slot
-                    if d is not None:
+                    if d is None:
+                        ops.transr_rows_to_dense(g_rows, row_slot, st.ids[0], st.ids[2], st.ids[3], g_dense)
+                        prev_ids.copy_(st.ids)
+                    else:
+                        ops.transr_rows_to_dense(g_rows, row_slot, st.ids[0], st.ids[2], st.ids[3], g_dense, keep_ids=keep)
                         st.adam_rolling = dict(deferred=d, ids=(st.ids[0], st.ids[2], st.ids[3]), row_slot=row_slot)
+                    st.adam_grads, st.adam_row_slot0 = [g_rows, g_rel, g_w], row_slot
                     return [g_dense, g_rel, g_w]
-                return body_fwd, body_bwd
+
+                def pre_submit(st):
+                    # slot claims left behind by a step the rolling update never consumed (first launch after the capture warm-up,
+                    # backward without update, update through the generic optimiser path): release them outside the graph
+                    if st.updated != st.serial or st.serial == 0:
+                        ops.transr_release_rows(g_dense, prev_ids.view(-1), row_slot)
+
+                return (body_fwd, body_bwd, pre_submit) if d is not None else (body_fwd, body_bwd)
 
             key = None if deferred is None else (id(deferred), deferred.state_tensors()[0].data_ptr())
             if deferred is not None:

@@ -493,11 +493,14 @@ def transr_step(emb, rel_emb, W, heads, rels, pos_t, neg_t, reg, loss, loss_sum,
                                C.byref(publish) if publish is not None else None, _stream()), "transr_step")
 
 
-def transr_rows_to_dense(g_rows, row_slot, heads, pos_t, neg_t, dense):
-    """dense[id] = g_rows[row_slot[id]] for the batch's ids (the dense ``embedding.weight.grad`` of a TransR step)."""
+def transr_rows_to_dense(g_rows, row_slot, heads, pos_t, neg_t, dense, keep_ids=None):
+    """dense[id] = g_rows[row_slot[id]] for the batch's ids (the dense ``embedding.weight.grad`` of a TransR step).
+    ``keep_ids``: three int64 [B] tensors that receive copies of heads / pos_t / neg_t in the same launch."""
     lib = _lib.load()
     check(lib.kgat_transr_rows_to_dense(_ptr(g_rows, f32), _ptr(row_slot, i32), _ptr(heads, i64), _ptr(pos_t, i64), _ptr(neg_t, i64),
-                                        heads.numel(), dense.shape[1], _ptr(dense, f32, "dense", True), dense.stride(0), _stream()),
+                                        heads.numel(), dense.shape[1], _ptr(dense, f32, "dense", True), dense.stride(0),
+                                        *((_ptr(keep_ids[0], i64), _ptr(keep_ids[1], i64), _ptr(keep_ids[2], i64)) if keep_ids is not None
+                                          else (None, None, None)), _stream()),
           "transr_rows_to_dense")
 
 
@@ -711,7 +714,7 @@ def adam_apply(params, grads, exp_avgs, exp_avg_sqs, hyper: torch.Tensor, peer_p
 
 @_timed("adam_rolling_prepare")
 def adam_rolling_prepare(heads, pos_t, neg_t, row_slot, g_rows, zero_a, zero_b, param, exp_avg, exp_avg_sq, row_step, cur_step_dev, s0, table, hyper,
-                         advanced: bool = False):
+                         advanced: bool = False, prev_ids=None, dense=None):
     """Rolling-window KG Adam, before the forward: claim compact gradient rows, zero ``g_rows`` / ``zero_a`` / ``zero_b``, bring
     the batch rows of ``param`` up to the steps done so far."""
     lib = _lib.load()
@@ -721,7 +724,10 @@ def adam_rolling_prepare(heads, pos_t, neg_t, row_slot, g_rows, zero_a, zero_b, 
                                         _ptr(g_rows, f32), _ptr(zero_a, f32) if zero_a is not None else None, zero_a.numel() if zero_a is not None else 0,
                                         _ptr(zero_b, f32) if zero_b is not None else None, zero_b.numel() if zero_b is not None else 0,
                                         _ptr(param, f32), _ptr(exp_avg, f32), _ptr(exp_avg_sq, f32), _ptr(row_step, i32), _ptr(cur_step_dev, i64),
-                                        int(bool(advanced)), _ptr(s0, i64), _ptr(table, f32), _ptr(hyper, f32), _stream()), "adam_rolling_prepare")
+                                        int(bool(advanced)), _ptr(s0, i64), _ptr(table, f32), _ptr(hyper, f32),
+                                        *((_ptr(prev_ids[0], i64), _ptr(prev_ids[1], i64), _ptr(prev_ids[2], i64), _ptr(dense, f32, "dense", True),
+                                           dense.stride(0)) if dense is not None else (None, None, None, None, 0)),
+                                        _stream()), "adam_rolling_prepare")
 
 
 @_timed("transr_step_claimed")
