@@ -143,14 +143,14 @@ class FusedAdam(torch.optim.Optimizer):
         """Captured ``adam_advance + adam_apply`` over exactly ``(ps, grads)`` (static gradient buffers of a graphed step),
         or None when it cannot be used yet: first sighting (the generic path creates the state and warms the kernels up),
         parameters with different step counts, graphs disabled, or some other parameter of the group holds a gradient."""
-        if not self.use_graphs or torch.cuda.is_current_stream_capturing():
+        if not self.use_graphs or torch._C._cuda_isCurrentStreamCapturing():
             return None
         group = self.param_groups[0]
         n_with = 0
         for p in group["params"]:
             if p.grad is not None:
                 n_with += 1
-        if n_with != len(ps) or len(self.param_groups) != 1:
+        if n_with != len(ps) or len(self.param_groups) != 1:  # (the caller has checked that every p in ps holds its gradient)
             return None
         beta1, beta2 = group["betas"]
         if grads_key is None:
