@@ -598,7 +598,10 @@ def main():
                 "algorithmic_bytes_per_launch": abytes,
                 "model": "B_min (every distinct byte once, SURVEY.md 8d) over the rows / edges the pruned step touches"}
 
-    roofline = roof(top)
+    # `roofline` follows the attentive SpMM (the HBM / L2 gather kernel north_star's 60 % target is about, and the kernel round 1's
+    # verdict named); the bi-interaction kernels are tensor-pipe / latency bound and are listed in roofline_propagation_kernels
+    roofline = roof(top_spmm)
+    roofline["largest_propagation_kernel"] = top
     roofline_all = {k: {kk: vv for kk, vv in roof(k).items() if kk in ("avg_us", "achieved", "frac", "algorithmic_bytes_per_launch")} for k in prop}
     # the same kernel against what actually bounds it while the 41 MB table sits in the L2: the L2 -> SM gather fabric
     l2 = l2_gather_peak()
