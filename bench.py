@@ -433,14 +433,20 @@ def c5_scaled_block(dev, peak):
     x5 = e0
     y5 = torch.empty_like(x5)
     t_spmm = time_cuda(lambda: g5.matmul(x5, out=y5), 5)
+    tfile = ROOT / "profiles" / "ncu_traffic.json"
+    c5_traffic = json.loads(tfile.read_text()).get("spmm_d128_c5_scaled") if tfile.exists() else None
     t_step = time_cuda(step, 3, warm=1)
     b_gather = 8.0 * g5.nnz + 16.0 * g5.plan.n_tasks + 4.0 * g5.nnz * d5 + 4.0 * n5 * d5
     out = {"nodes": n5, "nnz": g5.nnz, "dims": dims, "table_bytes": 4.0 * n5 * d5,
            "propagation_step_ms": t_step * 1e3, "propagated_edges_per_s": g5.nnz * 4 * 2 / t_step,
            "spmm_d128": {"ms": t_spmm * 1e3, "algorithmic_bytes": b_gather, "achieved": b_gather / t_spmm / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": b_gather / t_spmm / 1e9 / peak, "edges_per_s": g5.nnz / t_spmm,
+                         # what the launch really moves through HBM (ncu dram__bytes_read + write, profiles/r2_c5_spmm_d128_ncu.csv:
+                         # 14.81 + 1.12 GB, L2 hit rate 21 %) over the time measured here
+                         "traffic": c5_traffic, "achieved_by_traffic": (c5_traffic / t_spmm / 1e9) if c5_traffic else None,
+                         "frac_by_traffic": (c5_traffic / t_spmm / 1e9 / peak) if c5_traffic else None,
                          "model": "B_gather (SURVEY.md 8d): the table is 9x the L2, one 512 B neighbour row per edge is compulsory HBM traffic; "
-                                  "Zipf hubs still hit the L2, so the figure can exceed the copy peak"},
+                                  "Zipf hubs still hit the L2, so the figure can exceed the copy peak; frac_by_traffic uses the DRAM bytes ncu counts"},
            "what": "full (unpruned) 4-layer propagation forward + backward with message dropout, one GPU; the sharded run is in the N > 1 lines"}
     del g5, e0, layers, x5, y5
     torch.cuda.empty_cache()
