@@ -354,7 +354,7 @@ static int spmm_plain_ctas() {
 // loads in flight per lane for d = 64 (KGAT_SPMM_U = 4 | 8; A/B switch for the profiling runs).  Measured on captured CF steps
 // (tools/prof_cf.py, same box): depth 8 everywhere 647 us, depth 8 for the edge-masked instance only 658 us, depth 4 everywhere
 // 663 us.  (Per-kernel eager timings suggested the opposite for the plain forward instance; the captured step is what counts.)
-static int spmm_unroll64(bool /*edge_masked*/) {
+static int spmm_unroll64() {
     static int u = 0;
     if (u == 0) {
         const char* e = getenv("KGAT_SPMM_U");
@@ -395,7 +395,7 @@ static int spmm_launch(const int32_t* tasks, int64_t n_tasks, int32_t* heavy_row
         case 16: KGAT_SPMM_LAUNCH(16, 2); break;
         case 32: KGAT_SPMM_LAUNCH(32, 4); break;
         case 64:
-            if (spmm_unroll64(edge_mask != nullptr) == 8) KGAT_SPMM_LAUNCH(64, 8);
+            if (spmm_unroll64() == 8) KGAT_SPMM_LAUNCH(64, 8);
             else KGAT_SPMM_LAUNCH(64, 4);
             break;
         case 128: KGAT_SPMM_LAUNCH(128, 4); break;
@@ -474,7 +474,7 @@ extern "C" int kgat_spmm_csr_rows(const int32_t* tasks, int64_t n_tasks, int64_t
         case 16: KGAT_ROWS_LAUNCH(16, 2); break;
         case 32: KGAT_ROWS_LAUNCH(32, 4); break;
         case 64:
-            if (spmm_unroll64(em) == 8) KGAT_ROWS_LAUNCH(64, 8);
+            if (spmm_unroll64() == 8) KGAT_ROWS_LAUNCH(64, 8);
             else KGAT_ROWS_LAUNCH(64, 4);
             break;
         default: KGAT_ROWS_LAUNCH(128, 4); break;
