@@ -21,6 +21,36 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_balanced_ranges_cover_the_nodes_and_balance_the_cost(world):
+    """Host logic of the range-sharded engine (sharded_pruned.balanced_ranges): contiguous, 32-aligned node ranges that cover
+    [0, N) exactly once and carry about 1/world of the cost model each, on a degree profile shaped like the CKG's (many short
+    user rows first, then heavy item rows, then entity rows)."""
+    from kgat_b200.sharded_pruned import balanced_ranges
+
+    rng = np.random.default_rng(world)
+    lens = np.concatenate([rng.integers(1, 30, 7000), rng.integers(50, 3000, 2500), rng.integers(1, 400, 9000)])
+    t_lens = rng.permutation(lens)
+    row_ptr, t_ptr = np.concatenate([[0], np.cumsum(lens)]), np.concatenate([[0], np.cumsum(t_lens)])
+    n = lens.shape[0]
+    r = balanced_ranges(row_ptr, t_ptr, world)
+    assert len(r) == world and r[0][0] == 0 and r[-1][1] == n
+    for (lo, hi), (lo2, _) in zip(r, r[1:]):
+        assert hi == lo2
+    for lo, hi in r:
+        assert lo % 32 == 0 and hi > lo
+    row_cost = 48.0 + 64.0 * (world - 1)
+    cost = lens + t_lens + row_cost
+    shares = np.array([cost[lo:hi].sum() for lo, hi in r]) / cost.sum()
+    assert abs(shares.sum() - 1.0) < 1e-12
+    # a cut moves by at most 16 rows from the ideal one (32-alignment): the heaviest rows bound the imbalance
+    slack = 2 * 32 * cost.max() / cost.sum()
+    assert np.abs(shares - 1.0 / world).max() <= slack + 1e-12, (shares, slack)
+    # degenerate input: fewer 32-row blocks than ranks still yields valid, ordered ranges
+    tiny = balanced_ranges(np.arange(0, 41), np.arange(0, 41), 2)
+    assert tiny[0][0] == 0 and tiny[-1][1] == 40 and tiny[0][1] == tiny[1][0]
+
+
 def test_cyclic_partition_index_math():
     from kgat_b200.sharding import CyclicPartition, shard_csr
 
