@@ -175,6 +175,57 @@ def test_entity_table_settles_before_anyone_looks(golden_tiny):
     del m.__dict__["_kg_optimizer"]
 
 
+def test_kg_fast_path_closure_falls_back_when_anything_changed(golden_tiny):
+    """KGAT._make_kg_fast holds the decisions of a KG phase and re-submits the same captured step; it must hand control back
+    (return None) as soon as anything those decisions depended on has changed.  Host logic only: the step is a stand-in, and
+    every case below is decided before the closure would touch CUDA."""
+    g = golden_tiny
+    m = KGAT(KGATArgs(user_num=int(g["user_num"]), entity_num=int(g["entity_num"]), relation_num=int(g["relation_num"]), attentive_matrix=g.att_coo()))
+    m.train()
+
+    class Step:
+        _batch = 8
+        submitted = 0
+
+        def submit(self, ids):
+            Step.submitted += 1
+            return "loss"
+
+    params = [m._emb_raw(), m._relation_embedding.weight, m._trans_matrix]
+    m.kg_deferred_adam = False
+    fast = m._make_kg_fast(Step(), params, None, None)
+    ids = [torch.zeros(8, dtype=torch.int64) for _ in range(4)]
+
+    def none_after(change, undo):
+        change()
+        try:
+            assert fast(*ids) is None
+        finally:
+            undo()
+
+    none_after(lambda: setattr(m, "api_graphs", False), lambda: setattr(m, "api_graphs", True))
+    none_after(lambda: m.eval(), lambda: m.train())
+    none_after(lambda: setattr(m, "kg_deferred_adam", True), lambda: setattr(m, "kg_deferred_adam", False))
+    none_after(lambda: setattr(m, "kg_window", 8), lambda: setattr(m, "kg_window", 16))
+    none_after(lambda: m._trans_matrix.requires_grad_(False), lambda: m._trans_matrix.requires_grad_(True))
+    old = m._relation_embedding._parameters["weight"]
+    none_after(lambda: m._relation_embedding._parameters.__setitem__("weight", torch.nn.Parameter(old.detach().clone())),
+               lambda: m._relation_embedding._parameters.__setitem__("weight", old))
+    keep = m._trans_matrix.data
+    none_after(lambda: setattr(m._trans_matrix, "data", keep.clone()), lambda: setattr(m._trans_matrix, "data", keep))
+    m.__dict__["_kg_optimizer"] = object()  # an optimiser appeared: deferral may now be possible, re-decide
+    try:
+        assert fast(*ids) is None
+    finally:
+        del m.__dict__["_kg_optimizer"]
+    with torch.no_grad():
+        assert fast(*ids) is None
+    assert fast(ids[0], ids[1].to(torch.int32), ids[2], ids[3]) is None  # not int64
+    assert fast(ids[0], ids[1], ids[2], torch.zeros(9, dtype=torch.int64)) is None  # another batch size
+    assert fast(ids[0], torch.zeros(16, dtype=torch.int64)[::2], ids[2], ids[3]) is None  # not contiguous
+    assert Step.submitted == 0
+
+
 def test_no_silent_cpu_path(golden_tiny):
     g = golden_tiny
     m = KGAT(KGATArgs(user_num=int(g["user_num"]), entity_num=int(g["entity_num"]), relation_num=int(g["relation_num"]), attentive_matrix=g.att_coo()))
