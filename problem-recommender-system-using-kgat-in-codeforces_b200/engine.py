@@ -122,15 +122,12 @@ class TrainEngine:
         # node, csrc/losses.cu: transr_claim_rows) instead of a zero-filled N x d table that Adam would re-read
         self.kg_row_slot = torch.full((emb.shape[0],), -1, dtype=torch.int32, device=dev)
         self.kg_grad_rows = torch.zeros(3 * kg_batch, emb.shape[1], dtype=f32, device=dev)
-        # Opt-in: lazy exact Adam for the embedding table in the KG phase (see csrc/adam.cu).  Bit-identical to the
-        # dense sweep but MEASURED SLOWER at the C3 shape (12.5 s vs 4.4 s per epoch): every row-step must still
-        # be replayed once, and the replay (IEEE sqrt + division per element-step, serial per row) is
-        # latency-bound, whereas the dense sweep streams at 81-91 % of HBM peak.  Kept as a documented negative
-        # result and for graphs where only a vanishing fraction of the rows is ever touched.
-        # KG-phase Adam over the embedding table (all three are bit-identical, tested):
-        #   "rolling" (default)  bounded deferral: a rotating 1/kg_window slice of the table is replayed per step (csrc/adam.cu)
-        #   "dense"              the per-step 245 MB sweep (what torch.optim.Adam does)
-        #   "lazy"               unbounded deferral (the negative result above)
+        # KG-phase Adam over the embedding table (csrc/adam.cu; all three are bit-identical, tested):
+        #   "rolling" (default)  bounded deferral: the batch rows and a rotating 1/kg_window slice of the table are brought up to date
+        #                        per step, the zero-gradient updates replayed in registers (KG step 58 -> 36 us at the C3 shape)
+        #   "dense"              the per-step 245 MB sweep over table + moments (what torch.optim.Adam does; 0.85-0.95 of HBM peak)
+        #   "lazy"               unbounded deferral, a documented negative result (12.5 s vs 4.4 s per epoch when it was measured):
+        #                        a row idle for g steps replays g dependent (sqrt, divide) updates inside the step that reads it
         if kg_adam is None:
             kg_adam = "lazy" if lazy_kg_adam else os.environ.get("KGAT_KG_ADAM", "rolling")
         if kg_adam not in ("rolling", "dense", "lazy"):
